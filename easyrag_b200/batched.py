@@ -1,0 +1,237 @@
+"""Batched tensor API over the C ABI: the throughput path beside the drop-in retrievers.
+
+``NodeWithScore`` lists cannot be produced at 100k queries/s, so the
+retriever classes in :mod:`easyrag_b200.retrievers` are thin per-query views over this module.
+Everything here takes and returns torch CUDA tensors used purely as device buffers; the
+arithmetic is in easyrag_b200/csrc/*.cu.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .index import Bm25Index, DenseIndex
+
+
+def _i32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+class Workspace:
+    """Grow-only device scratch buffer (launch functions never allocate)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = torch.empty(0, dtype=torch.uint8, device=device)
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf.numel() < nbytes:
+            self.buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+@dataclass
+class TopK:
+    scores: torch.Tensor     # [Q, k] float32 (dense, bm25s) or float64 (Okapi, fusion)
+    ids: torch.Tensor        # [Q, k] int32, -1 padded
+    counts: torch.Tensor     # [Q] int32
+
+
+def dense_topk(index: DenseIndex, queries: torch.Tensor, k: int, q_group: Optional[torch.Tensor] = None,
+               id_base: Optional[int] = None, ws: Optional[Workspace] = None, stream=None,
+               out: Optional[TopK] = None) -> TopK:
+    """QdrantRetriever._aretrieve's search for a batch (retrievers.py:37-52): cosine top-k, ids descending on ties."""
+    L = _lib.lib()
+    dev = index.device
+    q = queries
+    if q.dtype != torch.bfloat16 or q.device != dev or not q.is_contiguous():
+        q = queries.to(device=dev, dtype=torch.bfloat16).contiguous()
+    nq, dim = q.shape
+    if dim != index.dim:
+        raise ValueError(f"query dim {dim} != corpus dim {index.dim}")
+    qg = _i32(q_group, dev)
+    if qg is not None and index.doc_group is None:
+        raise ValueError("q_group given but the index has no doc_group")
+    if out is None:
+        out = TopK(torch.empty(nq, k, dtype=torch.float32, device=dev), torch.empty(nq, k, dtype=torch.int32, device=dev),
+                   torch.empty(nq, dtype=torch.int32, device=dev))
+    need = L.ezr_dense_topk_workspace(index.n_rows, dim, nq, k)
+    ws = ws or Workspace(dev)
+    buf = ws.get(need)
+    base = index.row_lo if id_base is None else id_base
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_dense_topk(_lib.ptr(index.vectors), index.n_rows, dim, index.vectors.stride(0), _lib.ptr(q), nq,
+                                    q.stride(0), k, _lib.ptr(index.doc_group if qg is not None else None), _lib.ptr(qg),
+                                    base, _lib.ptr(out.scores), _lib.ptr(out.ids), _lib.ptr(out.counts), _lib.ptr(buf),
+                                    buf.numel(), _lib.stream_ptr(stream)), "ezr_dense_topk")
+    return out
+
+
+def bm25_topk(index: Bm25Index, q_ptr: torch.Tensor, q_terms: torch.Tensor, k: int,
+              q_group: Optional[torch.Tensor] = None, id_base: Optional[int] = None,
+              ws: Optional[Workspace] = None, stream=None, out: Optional[TopK] = None) -> TopK:
+    """BM25Retriever.get_scores + filter for a batch (retrievers.py:128-151,191-210)."""
+    L = _lib.lib()
+    dev = index.device
+    qp, qt = _i32(q_ptr, dev), _i32(q_terms, dev)
+    nq = qp.numel() - 1
+    qg = _i32(q_group, dev)
+    if qg is not None and index.doc_group is None:
+        raise ValueError("q_group given but the index has no doc_group")
+    if out is None:
+        out = TopK(torch.empty(nq, k, dtype=index.score_dtype, device=dev),
+                   torch.empty(nq, k, dtype=torch.int32, device=dev), torch.empty(nq, dtype=torch.int32, device=dev))
+    need = L.ezr_bm25_topk_workspace(index.struct, nq, k)
+    ws = ws or Workspace(dev)
+    buf = ws.get(need)
+    base = index.doc_lo if id_base is None else id_base
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_bm25_topk(index.struct, _lib.ptr(qp), _lib.ptr(qt), nq, k, _lib.ptr(qg), base,
+                                   _lib.ptr(out.scores), _lib.ptr(out.ids), _lib.ptr(out.counts), _lib.ptr(buf),
+                                   buf.numel(), _lib.stream_ptr(stream)), "ezr_bm25_topk")
+    return out
+
+
+def bm25_scores(index: Bm25Index, q_ptr: torch.Tensor, q_terms: torch.Tensor, stream=None) -> torch.Tensor:
+    """BM25Retriever.get_scores (retrievers.py:128-151): [Q, n_docs] score rows."""
+    L = _lib.lib()
+    dev = index.device
+    qp, qt = _i32(q_ptr, dev), _i32(q_terms, dev)
+    nq = qp.numel() - 1
+    out = torch.empty(nq, index.n_docs, dtype=index.score_dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_bm25_scores(index.struct, _lib.ptr(qp), _lib.ptr(qt), nq, _lib.ptr(out),
+                                     _lib.stream_ptr(stream)), "ezr_bm25_scores")
+    return out
+
+
+def select_rows(scores: torch.Tensor, k: int, positive_only: bool = False, doc_group: Optional[torch.Tensor] = None,
+                q_group: Optional[torch.Tensor] = None, id_base: int = 0, ws: Optional[Workspace] = None,
+                stream=None) -> TopK:
+    L = _lib.lib()
+    dev = scores.device
+    assert scores.dim() == 2 and scores.stride(1) == 1
+    st = _lib.F64 if scores.dtype == torch.float64 else _lib.F32
+    if scores.dtype not in (torch.float64, torch.float32):
+        raise TypeError("scores must be float32 or float64")
+    nq, n = scores.shape
+    out = TopK(torch.empty(nq, k, dtype=scores.dtype, device=dev), torch.empty(nq, k, dtype=torch.int32, device=dev),
+               torch.empty(nq, dtype=torch.int32, device=dev))
+    need = L.ezr_select_rows_workspace(nq, n, k, st)
+    ws = ws or Workspace(dev)
+    buf = ws.get(need)
+    dg, qg = _i32(doc_group, dev), _i32(q_group, dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_select_rows(_lib.ptr(scores), st, nq, n, scores.stride(0), k, int(positive_only), _lib.ptr(dg),
+                                     _lib.ptr(qg), id_base, _lib.ptr(out.scores), _lib.ptr(out.ids), _lib.ptr(out.counts),
+                                     _lib.ptr(buf), buf.numel(), _lib.stream_ptr(stream)), "ezr_select_rows")
+    return out
+
+
+def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int, stream=None) -> TopK:
+    """Merge candidate lists [Q, C] (id < 0 = empty) into the canonical top-k."""
+    L = _lib.lib()
+    dev = cand_scores.device
+    assert cand_scores.shape == cand_ids.shape and cand_scores.is_contiguous() and cand_ids.is_contiguous()
+    st = _lib.F64 if cand_scores.dtype == torch.float64 else _lib.F32
+    nq, c = cand_scores.shape
+    cand_ids = cand_ids.to(torch.int32)
+    out = TopK(torch.empty(nq, k, dtype=cand_scores.dtype, device=dev), torch.empty(nq, k, dtype=torch.int32, device=dev),
+               torch.empty(nq, dtype=torch.int32, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_merge_topk(_lib.ptr(cand_scores), _lib.ptr(cand_ids), st, nq, c, c, k,
+                                    _lib.ptr(out.scores), _lib.ptr(out.ids), _lib.ptr(out.counts), None, 0,
+                                    _lib.stream_ptr(stream)), "ezr_merge_topk")
+    return out
+
+
+def rrf_fuse(ids_a: torch.Tensor, cnt_a: torch.Tensor, ids_b: torch.Tensor, cnt_b: torch.Tensor, k_out: int,
+             K: int = 60, canon: Optional[torch.Tensor] = None, stream=None, out: Optional[TopK] = None) -> TopK:
+    """HybridRetriever.reciprocal_rank_fusion (retrievers.py:256-274) for a batch; list a = sparse, b = dense."""
+    L = _lib.lib()
+    dev = ids_a.device
+    assert ids_a.shape == ids_b.shape and ids_a.dtype == torch.int32 and ids_b.dtype == torch.int32
+    nq, stride = ids_a.shape
+    if out is None:
+        out = TopK(torch.empty(nq, k_out, dtype=torch.float64, device=dev),
+                   torch.empty(nq, k_out, dtype=torch.int32, device=dev), torch.empty(nq, dtype=torch.int32, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_rrf_fuse(_lib.ptr(ids_a.contiguous()), _lib.ptr(cnt_a), _lib.ptr(ids_b.contiguous()),
+                                  _lib.ptr(cnt_b), nq, stride, _lib.ptr(canon), 0, K, k_out, _lib.ptr(out.ids),
+                                  _lib.ptr(out.scores), _lib.ptr(out.counts), _lib.stream_ptr(stream)), "ezr_rrf_fuse")
+    return out
+
+
+def fusion_simple(ids_a: torch.Tensor, sc_a: torch.Tensor, cnt_a: torch.Tensor, ids_b: torch.Tensor, sc_b: torch.Tensor,
+                  cnt_b: torch.Tensor, k_out: int, canon: Optional[torch.Tensor] = None, stream=None) -> TopK:
+    """HybridRetriever.fusion (retrievers.py:239-253) for a batch."""
+    L = _lib.lib()
+    dev = ids_a.device
+    nq, stride = ids_a.shape
+    sa = sc_a.to(torch.float64).contiguous()
+    sb = sc_b.to(torch.float64).contiguous()
+    out = TopK(torch.empty(nq, k_out, dtype=torch.float64, device=dev),
+               torch.empty(nq, k_out, dtype=torch.int32, device=dev), torch.empty(nq, dtype=torch.int32, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_fusion_simple(_lib.ptr(ids_a.contiguous()), _lib.ptr(sa), _lib.ptr(cnt_a),
+                                       _lib.ptr(ids_b.contiguous()), _lib.ptr(sb), _lib.ptr(cnt_b), nq, stride,
+                                       _lib.ptr(canon), 0, k_out, _lib.ptr(out.ids), _lib.ptr(out.scores),
+                                       _lib.ptr(out.counts), _lib.stream_ptr(stream)), "ezr_fusion_simple")
+    return out
+
+
+class CoarseRanker:
+    """dense + BM25 + RRF for query batches on one GPU (``HybridRetriever._aretrieve``, retrievers.py:276-291).
+
+    The two routes are independent until the fusion, so they run on two CUDA streams; the RRF
+    kernel joins them.  All buffers are preallocated per (batch size, k) and reused.
+    """
+
+    def __init__(self, dense: DenseIndex, sparse: Bm25Index, canon: Optional[torch.Tensor] = None):
+        assert dense.device == sparse.device
+        self.dense, self.sparse = dense, sparse
+        self.device = dense.device
+        self.canon = None if canon is None else canon.to(device=self.device, dtype=torch.int32).contiguous()
+        self.s_dense = torch.cuda.Stream(device=self.device)
+        self.s_sparse = torch.cuda.Stream(device=self.device)
+        self.ws_dense = Workspace(self.device)
+        self.ws_sparse = Workspace(self.device)
+        self._bufs = {}
+
+    def _buffers(self, nq, kd, ks, ko):
+        key = (nq, kd, ks, ko)
+        if key not in self._bufs:
+            dev = self.device
+            mk = lambda dt, *shape: torch.empty(*shape, dtype=dt, device=dev)
+            self._bufs[key] = (
+                TopK(mk(torch.float32, nq, kd), mk(torch.int32, nq, kd), mk(torch.int32, nq)),
+                TopK(mk(self.sparse.score_dtype, nq, ks), mk(torch.int32, nq, ks), mk(torch.int32, nq)),
+                TopK(mk(torch.float64, nq, ko), mk(torch.int32, nq, ko), mk(torch.int32, nq)),
+            )
+        return self._bufs[key]
+
+    def hybrid(self, queries: torch.Tensor, q_ptr: torch.Tensor, q_terms: torch.Tensor, k_dense: int = 10,
+               k_sparse: int = 10, k_out: int = 10, K: int = 60, q_group: Optional[torch.Tensor] = None
+               ) -> Tuple[TopK, TopK, TopK]:
+        """Returns (fused, sparse, dense).  Inputs must already be on the device."""
+        nq = queries.shape[0]
+        if k_dense != k_sparse:
+            raise ValueError("the fused path keeps both routes at the same k (pad the shorter list upstream)")
+        d_out, s_out, f_out = self._buffers(nq, k_dense, k_sparse, k_out)
+        cur = torch.cuda.current_stream(self.device)
+        self.s_dense.wait_stream(cur)
+        self.s_sparse.wait_stream(cur)
+        with torch.cuda.stream(self.s_sparse):
+            bm25_topk(self.sparse, q_ptr, q_terms, k_sparse, q_group=q_group, ws=self.ws_sparse, stream=self.s_sparse,
+                      out=s_out)
+        with torch.cuda.stream(self.s_dense):
+            dense_topk(self.dense, queries, k_dense, q_group=q_group, ws=self.ws_dense, stream=self.s_dense, out=d_out)
+        cur.wait_stream(self.s_sparse)
+        cur.wait_stream(self.s_dense)
+        rrf_fuse(s_out.ids, s_out.counts, d_out.ids, d_out.counts, k_out, K=K, canon=self.canon, stream=cur, out=f_out)
+        return f_out, s_out, d_out

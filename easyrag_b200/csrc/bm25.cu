@@ -1,0 +1,552 @@
+// BM25 for the coarse-ranking path: index-side weight precompute, batched
+// scoring with shared-memory accumulators, fused top-k.
+//
+// Reference behaviour being replaced: retrievers.py:128-151 (get_scores ->
+// rank_bm25.BM25Okapi.get_scores / bm25s.get_scores) and retrievers.py:191-210
+// (filter).  Arithmetic order: oracle/bm25.py (OkapiCSR docstring).
+//
+// Design (DESIGN.md "BM25"): the per-posting contribution is query independent,
+// so it is computed once at index build with explicit round-to-nearest
+// intrinsics (no FMA contraction) and stored next to the doc id (12 B/posting).
+// At query time a CTA owns (query, range of 8192 documents): its float64
+// accumulators live in shared memory, query terms are applied strictly in
+// token order (one barrier per term keeps the float64 sum order of the
+// reference), and the top-k is taken from shared memory by warp-shuffle
+// insertion.  Score vectors never touch HBM.
+#include "ezr_common.cuh"
+#include "select.cuh"
+#include "../../include/easyrag_b200.h"
+
+namespace ezr {
+
+// ------------------------------------------------------------ index build --
+__global__ void bm25_doc_norm_kernel(const int32_t* __restrict__ doc_len, int64_t n, double k1, double b,
+                                     double one_minus_b, double avgdl, double* __restrict__ kd) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double t1 = __dmul_rn(b, (double)doc_len[i]);
+    const double t2 = __ddiv_rn(t1, avgdl);
+    const double t3 = __dadd_rn(one_minus_b, t2);
+    kd[i] = __dmul_rn(k1, t3);
+}
+
+template <typename S>
+__global__ void bm25_weights_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ post_doc,
+                                    const int32_t* __restrict__ post_tf, int32_t vocab, int64_t n_post,
+                                    const double* __restrict__ idf, const double* __restrict__ kd,
+                                    double num_scale, S* __restrict__ out_w) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_post) return;
+    // term of posting p: largest t with indptr[t] <= p
+    int lo = 0, hi = vocab;   // invariant: indptr[lo] <= p < indptr[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (indptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    const double tf = (double)post_tf[p];
+    const double num = __dmul_rn(tf, num_scale);
+    const double den = __dadd_rn(tf, kd[post_doc[p]]);
+    const double r = __ddiv_rn(num, den);
+    out_w[p] = (S)__dmul_rn(idf[lo], r);
+}
+
+__global__ void bm25_range_index_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ post_doc,
+                                        int32_t vocab, int32_t range_size, int32_t n_ranges,
+                                        uint32_t* __restrict__ range_off) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)vocab * (n_ranges + 1);
+    if (i >= total) return;
+    const int t = (int)(i / (n_ranges + 1));
+    const int r = (int)(i % (n_ranges + 1));
+    const int64_t s = indptr[t], e = indptr[t + 1];
+    const int64_t want = (int64_t)r * range_size;    // first doc id of range r
+    int64_t lo = s, hi = e;                           // lower_bound(post_doc[s:e], want)
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (post_doc[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    range_off[i] = (uint32_t)(lo - s);
+}
+
+// ---------------------------------------------------------------- scoring --
+constexpr int kBmRange = 8192;   // documents per CTA: 64 KB of float64 accumulators
+constexpr int kBmThreads = 512;
+constexpr int kBmMaxT = 12;      // query terms preloaded per round (queries are 4-12 terms; longer ones loop)
+
+struct Bm25Params {
+    const int64_t* indptr;
+    const int32_t* post_doc;
+    const void* post_w;
+    const uint32_t* range_off;
+    const int32_t* doc_group;
+    const int32_t* q_ptr;
+    const int32_t* q_terms;
+    const int32_t* q_group;
+    int64_t n_docs;
+    int32_t vocab;
+    int32_t n_ranges;
+    int32_t k;
+    int32_t id_base;
+    void* out_scores;   // fused: partial [Q][n_ranges][k]; rows: [Q][n_docs]
+    int32_t* out_ids;   // fused: partial ids
+};
+
+// MODE 0: fused top-k (k<=32) -> per-(query,range) partial lists.  MODE 1: write the score row.
+template <typename S, int MODE>
+__global__ void __launch_bounds__(kBmThreads)
+bm25_score_kernel(const Bm25Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S* acc = reinterpret_cast<S*>(smem_raw);
+    __shared__ int64_t s_beg[kBmMaxT];
+    __shared__ int64_t s_end[kBmMaxT];
+    __shared__ S s_ws[(kBmThreads / 32) * 32];
+    __shared__ int s_wi[(kBmThreads / 32) * 32];
+
+    const int q = blockIdx.x;
+    const int r = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int rbase = r * kBmRange;
+    const int rn = (int)min((int64_t)kBmRange, p.n_docs - rbase);
+    const int qs = p.q_ptr[q];
+    const int m = p.q_ptr[q + 1] - qs;
+    const S* __restrict__ post_w = reinterpret_cast<const S*>(p.post_w);
+
+    for (int tb = 0; tb < m; tb += kBmMaxT) {
+        const int mt = min(kBmMaxT, m - tb);
+        if (tid < mt) {
+            const int t = p.q_terms[qs + tb + tid];
+            int64_t beg = 0, end = 0;
+            if (t >= 0 && t < p.vocab) {
+                const int64_t base = p.indptr[t];
+                const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
+                beg = base + ro[0];
+                end = base + ro[1];
+            }
+            s_beg[tid] = beg;
+            s_end[tid] = end;
+        }
+        __syncthreads();
+        // issue the first posting of every term before touching shared memory:
+        // all loads of the round are in flight together
+        int d[kBmMaxT];
+        S w[kBmMaxT];
+#pragma unroll
+        for (int j = 0; j < kBmMaxT; ++j) {
+            d[j] = -1;
+            w[j] = (S)0;
+            if (j < mt) {
+                const int64_t pp = s_beg[j] + tid;
+                if (pp < s_end[j]) {
+                    d[j] = __ldg(p.post_doc + pp);
+                    w[j] = __ldg(post_w + pp);
+                }
+            }
+        }
+        if (tb == 0) {
+            for (int i = tid; i < kBmRange; i += kBmThreads) acc[i] = (S)0;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < kBmMaxT; ++j) {
+            if (j < mt) {   // block-uniform
+                if (d[j] >= 0) acc[d[j] - rbase] += w[j];
+                for (int64_t pp = s_beg[j] + tid + kBmThreads; pp < s_end[j]; pp += kBmThreads) {
+                    const int dd = __ldg(p.post_doc + pp);
+                    acc[dd - rbase] += __ldg(post_w + pp);
+                }
+                __syncthreads();   // term j fully applied before term j+1: float sum order of the reference
+            }
+        }
+    }
+    if (m == 0) {
+        for (int i = tid; i < kBmRange; i += kBmThreads) acc[i] = (S)0;
+        __syncthreads();
+    }
+
+    if (MODE == 1) {
+        S* out = reinterpret_cast<S*>(p.out_scores) + (int64_t)q * p.n_docs + rbase;
+        for (int i = tid; i < rn; i += kBmThreads) out[i] = acc[i];
+        return;
+    }
+
+    // ---- fused top-k: per-warp lists, then warp 0 merges them ----
+    const int lane = tid & 31, warp = tid >> 5;
+    const int want = p.q_group ? p.q_group[q] : -1;
+    WarpTopK<S> tk;
+    tk.init(p.k);
+    for (int i0 = warp * 32; i0 < rn; i0 += kBmThreads) {
+        const int i = i0 + lane;
+        S s = (S)0;
+        bool ok = false;
+        if (i < rn) {
+            s = acc[i];
+            ok = s > (S)0 && better<S>(s, rbase + i, tk.kth_s, tk.kth_id);
+            if (ok && want != -1) ok = (p.doc_group[rbase + i] == want);
+        }
+        tk.offer(s, rbase + i, ok);
+    }
+    s_ws[warp * 32 + lane] = tk.s;
+    s_wi[warp * 32 + lane] = tk.id;
+    __syncthreads();
+    if (warp == 0) {
+        WarpTopK<S> fin;
+        fin.init(p.k);
+        for (int w2 = 0; w2 < kBmThreads / 32; ++w2) {
+            const S s = s_ws[w2 * 32 + lane];
+            const int id = s_wi[w2 * 32 + lane];
+            fin.offer(s, id, lane < p.k && id >= 0);
+        }
+        if (lane < p.k) {
+            const int64_t o = ((int64_t)q * p.n_ranges + r) * p.k + lane;
+            reinterpret_cast<S*>(p.out_scores)[o] = fin.s;
+            p.out_ids[o] = fin.id;      // local id, -1 = empty
+        }
+    }
+}
+
+// One warp per row: merge n_cand candidates (id<0 = empty) into the final top-k (k<=32).
+template <typename S>
+__global__ void merge_warp_kernel(const S* __restrict__ cs, const int32_t* __restrict__ cid, int n_rows, int n_cand,
+                                  int64_t stride, int k, int id_add, S* __restrict__ out_s,
+                                  int32_t* __restrict__ out_id, int32_t* __restrict__ out_cnt) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    WarpTopK<S> tk;
+    tk.init(k);
+    const S* rs = cs + (int64_t)row * stride;
+    const int32_t* ri = cid + (int64_t)row * stride;
+    for (int i0 = 0; i0 < n_cand; i0 += 32) {
+        const int i = i0 + lane;
+        S s = (S)0;
+        int id = -1;
+        if (i < n_cand) { s = rs[i]; id = ri[i]; }
+        tk.offer(s, id, id >= 0);
+    }
+    if (lane < k) {
+        out_s[(int64_t)row * k + lane] = tk.id >= 0 ? tk.s : ScoreTraits<S>::lowest();
+        out_id[(int64_t)row * k + lane] = tk.id >= 0 ? tk.id + id_add : -1;
+    }
+    const unsigned have = __ballot_sync(0xffffffffu, lane < k && tk.id >= 0);
+    if (lane == 0 && out_cnt) out_cnt[row] = __popc(have);
+}
+
+// ------------------------------------------------------------ generic select
+// grid (parts, rows).  Each CTA reduces a slice of one row to its sorted top-k.
+// ids == nullptr: candidate id = column index.  Output slot (row*parts+part)*k.
+template <typename S>
+__global__ void __launch_bounds__(256)
+select_kernel(const S* __restrict__ scores, const int32_t* __restrict__ ids, int64_t n_cols, int64_t row_stride,
+              int parts, int k, int positive_only, const int32_t* __restrict__ doc_group,
+              const int32_t* __restrict__ q_group, int id_add, S* __restrict__ out_s, int32_t* __restrict__ out_id,
+              int32_t* __restrict__ out_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SelSmem<S> sm = sel_carve<S>(smem_raw);
+    sel_init<S>(sm);
+    const int part = blockIdx.x, row = blockIdx.y;
+    const int64_t chunk = (n_cols + parts - 1) / parts;
+    const int64_t c0 = part * chunk;
+    const int64_t c1 = min(n_cols, c0 + chunk);
+    const S* rs = scores + (int64_t)row * row_stride;
+    const int32_t* ri = ids ? ids + (int64_t)row * row_stride : nullptr;
+    const int want = q_group ? q_group[row] : -1;
+    constexpr int kItems = kSelReserve / 256;
+    for (int64_t base = c0; base < c1; base += kSelReserve) {
+#pragma unroll
+        for (int it = 0; it < kItems; ++it) {
+            const int64_t c = base + it * 256 + threadIdx.x;
+            if (c < c1) {
+                const S s = rs[c];
+                const int id = ri ? ri[c] : (int)c;
+                bool ok = id >= 0 && (!positive_only || s > (S)0) && s > ScoreTraits<S>::lowest();
+                if (ok && better<S>(s, id, *sm.thr_s, *sm.thr_id)) {
+                    if (want != -1) ok = (doc_group[id] == want);
+                    if (ok) sel_push<S>(sm, s, id);
+                }
+            }
+        }
+        sel_maybe_flush<S>(sm, k);
+    }
+    sel_compact<S>(sm, k);
+    const int n = *sm.cnt;
+    const int64_t o = ((int64_t)row * parts + part) * k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        out_s[o + i] = i < n ? sm.ks[i] : ScoreTraits<S>::lowest();
+        out_id[o + i] = i < n ? sm.kid[i] + id_add : -1;
+    }
+    if (threadIdx.x == 0 && out_cnt) out_cnt[row] = n;
+}
+
+template <typename S>
+static int launch_select(const S* scores, const int32_t* ids, int n_rows, int64_t n_cols, int64_t row_stride,
+                         int parts, int k, int positive_only, const int32_t* doc_group, const int32_t* q_group,
+                         int id_add, S* out_s, int32_t* out_id, int32_t* out_cnt, cudaStream_t st) {
+    const size_t smem = sel_smem_bytes<S>();
+    static bool attr_done[2] = {false, false};
+    const int which = sizeof(S) == 8 ? 0 : 1;
+    if (!attr_done[which]) {
+        EZR_CUDA(cudaFuncSetAttribute(select_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[which] = true;
+    }
+    dim3 grid(parts, n_rows);
+    ProfScope prof(EZR_PROF_MERGE, st);
+    select_kernel<S><<<grid, 256, smem, st>>>(scores, ids, n_cols, row_stride, parts, k, positive_only, doc_group,
+                                              q_group, id_add, out_s, out_id, out_cnt);
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+static int select_parts(int n_rows, int64_t n_cols) {
+    // enough CTAs to fill the machine, at least 4096 columns each
+    int64_t want = (int64_t)4 * sm_count() / (n_rows > 0 ? n_rows : 1);
+    int64_t maxp = (n_cols + 4095) / 4096;
+    int64_t parts = want < 1 ? 1 : want;
+    if (parts > maxp) parts = maxp;
+    if (parts < 1) parts = 1;
+    return (int)parts;
+}
+
+template <typename S>
+static size_t select_rows_ws(int n_rows, int64_t n_cols, int k) {
+    const int parts = select_parts(n_rows, n_cols);
+    if (parts == 1) return 0;
+    return align_up((size_t)n_rows * parts * k * sizeof(S), 256) + align_up((size_t)n_rows * parts * k * 4, 256);
+}
+
+template <typename S>
+static int select_rows_impl(const S* scores, int n_rows, int64_t n_cols, int64_t row_stride, int k,
+                            int positive_only, const int32_t* doc_group, const int32_t* q_group, int id_base,
+                            S* out_s, int32_t* out_id, int32_t* out_cnt, void* ws, size_t ws_bytes,
+                            cudaStream_t st) {
+    const int parts = select_parts(n_rows, n_cols);
+    if (parts == 1)
+        return launch_select<S>(scores, nullptr, n_rows, n_cols, row_stride, 1, k, positive_only, doc_group,
+                                q_group, id_base, out_s, out_id, out_cnt, st);
+    const size_t need = select_rows_ws<S>(n_rows, n_cols, k);
+    if (ws_bytes < need || !ws) {
+        set_error("select_rows: workspace %zu < %zu", ws_bytes, need);
+        return EZR_ERR_WORKSPACE;
+    }
+    S* ps = reinterpret_cast<S*>(ws);
+    int32_t* pi = reinterpret_cast<int32_t*>((char*)ws + align_up((size_t)n_rows * parts * k * sizeof(S), 256));
+    int rc = launch_select<S>(scores, nullptr, n_rows, n_cols, row_stride, parts, k, positive_only, doc_group,
+                              q_group, 0, ps, pi, nullptr, st);
+    if (rc) return rc;
+    return launch_select<S>(ps, pi, n_rows, (int64_t)parts * k, (int64_t)parts * k, 1, k, 0, nullptr, nullptr,
+                            id_base, out_s, out_id, out_cnt, st);
+}
+
+template <typename S>
+static int merge_impl(const S* cs, const int32_t* cid, int n_rows, int n_cand, int64_t stride, int k, int id_add,
+                      S* out_s, int32_t* out_id, int32_t* out_cnt, cudaStream_t st) {
+    if (n_rows == 0) return EZR_OK;
+    if (k <= 32) {
+        const int wpb = 8;
+        ProfScope prof(EZR_PROF_MERGE, st);
+        merge_warp_kernel<S><<<ceil_div(n_rows, wpb), wpb * 32, 0, st>>>(cs, cid, n_rows, n_cand, stride, k, id_add,
+                                                                        out_s, out_id, out_cnt);
+        EZR_LAUNCH_CHECK();
+        return EZR_OK;
+    }
+    return launch_select<S>(cs, cid, n_rows, n_cand, stride, 1, k, 0, nullptr, nullptr, id_add, out_s, out_id,
+                            out_cnt, st);
+}
+
+template <typename S>
+static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t* q_terms, int n_queries,
+                       int k, const int32_t* q_group, int id_base, int mode, void* out_scores, int32_t* out_ids,
+                       cudaStream_t st) {
+    Bm25Params p;
+    p.indptr = ix->indptr; p.post_doc = ix->post_doc; p.post_w = ix->post_w; p.range_off = ix->range_off;
+    p.doc_group = ix->doc_group; p.q_ptr = q_ptr; p.q_terms = q_terms; p.q_group = q_group;
+    p.n_docs = ix->n_docs; p.vocab = ix->vocab; p.n_ranges = ix->n_ranges; p.k = k; p.id_base = id_base;
+    p.out_scores = out_scores; p.out_ids = out_ids;
+    const size_t smem = (size_t)kBmRange * sizeof(S);
+    static bool attr_done[4] = {false, false, false, false};
+    const int which = (sizeof(S) == 8 ? 0 : 2) + mode;
+    auto kern = mode == 0 ? bm25_score_kernel<S, 0> : bm25_score_kernel<S, 1>;
+    if (!attr_done[which]) {
+        EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[which] = true;
+    }
+    dim3 grid(n_queries, ix->n_ranges);
+    ProfScope prof(EZR_PROF_BM25_SCORE, st);
+    kern<<<grid, kBmThreads, smem, st>>>(p);
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+static int check_index(const ezr_bm25_index* ix) {
+    EZR_CHECK_ARG(ix != nullptr, "bm25: index is NULL");
+    EZR_CHECK_ARG(ix->range_size == kBmRange, "bm25: range_size must be %d (got %d)", kBmRange, ix->range_size);
+    EZR_CHECK_ARG(ix->n_docs >= 0 && ix->n_docs < ((int64_t)1 << 31), "bm25: n_docs out of range");
+    EZR_CHECK_ARG(ix->n_ranges == ceil_div(ix->n_docs, kBmRange), "bm25: n_ranges != ceil(n_docs/range_size)");
+    EZR_CHECK_ARG(ix->n_ranges <= 65535, "bm25: too many ranges (%d) for one shard", ix->n_ranges);
+    EZR_CHECK_ARG(ix->score_type == EZR_F64 || ix->score_type == EZR_F32, "bm25: bad score_type");
+    return EZR_OK;
+}
+
+}  // namespace ezr
+
+using namespace ezr;
+
+extern "C" {
+
+int ezr_bm25_doc_norm(const int32_t* doc_len, int64_t n_docs, double k1, double b, double one_minus_b,
+                      double avgdl, double* out_kd, void* stream) {
+    if (n_docs == 0) return EZR_OK;
+    bm25_doc_norm_kernel<<<ceil_div(n_docs, 256), 256, 0, (cudaStream_t)stream>>>(doc_len, n_docs, k1, b,
+                                                                                  one_minus_b, avgdl, out_kd);
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+int ezr_bm25_weights(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf, int32_t vocab,
+                     int64_t n_postings, const double* idf, const double* kd, double num_scale,
+                     int32_t score_type, void* out_w, void* stream) {
+    if (n_postings == 0) return EZR_OK;
+    EZR_CHECK_ARG(score_type == EZR_F64 || score_type == EZR_F32, "bm25_weights: bad score_type");
+    const int64_t blocks = (n_postings + 255) / 256;
+    EZR_CHECK_ARG(blocks < ((int64_t)1 << 31), "bm25_weights: too many postings");
+    if (score_type == EZR_F64)
+        bm25_weights_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            indptr, post_doc, post_tf, vocab, n_postings, idf, kd, num_scale, (double*)out_w);
+    else
+        bm25_weights_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            indptr, post_doc, post_tf, vocab, n_postings, idf, kd, num_scale, (float*)out_w);
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+int ezr_bm25_range_index(const int64_t* indptr, const int32_t* post_doc, int32_t vocab, int32_t range_size,
+                         int32_t n_ranges, uint32_t* out_range_off, void* stream) {
+    const int64_t total = (int64_t)vocab * (n_ranges + 1);
+    if (total == 0) return EZR_OK;
+    const int64_t blocks = (total + 255) / 256;
+    EZR_CHECK_ARG(blocks < ((int64_t)1 << 31), "bm25_range_index: table too large");
+    bm25_range_index_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(indptr, post_doc, vocab, range_size,
+                                                                               n_ranges, out_range_off);
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+size_t ezr_bm25_topk_workspace(const ezr_bm25_index* ix, int32_t n_queries, int32_t k) {
+    if (!ix || n_queries <= 0 || k <= 0) return 0;
+    const size_t ss = ix->score_type == EZR_F64 ? 8 : 4;
+    if (k <= 32) {
+        const size_t n = (size_t)n_queries * ix->n_ranges * k;
+        return align_up(n * ss, 256) + align_up(n * 4, 256);
+    }
+    // score rows, one query block at a time is the caller's job: here all rows at once
+    size_t rows = align_up((size_t)n_queries * ix->n_docs * ss, 256);
+    size_t sel = ix->score_type == EZR_F64 ? select_rows_ws<double>(n_queries, ix->n_docs, k)
+                                            : select_rows_ws<float>(n_queries, ix->n_docs, k);
+    return rows + sel;
+}
+
+int ezr_bm25_topk(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t* q_terms, int32_t n_queries,
+                  int32_t k, const int32_t* q_group, int32_t id_base, void* out_scores, int32_t* out_ids,
+                  int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_index(ix);
+    if (rc) return rc;
+    EZR_CHECK_ARG(k >= 1 && k <= kSelMaxK, "bm25_topk: k=%d out of [1,%d]", k, kSelMaxK);
+    EZR_CHECK_ARG(q_group == nullptr || ix->doc_group != nullptr, "bm25_topk: q_group given but index has no doc_group");
+    if (n_queries == 0) return EZR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t need = ezr_bm25_topk_workspace(ix, n_queries, k);
+    if (workspace_bytes < need || (need && !workspace)) {
+        set_error("bm25_topk: workspace %zu < %zu", workspace_bytes, need);
+        return EZR_ERR_WORKSPACE;
+    }
+    if (ix->n_docs == 0) {
+        EZR_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)n_queries * 4, st));
+        EZR_CUDA(cudaMemsetAsync(out_ids, 0xff, (size_t)n_queries * k * 4, st));
+        return EZR_OK;
+    }
+    const bool f64 = ix->score_type == EZR_F64;
+    const size_t ss = f64 ? 8 : 4;
+    if (k <= 32) {
+        const size_t n = (size_t)n_queries * ix->n_ranges * k;
+        void* ps = workspace;
+        int32_t* pi = reinterpret_cast<int32_t*>((char*)workspace + align_up(n * ss, 256));
+        rc = f64 ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, st)
+                 : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, st);
+        if (rc) return rc;
+        const int n_cand = ix->n_ranges * k;
+        return f64 ? merge_impl<double>((const double*)ps, pi, n_queries, n_cand, n_cand, k, id_base,
+                                        (double*)out_scores, out_ids, out_counts, st)
+                   : merge_impl<float>((const float*)ps, pi, n_queries, n_cand, n_cand, k, id_base,
+                                       (float*)out_scores, out_ids, out_counts, st);
+    }
+    void* rows = workspace;
+    void* sel_ws = (char*)workspace + align_up((size_t)n_queries * ix->n_docs * ss, 256);
+    const size_t sel_bytes = workspace_bytes - align_up((size_t)n_queries * ix->n_docs * ss, 256);
+    rc = f64 ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, k, nullptr, 0, 1, rows, nullptr, st)
+             : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, k, nullptr, 0, 1, rows, nullptr, st);
+    if (rc) return rc;
+    return f64 ? select_rows_impl<double>((const double*)rows, n_queries, ix->n_docs, ix->n_docs, k, 1,
+                                          ix->doc_group, q_group, id_base, (double*)out_scores, out_ids,
+                                          out_counts, sel_ws, sel_bytes, st)
+               : select_rows_impl<float>((const float*)rows, n_queries, ix->n_docs, ix->n_docs, k, 1,
+                                         ix->doc_group, q_group, id_base, (float*)out_scores, out_ids,
+                                         out_counts, sel_ws, sel_bytes, st);
+}
+
+int ezr_bm25_scores(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t* q_terms, int32_t n_queries,
+                    void* out_scores, void* stream) {
+    int rc = check_index(ix);
+    if (rc) return rc;
+    if (n_queries == 0 || ix->n_docs == 0) return EZR_OK;
+    return ix->score_type == EZR_F64
+               ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, 1, nullptr, 0, 1, out_scores, nullptr,
+                                     (cudaStream_t)stream)
+               : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, 1, nullptr, 0, 1, out_scores, nullptr,
+                                    (cudaStream_t)stream);
+}
+
+size_t ezr_select_rows_workspace(int32_t n_rows, int64_t n_cols, int32_t k, int32_t score_type) {
+    if (n_rows <= 0 || n_cols <= 0 || k <= 0) return 0;
+    return score_type == EZR_F64 ? select_rows_ws<double>(n_rows, n_cols, k) : select_rows_ws<float>(n_rows, n_cols, k);
+}
+
+int ezr_select_rows(const void* scores, int32_t score_type, int32_t n_rows, int64_t n_cols, int64_t row_stride,
+                    int32_t k, int32_t positive_only, const int32_t* doc_group, const int32_t* q_group,
+                    int32_t id_base, void* out_scores, int32_t* out_ids, int32_t* out_counts, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    EZR_CHECK_ARG(k >= 1 && k <= kSelMaxK, "select_rows: k=%d out of [1,%d]", k, kSelMaxK);
+    EZR_CHECK_ARG(score_type == EZR_F64 || score_type == EZR_F32, "select_rows: bad score_type");
+    EZR_CHECK_ARG(n_cols < ((int64_t)1 << 31), "select_rows: n_cols too large");
+    EZR_CHECK_ARG(q_group == nullptr || doc_group != nullptr, "select_rows: q_group without doc_group");
+    if (n_rows == 0) return EZR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_cols == 0) {
+        if (out_counts) EZR_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)n_rows * 4, st));
+        EZR_CUDA(cudaMemsetAsync(out_ids, 0xff, (size_t)n_rows * k * 4, st));
+        return EZR_OK;
+    }
+    return score_type == EZR_F64
+               ? select_rows_impl<double>((const double*)scores, n_rows, n_cols, row_stride, k, positive_only,
+                                          doc_group, q_group, id_base, (double*)out_scores, out_ids, out_counts,
+                                          workspace, workspace_bytes, st)
+               : select_rows_impl<float>((const float*)scores, n_rows, n_cols, row_stride, k, positive_only,
+                                         doc_group, q_group, id_base, (float*)out_scores, out_ids, out_counts,
+                                         workspace, workspace_bytes, st);
+}
+
+size_t ezr_merge_topk_workspace(int32_t, int32_t, int32_t, int32_t) { return 0; }
+
+int ezr_merge_topk(const void* cand_scores, const int32_t* cand_ids, int32_t score_type, int32_t n_rows,
+                   int32_t n_cand, int64_t cand_stride, int32_t k, void* out_scores, int32_t* out_ids,
+                   int32_t* out_counts, void*, size_t, void* stream) {
+    EZR_CHECK_ARG(k >= 1 && k <= kSelMaxK, "merge_topk: k=%d out of [1,%d]", k, kSelMaxK);
+    EZR_CHECK_ARG(score_type == EZR_F64 || score_type == EZR_F32, "merge_topk: bad score_type");
+    EZR_CHECK_ARG(n_cand >= 0 && cand_stride >= n_cand, "merge_topk: bad n_cand/stride");
+    cudaStream_t st = (cudaStream_t)stream;
+    return score_type == EZR_F64
+               ? merge_impl<double>((const double*)cand_scores, cand_ids, n_rows, n_cand, cand_stride, k, 0,
+                                    (double*)out_scores, out_ids, out_counts, st)
+               : merge_impl<float>((const float*)cand_scores, cand_ids, n_rows, n_cand, cand_stride, k, 0,
+                                   (float*)out_scores, out_ids, out_counts, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+// Dense cosine top-k on 5th-gen tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM,
+// with the top-k taken in the epilogue straight from the accumulators.
+//
+// Replaces the vector search behind QdrantRetriever._aretrieve (retrievers.py:37-52;
+// Distance.COSINE, ingestion.py:180-182).  Work decomposition (DESIGN.md "Dense"):
+//   grid = (corpus slices, query blocks).  A CTA keeps one block of 128 queries resident in
+//   shared memory for its whole life (A operand, K-major, 128B-swizzled, dim/64 chunks of
+//   16 KB) and streams its slice of corpus rows through a ring of 8 KB TMA stages
+//   (B operand: 64 rows x 64 bf16).  One elected thread issues tcgen05.mma 128x64x16 into one
+//   of four 64-column TMEM accumulator stages; the four epilogue warps read a finished stage
+//   with tcgen05.ld (one query row per thread) and push the 64 scores through a per-thread
+//   register-resident sorted list of k <= 16.  Scores never reach HBM: per (query, slice) the
+//   CTA writes k (score,id) pairs, and a warp-per-query merge produces the final list.
+// The corpus is read from HBM exactly once per query block, so a launch is HBM-bound for
+// blocks of <= ~220 queries (ridge of measured bf16 peak / measured HBM bandwidth).
+#include "ezr_common.cuh"
+#include "ptx.cuh"
+#include "dense_tc.h"
+#include "../../include/easyrag_b200.h"
+
+namespace ezr {
+
+constexpr int TC_M = 128;       // queries per CTA = UMMA M
+constexpr int TC_N = 64;        // corpus rows per tile = UMMA N
+constexpr int TC_KC = 64;       // bf16 per k-chunk = one 128-byte swizzle row
+constexpr int TC_MAXD = 768;
+constexpr int TC_ACC = 4;       // TMEM accumulator stages (TC_N fp32 columns each)
+constexpr int TC_MAX_STAGES = 16;
+constexpr int TC_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TC_KMAX = 16;
+constexpr int TC_A_CHUNK_BYTES = TC_M * TC_KC * 2;   // 16384
+constexpr int TC_B_STAGE_BYTES = TC_N * TC_KC * 2;   // 8192
+constexpr int TC_SMEM_LIMIT = 232448;                 // 227 KB opt-in maximum per CTA
+
+struct TcParams {
+    int64_t n_rows;
+    int rows_per_slice;   // multiple of TC_N
+    int n_queries;
+    int kchunks;          // dim / 64
+    int n_stages;
+    int k;
+    int id_base;
+    const int32_t* doc_group;
+    const int32_t* q_group;
+    float* part_s;        // [n_queries][n_slices][k]
+    int32_t* part_id;
+    int n_slices;
+};
+
+struct TcBarriers {
+    uint64_t a_full;
+    uint64_t b_full[TC_MAX_STAGES];
+    uint64_t b_empty[TC_MAX_STAGES];
+    uint64_t acc_full[TC_ACC];
+    uint64_t acc_empty[TC_ACC];
+    uint32_t tmem_base;
+};
+
+// KT = compile-time list length (smallest of 4/8/12/16 >= k) so the per-thread list stays in registers
+template <bool FILTER, int KT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                const TcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 128B swizzle needs 1024-byte aligned tiles
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem_a = smem;
+    unsigned char* smem_b = smem + (size_t)p.kchunks * TC_A_CHUNK_BYTES;
+    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_b + (size_t)p.n_stages * TC_B_STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int slice = blockIdx.x;
+    const int q0 = blockIdx.y * TC_M;
+    const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
+    const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
+    const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_q);
+        ptx::prefetch_tensormap(&map_c);
+        ptx::mbar_init(&bars->a_full, 1);
+        for (int i = 0; i < p.n_stages; ++i) {
+            ptx::mbar_init(&bars->b_full[i], 1);
+            ptx::mbar_init(&bars->b_empty[i], 1);
+        }
+        for (int i = 0; i < TC_ACC; ++i) {
+            ptx::mbar_init(&bars->acc_full[i], 1);
+            ptx::mbar_init(&bars->acc_empty[i], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<TC_ACC * TC_N>(&bars->tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            ptx::mbar_expect_tx(&bars->a_full, (uint32_t)p.kchunks * TC_A_CHUNK_BYTES);
+            for (int kc = 0; kc < p.kchunks; ++kc)
+                ptx::tma_load_2d_hint(smem_a + (size_t)kc * TC_A_CHUNK_BYTES, &map_q, &bars->a_full, kc * TC_KC, q0,
+                                      ptx::kEvictLast);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int row0 = (int)(row_begin + (int64_t)t * TC_N);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&bars->b_empty[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&bars->b_full[stage], TC_B_STAGE_BYTES);
+                    ptx::tma_load_2d_hint(smem_b + (size_t)stage * TC_B_STAGE_BYTES, &map_c, &bars->b_full[stage],
+                                          kc * TC_KC, row0, ptx::kEvictFirst);
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_M, TC_N);
+            ptx::mbar_wait(&bars->a_full, 0);
+            ptx::tc_fence_after();
+            const uint32_t a_base = ptx::smem_u32(smem_a);
+            const uint32_t b_base = ptx::smem_u32(smem_b);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int as = t % TC_ACC;
+                const uint32_t aph = (uint32_t)(t / TC_ACC) & 1u;
+                ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_N);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&bars->b_full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = a_base + (uint32_t)kc * TC_A_CHUNK_BYTES;
+                    const uint32_t b_addr = b_base + (uint32_t)stage * TC_B_STAGE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < TC_KC / 16; ++k4) {
+                        ptx::umma_f16_ss(d_tmem, ptx::make_desc_sw128(a_addr + k4 * 32),
+                                         ptx::make_desc_sw128(b_addr + k4 * 32), idesc, (uint32_t)((kc | k4) != 0));
+                    }
+                    ptx::umma_commit(&bars->b_empty[stage]);          // frees the smem stage when the MMAs retire
+                    if (kc == p.kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: one query row per thread ----------------
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int m = quad * 32 + lane;
+        const int qg = q0 + m;
+        const bool active = qg < p.n_queries;
+        const int k = p.k;
+        int want = -1;
+        if (FILTER && active) want = p.q_group[qg];
+        float ts[KT];
+        int ti[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) { ts[j] = -INFINITY; ti[j] = -1; }
+        float thr = -INFINITY;
+
+        for (int t = 0; t < n_tiles; ++t) {
+            const int as = t % TC_ACC;
+            const uint32_t aph = (uint32_t)(t / TC_ACC) & 1u;
+            ptx::mbar_wait(&bars->acc_full[as], aph);
+            ptx::tc_fence_after();
+            const int64_t row0 = row_begin + (int64_t)t * TC_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TC_N);
+#pragma unroll
+            for (int half = 0; half < TC_N / 32; ++half) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(taddr + half * 32, r);
+                ptx::tmem_ld_wait();
+                if (half == TC_N / 32 - 1) {
+                    // accumulator stage is in registers: hand it back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float v = __uint_as_float(r[j]) + 0.0f;       // -0.0 -> +0.0
+                    const int64_t doc = row0 + half * 32 + j;
+                    bool ok = active && doc < row_end && v >= thr;
+                    if (FILTER) {
+                        if (ok && want != -1) ok = (__ldg(p.doc_group + doc) == want);
+                    }
+                    if (ok) {
+                        // candidates arrive in increasing id order, so on equal score the newcomer (higher id)
+                        // ranks first under the canonical order: ">=" everywhere.
+                        float cv = v;
+                        int ci = (int)doc + p.id_base;
+#pragma unroll
+                        for (int s = 0; s < KT; ++s) {
+                            const bool b = cv >= ts[s];
+                            const float fs = ts[s];
+                            const int is = ti[s];
+                            ts[s] = b ? cv : fs;
+                            ti[s] = b ? ci : is;
+                            cv = b ? fs : cv;
+                            ci = b ? is : ci;
+                        }
+                        thr = ts[KT - 1];
+                    }
+                }
+            }
+        }
+        if (active) {
+            const int64_t o = ((int64_t)qg * p.n_slices + slice) * k;
+#pragma unroll
+            for (int s = 0; s < KT; ++s) {
+                if (s < k) {
+                    p.part_s[o + s] = ts[s];
+                    p.part_id[o + s] = ti[s];
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<TC_ACC * TC_N>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------ host ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems,
+                        uint32_t box_cols, uint32_t box_rows) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        EZR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !sym) {
+            set_error("cuTensorMapEncodeTiled not available from the driver");
+            return EZR_ERR_CUDA;
+        }
+        fn = reinterpret_cast<PFN_encodeTiled>(sym);
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): cols=%llu rows=%llu stride=%llu box=%ux%u", (int)r,
+                  (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_elems, box_cols,
+                  box_rows);
+        return EZR_ERR_CUDA;
+    }
+    return EZR_OK;
+}
+
+static int tc_slices(int64_t n_rows) {
+    const int64_t tiles = (n_rows + TC_N - 1) / TC_N;
+    const int sms = sm_count();
+    return (int)(tiles < sms ? tiles : sms);
+}
+
+static int tc_rows_per_slice(int64_t n_rows, int slices) {
+    const int64_t tiles = (n_rows + TC_N - 1) / TC_N;
+    return (int)((tiles + slices - 1) / slices) * TC_N;
+}
+
+bool dense_tc_supported(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t ldc, const __nv_bfloat16* queries,
+                        int n_queries, int64_t ldq, int k) {
+    if (dim % TC_KC != 0 || dim > TC_MAXD || dim <= 0) return false;
+    if (k < 1 || k > TC_KMAX) return false;
+    if (ldc % 8 != 0 || ldq % 8 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(corpus) & 15) || (reinterpret_cast<uintptr_t>(queries) & 15)) return false;
+    if (n_rows < 1 || n_queries < 1) return false;
+    return true;
+}
+
+size_t dense_tc_workspace(int64_t n_rows, int dim, int n_queries, int k) {
+    if (dim % TC_KC != 0 || dim > TC_MAXD || k > TC_KMAX || n_rows < 1) return 0;
+    const int slices = tc_slices(n_rows);
+    const size_t n = (size_t)n_queries * slices * k;
+    return align_up(n * 4, 256) * 2;
+}
+
+int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t ldc, const __nv_bfloat16* queries,
+                  int n_queries, int64_t ldq, int k, const int32_t* doc_group, const int32_t* q_group, int id_base,
+                  float* out_scores, int32_t* out_ids, int32_t* out_counts, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+    const size_t need = dense_tc_workspace(n_rows, dim, n_queries, k);
+    if (ws_bytes < need || !ws) {
+        set_error("dense_topk(tcgen05): workspace %zu < %zu", ws_bytes, need);
+        return EZR_ERR_WORKSPACE;
+    }
+    TcParams p;
+    p.n_rows = n_rows;
+    p.n_slices = tc_slices(n_rows);
+    p.rows_per_slice = tc_rows_per_slice(n_rows, p.n_slices);
+    // with the rounded-up slice size the last slices may be empty: shrink the grid to non-empty ones
+    p.n_slices = (int)((n_rows + p.rows_per_slice - 1) / p.rows_per_slice);
+    p.n_queries = n_queries;
+    p.kchunks = dim / TC_KC;
+    p.k = k;
+    p.id_base = id_base;
+    p.doc_group = doc_group;
+    p.q_group = q_group;
+    const size_t a_bytes = (size_t)p.kchunks * TC_A_CHUNK_BYTES;
+    const size_t fixed = 1024 /*alignment slack*/ + sizeof(TcBarriers) + 64;
+    int stages = (int)((TC_SMEM_LIMIT - fixed - a_bytes) / TC_B_STAGE_BYTES);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) {
+        set_error("dense_topk(tcgen05): dim=%d leaves no room for a TMA ring", dim);
+        return EZR_ERR_UNSUPPORTED;
+    }
+    p.n_stages = stages;
+    const size_t smem = fixed + a_bytes + (size_t)stages * TC_B_STAGE_BYTES;
+    const size_t n_part = (size_t)n_queries * p.n_slices * k;
+    p.part_s = reinterpret_cast<float*>(ws);
+    p.part_id = reinterpret_cast<int32_t*>((char*)ws + align_up(n_part * 4, 256));
+
+    CUtensorMap map_q, map_c;
+    int rc = encode_tmap_2d_bf16(&map_q, queries, (uint64_t)dim, (uint64_t)n_queries, (uint64_t)ldq, TC_KC, TC_M);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&map_c, corpus, (uint64_t)dim, (uint64_t)n_rows, (uint64_t)ldc, TC_KC, TC_N);
+    if (rc) return rc;
+
+    const bool filter = (q_group != nullptr);
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const TcParams);
+    static const kern_t table[2][4] = {
+        {dense_tc_kernel<false, 4>, dense_tc_kernel<false, 8>, dense_tc_kernel<false, 12>, dense_tc_kernel<false, 16>},
+        {dense_tc_kernel<true, 4>, dense_tc_kernel<true, 8>, dense_tc_kernel<true, 12>, dense_tc_kernel<true, 16>}};
+    const int kt = (k + 3) / 4 - 1;
+    kern_t kern = table[filter ? 1 : 0][kt];
+    static bool attr_done[2][4] = {{false, false, false, false}, {false, false, false, false}};
+    if (!attr_done[filter ? 1 : 0][kt]) {
+        EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        attr_done[filter ? 1 : 0][kt] = true;
+    }
+    dim3 grid(p.n_slices, (n_queries + TC_M - 1) / TC_M);
+    {
+        ProfScope prof(EZR_PROF_DENSE_TC, st);
+        kern<<<grid, TC_THREADS, smem, st>>>(map_q, map_c, p);
+    }
+    EZR_LAUNCH_CHECK();
+    const int n_cand = p.n_slices * k;
+    return ezr_merge_topk(p.part_s, p.part_id, EZR_F32, n_queries, n_cand, n_cand, k, out_scores, out_ids, out_counts,
+                          nullptr, 0, st);
+}
+
+}  // namespace ezr

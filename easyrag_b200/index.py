@@ -1,0 +1,193 @@
+"""Index construction for the two coarse-ranking routes.
+
+* :class:`Bm25Stats` -- corpus statistics exactly as ``rank_bm25.BM25Okapi.__init__`` /
+  ``bm25s.BM25.index`` derive them (reference call sites retrievers.py:98-118): document
+  frequencies, ``avgdl``, ``idf`` with the epsilon floor.  The transcendental part (``math.log``)
+  and the order-sensitive float64 sum stay on the host so they are bit-identical to CPython
+  (SURVEY.md section 7 "hard parts"); counting/sorting uses torch ops on whatever device holds the tokens.
+* :class:`Bm25Index` -- device-resident term-major postings with the per-posting contribution
+  precomputed by ``ezr_bm25_weights`` (CUDA, round-to-nearest, no FMA), plus the range table the
+  query kernel uses.  Needs a GPU; there is no CPU path.
+* :class:`DenseIndex` -- the bf16 corpus matrix that replaces the Qdrant collection
+  (ingestion.py:155-191), with the optional ``dir`` class per row for payload filters.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+K1, B, EPSILON = 1.5, 0.75, 0.25     # retrievers.py:103-105
+
+
+@dataclass
+class Bm25Stats:
+    n_docs: int
+    vocab: int
+    bm25_type: int                 # 0 = BM25Okapi (float64), 1 = bm25s lucene (float32)
+    avgdl: float
+    doc_len: torch.Tensor          # int32 [N]
+    df: torch.Tensor               # int64 [V]
+    idf: np.ndarray                # float64 [V] (type 1: float32 values widened)
+    indptr: torch.Tensor           # int64 [V+1]
+    post_doc: torch.Tensor         # int32 [P], ascending within a term
+    post_tf: torch.Tensor          # int32 [P]
+    average_idf: float = 0.0
+
+    @staticmethod
+    def from_tokens(tokens: torch.Tensor, doc_ptr: torch.Tensor, vocab: int, bm25_type: int = 0,
+                    k1: float = K1, b: float = B, epsilon: float = EPSILON) -> "Bm25Stats":
+        """``tokens`` int32/int64 [T] term ids, ``doc_ptr`` int64 [N+1]."""
+        dev = tokens.device
+        n = doc_ptr.numel() - 1
+        if n == 0:
+            raise ZeroDivisionError("division by zero")      # rank_bm25: avgdl = num_doc / corpus_size
+        lens = (doc_ptr[1:] - doc_ptr[:-1]).to(torch.int64)
+        total = int(lens.sum())
+        avgdl = total / n
+        tok = tokens.to(torch.int64)
+        if total:
+            if int(tok.min()) < 0 or int(tok.max()) >= vocab:
+                raise ValueError("token id out of range [0, vocab)")
+        doc_of = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), lens)
+        key = tok * n + doc_of
+        ukey, counts = torch.unique(key, return_counts=True)       # sorted: term-major, doc ascending
+        post_term = torch.div(ukey, n, rounding_mode="floor")
+        post_doc = (ukey - post_term * n).to(torch.int32)
+        post_tf = counts.to(torch.int32)
+        df = torch.bincount(post_term, minlength=vocab)
+        indptr = torch.zeros(vocab + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(df, 0, out=indptr[1:])
+        df_host = df.cpu().numpy()
+        present = np.nonzero(df_host)[0]
+        idf = np.zeros(vocab, dtype=np.float64)
+        average_idf = 0.0
+        if bm25_type == 0:
+            # rank_bm25 _calc_idf: idf = log(N - n + 0.5) - log(n + 0.5); sequential float64 sum over
+            # terms in first-seen order; negatives replaced by epsilon * mean.
+            vals = np.array([math.log(n - int(d) + 0.5) - math.log(int(d) + 0.5) for d in df_host[present]],
+                            dtype=np.float64)
+            idf[present] = vals
+            if present.size:
+                first_pos = torch.full((vocab,), total, dtype=torch.int64, device=dev)
+                first_pos.scatter_reduce_(0, tok, torch.arange(total, device=dev, dtype=torch.int64), reduce="amin")
+                order = torch.argsort(first_pos[torch.as_tensor(present, device=dev)], stable=True).cpu().numpy()
+                seq = np.cumsum(vals[order])          # np.cumsum is a plain left-to-right float64 sum
+                average_idf = float(seq[-1]) / present.size
+                neg = present[vals < 0]
+                idf[neg] = epsilon * average_idf
+        elif bm25_type == 1:
+            vals = np.array([math.log(1 + (n - int(d) + 0.5) / (int(d) + 0.5)) for d in df_host[present]],
+                            dtype=np.float64).astype(np.float32)
+            idf[present] = vals.astype(np.float64)
+        else:
+            raise ValueError("bm25_type must be 0 (BM25Okapi) or 1 (bm25s)")
+        return Bm25Stats(n_docs=n, vocab=vocab, bm25_type=bm25_type, avgdl=avgdl, doc_len=lens.to(torch.int32),
+                         df=df, idf=idf, indptr=indptr, post_doc=post_doc, post_tf=post_tf,
+                         average_idf=average_idf)
+
+
+class Bm25Index:
+    """Device-resident BM25 index over documents ``[doc_lo, doc_hi)`` of a corpus described by ``stats``.
+
+    Global statistics (idf, avgdl) always come from the whole corpus so that a row-sharded index
+    scores exactly like the unsharded one.
+    """
+
+    def __init__(self, stats: Bm25Stats, device=None, doc_lo: int = 0, doc_hi: Optional[int] = None,
+                 doc_group: Optional[torch.Tensor] = None, k1: float = K1, b: float = B):
+        _lib.require_cuda()
+        L = _lib.lib()
+        device = torch.device(device if device is not None else "cuda")
+        doc_hi = stats.n_docs if doc_hi is None else doc_hi
+        self.stats = stats
+        self.doc_lo, self.doc_hi = doc_lo, doc_hi
+        self.n_docs = doc_hi - doc_lo
+        self.vocab = stats.vocab
+        self.score_type = _lib.F64 if stats.bm25_type == 0 else _lib.F32
+        self.score_dtype = torch.float64 if stats.bm25_type == 0 else torch.float32
+        self.device = device
+        with torch.cuda.device(device):
+            post_doc = stats.post_doc.to(device)
+            post_tf = stats.post_tf.to(device)
+            indptr = stats.indptr.to(device)
+            if doc_lo != 0 or doc_hi != stats.n_docs:
+                keep = (post_doc >= doc_lo) & (post_doc < doc_hi)
+                term_of = torch.repeat_interleave(torch.arange(stats.vocab, device=device),
+                                                  (indptr[1:] - indptr[:-1]))
+                df_local = torch.bincount(term_of[keep], minlength=stats.vocab)
+                indptr = torch.zeros(stats.vocab + 1, dtype=torch.int64, device=device)
+                torch.cumsum(df_local, 0, out=indptr[1:])
+                post_doc = (post_doc[keep] - doc_lo).to(torch.int32)
+                post_tf = post_tf[keep]
+            self.indptr = indptr.contiguous()
+            self.post_doc = post_doc.contiguous()
+            self.n_postings = int(self.post_doc.numel())
+            st = _lib.stream_ptr()
+            doc_len = stats.doc_len[doc_lo:doc_hi].to(device).contiguous()
+            kd = torch.empty(self.n_docs, dtype=torch.float64, device=device)
+            _lib.check(L.ezr_bm25_doc_norm(_lib.ptr(doc_len), self.n_docs, k1, b, 1 - b, stats.avgdl,
+                                           _lib.ptr(kd), st), "ezr_bm25_doc_norm")
+            idf_dev = torch.from_numpy(stats.idf).to(device)
+            self.post_w = torch.empty(self.n_postings, dtype=self.score_dtype, device=device)
+            num_scale = (k1 + 1) if stats.bm25_type == 0 else 1.0
+            _lib.check(L.ezr_bm25_weights(_lib.ptr(self.indptr), _lib.ptr(self.post_doc), _lib.ptr(post_tf.contiguous()),
+                                          self.vocab, self.n_postings, _lib.ptr(idf_dev), _lib.ptr(kd), num_scale,
+                                          self.score_type, _lib.ptr(self.post_w), st), "ezr_bm25_weights")
+            self.n_ranges = (self.n_docs + _lib.BM25_RANGE - 1) // _lib.BM25_RANGE
+            self.range_off = torch.empty(self.vocab * (self.n_ranges + 1), dtype=torch.int32, device=device)
+            _lib.check(L.ezr_bm25_range_index(_lib.ptr(self.indptr), _lib.ptr(self.post_doc), self.vocab,
+                                              _lib.BM25_RANGE, self.n_ranges, _lib.ptr(self.range_off), st),
+                       "ezr_bm25_range_index")
+            self.doc_group = None
+            if doc_group is not None:
+                self.doc_group = doc_group[doc_lo:doc_hi].to(device=device, dtype=torch.int32).contiguous()
+            torch.cuda.current_stream().synchronize()
+        self._struct = None
+        self.refresh_struct()
+
+    def refresh_struct(self):
+        s = _lib.Bm25IndexStruct()
+        s.n_docs, s.n_postings, s.vocab = self.n_docs, self.n_postings, self.vocab
+        s.score_type, s.range_size, s.n_ranges = self.score_type, _lib.BM25_RANGE, self.n_ranges
+        s.indptr = self.indptr.data_ptr()
+        s.post_doc = self.post_doc.data_ptr()
+        s.post_w = self.post_w.data_ptr()
+        s.range_off = self.range_off.data_ptr()
+        s.doc_group = self.doc_group.data_ptr() if self.doc_group is not None else None
+        self._struct = s
+
+    def set_doc_group(self, doc_group: Optional[torch.Tensor]):
+        self.doc_group = None if doc_group is None else doc_group.to(device=self.device, dtype=torch.int32).contiguous()
+        self.refresh_struct()
+
+    @property
+    def struct(self):
+        import ctypes
+        return ctypes.byref(self._struct)
+
+    def index_bytes(self) -> int:
+        return (self.post_doc.numel() * 4 + self.post_w.numel() * self.post_w.element_size()
+                + self.range_off.numel() * 4 + self.indptr.numel() * 8)
+
+
+class DenseIndex:
+    """Row-major bf16 matrix of L2-normalised chunk embeddings (rows ``[row_lo, row_hi)`` of the corpus)."""
+
+    def __init__(self, vectors: torch.Tensor, device=None, row_lo: int = 0, doc_group: Optional[torch.Tensor] = None,
+                 normalize: bool = False):
+        _lib.require_cuda()
+        device = torch.device(device if device is not None else "cuda")
+        v = vectors.to(device)
+        if normalize:
+            v = torch.nn.functional.normalize(v.float(), dim=1)
+        self.vectors = v.to(torch.bfloat16).contiguous()
+        self.n_rows, self.dim = self.vectors.shape
+        self.row_lo = row_lo
+        self.device = device
+        self.doc_group = None if doc_group is None else doc_group.to(device=device, dtype=torch.int32).contiguous()

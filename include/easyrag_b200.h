@@ -1,0 +1,174 @@
+/*
+ * easyrag_b200 -- C ABI of the B200-native coarse-ranking path.
+ *
+ * The reference (BUAADreamer/EasyRAG) has no native code and therefore no FFI
+ * for this path: its boundary is the Python class surface of
+ * src/easyrag/custom/retrievers.py.  Each entry point below replaces the
+ * arithmetic behind one of those methods; the Python classes in
+ * easyrag_b200/retrievers.py keep the reference's signatures and call these
+ * through ctypes (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ezr_status otherwise;
+ *     ezr_last_error() returns a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - launch functions never synchronise and never allocate: outputs and the
+ *     workspace are caller-owned (query the size with the *_workspace call).
+ *   - document ids are int32, local to the shard the index was built over;
+ *     `id_base` is added on output so a row-sharded corpus yields global ids.
+ *   - canonical rank order everywhere: score descending, then id descending
+ *     (== numpy argsort(kind="stable")[::-1]).
+ *   - the library targets sm_100a only; ezr_device_check() fails elsewhere.
+ */
+#ifndef EASYRAG_B200_H
+#define EASYRAG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ezr_status {
+    EZR_OK = 0,
+    EZR_ERR_INVALID = -1,
+    EZR_ERR_CUDA = -2,
+    EZR_ERR_WORKSPACE = -3,
+    EZR_ERR_UNSUPPORTED = -4,
+    EZR_ERR_ARCH = -5
+} ezr_status;
+
+typedef enum ezr_score_type {
+    EZR_F64 = 0, /* rank_bm25.BM25Okapi, bm25_type 0 (retrievers.py:113-118) */
+    EZR_F32 = 1  /* bm25s, bm25_type 1 (retrievers.py:107-111); dense cosine */
+} ezr_score_type;
+
+int ezr_version(void);
+const char* ezr_last_error(void);
+/* fails with EZR_ERR_ARCH unless the current device is compute capability 10.x */
+int ezr_device_check(void);
+
+/* ------------------------------------------------------------------ BM25 --
+ * Term-major (CSC) posting lists with per-posting precomputed contribution
+ *   w = idf[t] * tf*(k1+1) / (tf + k1*((1-b) + b*dl/avgdl))
+ * evaluated with IEEE round-to-nearest, no FMA contraction, in exactly the
+ * operation order numpy applies to rank_bm25's expression (oracle/bm25.py).
+ * Documents are cut into ranges of `range_size` ids; range_off[t*(n_ranges+1)+r]
+ * is the offset (relative to indptr[t]) of the first posting of term t whose
+ * document id is >= r*range_size.
+ */
+typedef struct ezr_bm25_index {
+    int64_t n_docs;
+    int64_t n_postings;
+    int32_t vocab;
+    int32_t score_type;        /* ezr_score_type of post_w */
+    int32_t range_size;        /* 8192 */
+    int32_t n_ranges;          /* ceil(n_docs / range_size) */
+    const int64_t* indptr;     /* [vocab+1] */
+    const int32_t* post_doc;   /* [n_postings] ascending inside a term */
+    const void* post_w;        /* [n_postings] double or float */
+    const uint32_t* range_off; /* [vocab*(n_ranges+1)] */
+    const int32_t* doc_group;  /* [n_docs] metadata class of each document, or NULL */
+} ezr_bm25_index;
+
+/* K_d[i] = k1 * (one_minus_b + (b*doc_len[i]) / avgdl)   -- rank_bm25 get_scores denominator term */
+int ezr_bm25_doc_norm(const int32_t* doc_len, int64_t n_docs, double k1, double b, double one_minus_b,
+                      double avgdl, double* out_kd, void* stream);
+
+/* out_w[p] = (S)( idf[term(p)] * ((tf*num_scale) / (tf + K_d[doc])) ); num_scale = k1+1 (Okapi) or 1 (bm25s) */
+int ezr_bm25_weights(const int64_t* indptr, const int32_t* post_doc, const int32_t* post_tf, int32_t vocab,
+                     int64_t n_postings, const double* idf, const double* kd, double num_scale,
+                     int32_t score_type, void* out_w, void* stream);
+
+int ezr_bm25_range_index(const int64_t* indptr, const int32_t* post_doc, int32_t vocab, int32_t range_size,
+                         int32_t n_ranges, uint32_t* out_range_off, void* stream);
+
+/* BM25Retriever.get_scores + .filter for a batch of queries (retrievers.py:128-151,191-210):
+ * query i has terms q_terms[q_ptr[i] .. q_ptr[i+1]) in token order (duplicates repeat, <0 or >=vocab = unknown).
+ * Only documents with score > 0 qualify (retrievers.py:195-196); q_group[i] >= 0 additionally requires
+ * doc_group[d] == q_group[i] (filter_dict, retrievers.py:198-202); -1 = no filter.
+ * Outputs: out_scores[Q*k] (double/float per index->score_type), out_ids[Q*k] (-1 padded), out_counts[Q].
+ * k <= 32 runs fused (accumulators never leave shared memory); larger k (<=1024) goes through a score row. */
+size_t ezr_bm25_topk_workspace(const ezr_bm25_index* index, int32_t n_queries, int32_t k);
+int ezr_bm25_topk(const ezr_bm25_index* index, const int32_t* q_ptr, const int32_t* q_terms, int32_t n_queries,
+                  int32_t k, const int32_t* q_group, int32_t id_base, void* out_scores, int32_t* out_ids,
+                  int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* BM25Retriever.get_scores (retrievers.py:128-151): full score rows, out_scores[Q * n_docs] */
+int ezr_bm25_scores(const ezr_bm25_index* index, const int32_t* q_ptr, const int32_t* q_terms,
+                    int32_t n_queries, void* out_scores, void* stream);
+
+/* ------------------------------------------------------- generic top-k --
+ * Row-wise top-k of a score matrix (k <= 1024): scores[q*row_stride + j], j < n_cols.
+ * positive_only != 0 keeps only scores > 0 (BM25Retriever.filter). */
+size_t ezr_select_rows_workspace(int32_t n_rows, int64_t n_cols, int32_t k, int32_t score_type);
+int ezr_select_rows(const void* scores, int32_t score_type, int32_t n_rows, int64_t n_cols, int64_t row_stride,
+                    int32_t k, int32_t positive_only, const int32_t* doc_group, const int32_t* q_group,
+                    int32_t id_base, void* out_scores, int32_t* out_ids, int32_t* out_counts, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* Merge per-shard / per-partition candidate lists: row q has n_cand (score,id) pairs at q*cand_stride,
+ * id < 0 = empty slot.  Used after the all-gather of per-shard top-k. k <= 1024. */
+size_t ezr_merge_topk_workspace(int32_t n_rows, int32_t n_cand, int32_t k, int32_t score_type);
+int ezr_merge_topk(const void* cand_scores, const int32_t* cand_ids, int32_t score_type, int32_t n_rows,
+                   int32_t n_cand, int64_t cand_stride, int32_t k, void* out_scores, int32_t* out_ids,
+                   int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------- dense ----
+ * QdrantRetriever (retrievers.py:37-52) over a COSINE collection (ingestion.py:180-182):
+ * corpus rows and queries are L2-normalised bf16; score = fp32-accumulated dot product.
+ * ld_* are row strides in elements.  q_group / doc_group implement the `dir` payload filter
+ * (ingestion.py:207-216).  Rows short of k are padded with id -1, score -inf. */
+size_t ezr_dense_topk_workspace(int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k);
+int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t ld_corpus,
+                   const void* queries_bf16, int32_t n_queries, int64_t ld_queries, int32_t k,
+                   const int32_t* doc_group, const int32_t* q_group, int32_t id_base, float* out_scores,
+                   int32_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* 0 = pick automatically, 1 = force the generic SIMT kernel, 2 = force tcgen05 (error if unsupported) */
+int ezr_dense_set_kernel(int32_t which);
+/* name of the kernel the last ezr_dense_topk call on this thread launched ("tcgen05" / "simt") */
+const char* ezr_dense_last_kernel(void);
+
+/* ------------------------------------------------------------- fusion ---
+ * HybridRetriever.reciprocal_rank_fusion (retrievers.py:256-274): list a first, then list b
+ * (the reference passes [sparse, dense], retrievers.py:290); score += 1/(rank+K), rank from 1, fp64;
+ * key = canon[id] (documents with identical text share a key, retrievers.py:263-265; NULL = identity);
+ * the returned id is the LAST occurrence of the key (text_to_node overwrite, :264); ties keep
+ * first-insertion order (stable sort, :266).  ids_x is [Q][stride_in], cnt_x[Q] valid entries each. */
+int ezr_rrf_fuse(const int32_t* ids_a, const int32_t* cnt_a, const int32_t* ids_b, const int32_t* cnt_b,
+                 int32_t n_queries, int32_t stride_in, const int32_t* canon, int32_t canon_base, int32_t K,
+                 int32_t k_out, int32_t* out_ids, double* out_scores, int32_t* out_counts, void* stream);
+
+/* HybridRetriever.fusion (retrievers.py:239-253): concatenate, drop later items whose text was seen,
+ * stable sort by raw score descending, keep k_out. */
+int ezr_fusion_simple(const int32_t* ids_a, const double* scores_a, const int32_t* cnt_a, const int32_t* ids_b,
+                      const double* scores_b, const int32_t* cnt_b, int32_t n_queries, int32_t stride_in,
+                      const int32_t* canon, int32_t canon_base, int32_t k_out, int32_t* out_ids,
+                      double* out_scores, int32_t* out_counts, void* stream);
+
+/* ----------------------------------------------------------- profiling ---
+ * Per-kernel CUDA-event timing on the launching stream, for bench.py's roofline figures.
+ * ezr_profile_read synchronises on the recorded events and returns the summed duration of the
+ * kernel launches recorded in `slot` since the last reset. */
+typedef enum ezr_prof_slot {
+    EZR_PROF_BM25_SCORE = 0, /* bm25_score_kernel (fused top-k or score rows) */
+    EZR_PROF_DENSE_TC = 1,   /* dense_tc_kernel (tcgen05) */
+    EZR_PROF_DENSE_SIMT = 2, /* dense_scores_simt_kernel */
+    EZR_PROF_MERGE = 3,      /* merge / select kernels */
+    EZR_PROF_FUSE = 4,       /* rrf / simple fusion */
+    EZR_PROF_ENC_GEMM = 5,   /* encoder GEMMs */
+    EZR_PROF_ENC_ATTN = 6,   /* encoder attention */
+    EZR_PROF_ENC_OTHER = 7,  /* encoder norms / elementwise */
+    EZR_PROF_COUNT = 8
+} ezr_prof_slot;
+int ezr_profile_enable(int32_t on);
+int ezr_profile_reset(void);
+int ezr_profile_read(int32_t slot, double* total_ms, int32_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EASYRAG_B200_H */

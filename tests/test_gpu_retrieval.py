@@ -1,0 +1,366 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): bit-exact doc-id rank lists and scores for BM25 / RRF / fusion;
+cosine scores within 1e-3 for the bf16 dense route (and bit-exact where the inputs make the
+dot products exactly representable).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25 as obm
+from oracle import retrieve as ort
+from easyrag_b200 import synth, _lib, batched
+from easyrag_b200.index import Bm25Index, Bm25Stats, DenseIndex
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+COS_TOL = 1e-3          # north_star: "cosine scores within 1e-3 for bf16 embedding"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib_ready(lib_built):
+    _lib.require_cuda()
+
+
+def _pad_ids(ids, k):
+    out = np.full(k, -1, dtype=np.int64)
+    out[:len(ids)] = ids
+    return out
+
+
+def _check_bm25_topk(res, rows, k, allowed=None, id_base=0):
+    ids = res.ids.cpu().numpy()
+    sc = res.scores.cpu().numpy()
+    cnt = res.counts.cpu().numpy()
+    for q, row in enumerate(rows):
+        al = None
+        if allowed is not None:
+            al = allowed[q] if isinstance(allowed, list) else allowed
+        ref_i, ref_s = ort.bm25_topk_ids(row, k, al)
+        assert cnt[q] == ref_i.size, f"query {q}: count {cnt[q]} != {ref_i.size}"
+        assert np.array_equal(ids[q, :cnt[q]], ref_i + id_base), f"query {q}: ids differ"
+        assert sc[q, :cnt[q]].tobytes() == ref_s.astype(sc.dtype).tobytes(), f"query {q}: scores not bit-exact"
+        assert (ids[q, cnt[q]:] == -1).all()
+
+
+# ------------------------------------------------------------------ BM25 ----
+@pytest.fixture(scope="module")
+def c1():
+    """BASELINE config 1 shape: 10k chunks, V=50k, 100 queries of 4-12 terms."""
+    corpus = synth.make_sparse_corpus(10_000, 50_000, 20240922 + 1)
+    queries = synth.make_queries(corpus, 100, 20240922 + 101)
+    oracle = obm.OkapiCSR(corpus.doc_lists(), corpus.vocab)
+    stats = Bm25Stats.from_tokens(corpus.tokens, corpus.doc_ptr, corpus.vocab, bm25_type=0)
+    groups = synth.make_groups(corpus.n_docs, 4, 7)
+    index = Bm25Index(stats, device=DEV, doc_group=groups)
+    rows = [oracle.get_scores([int(t) for t in terms]) for terms in queries.term_lists()]
+    return dict(corpus=corpus, queries=queries, oracle=oracle, stats=stats, index=index, rows=rows, groups=groups)
+
+
+def test_bm25_weights_bit_exact(c1):
+    o, ix = c1["oracle"], c1["index"]
+    w = ix.post_w.cpu().numpy()
+    for t in np.random.default_rng(0).choice(np.nonzero(o.df)[0], 200, replace=False):
+        s, e = o.indptr[t], o.indptr[t + 1]
+        assert w[s:e].tobytes() == o.contributions(int(t)).tobytes()
+
+
+def test_bm25_score_rows_bit_exact(c1):
+    q = c1["queries"]
+    got = batched.bm25_scores(c1["index"], q.term_ptr, q.terms).cpu().numpy()
+    for i, row in enumerate(c1["rows"]):
+        assert got[i].tobytes() == row.tobytes(), f"query {i}"
+
+
+def test_bm25_score_rows_match_literal_reference_loop(c1):
+    # the literal per-term / per-document loop of rank_bm25 (what the reference executes), on a subset
+    docs = [list(map(int, d)) for d in c1["corpus"].doc_lists()[:1500]]
+    lit = obm.OkapiLiteral(docs)
+    sub = synth.SparseCorpus(tokens=c1["corpus"].tokens[:int(c1["corpus"].doc_ptr[1500])],
+                             doc_ptr=c1["corpus"].doc_ptr[:1501].clone(), vocab=c1["corpus"].vocab)
+    ix = Bm25Index(Bm25Stats.from_tokens(sub.tokens, sub.doc_ptr, sub.vocab), device=DEV)
+    q = c1["queries"]
+    got = batched.bm25_scores(ix, q.term_ptr[:6], q.terms[:int(q.term_ptr[5])]).cpu().numpy()
+    for i, terms in enumerate(q.term_lists()[:5]):
+        assert got[i].tobytes() == lit.get_scores([int(t) for t in terms]).tobytes()
+
+
+@pytest.mark.parametrize("k", [1, 10, 32])
+def test_bm25_topk_fused_bit_exact(c1, k):
+    q = c1["queries"]
+    res = batched.bm25_topk(c1["index"], q.term_ptr, q.terms, k)
+    _check_bm25_topk(res, c1["rows"], k)
+
+
+@pytest.mark.parametrize("k", [33, 192, 1024])
+def test_bm25_topk_large_k_bit_exact(c1, k):
+    q = c1["queries"]
+    nq = 12
+    res = batched.bm25_topk(c1["index"], q.term_ptr[:nq + 1], q.terms, k)
+    _check_bm25_topk(res, c1["rows"][:nq], k)
+
+
+@pytest.mark.parametrize("k", [10, 64])
+def test_bm25_topk_with_dir_filter(c1, k):
+    q = c1["queries"]
+    g = c1["groups"].numpy()
+    want = np.array([i % 6 - 1 for i in range(q.n)], dtype=np.int32)     # -1 none, 0..3 classes, 4 = no such class
+    want[want == 4] = -2
+    allowed = [None if w == -1 else (g == w) for w in want]
+    res = batched.bm25_topk(c1["index"], q.term_ptr, q.terms, k, q_group=torch.from_numpy(want))
+    _check_bm25_topk(res, c1["rows"], k, allowed=allowed)
+
+
+def test_bm25_edge_queries(c1):
+    # empty query, all-unknown query, duplicated term, term id out of range, long query (> 12 terms: two rounds)
+    o = c1["oracle"]
+    present = np.nonzero(o.df)[0]
+    lists = [[], [-1, -1], [int(present[3])] * 3, [c1["corpus"].vocab + 5, int(present[10])],
+             [int(t) for t in present[:30]]]
+    ptr = torch.tensor(np.cumsum([0] + [len(l) for l in lists]), dtype=torch.int32)
+    terms = torch.tensor([t for l in lists for t in l] or [0], dtype=torch.int32)
+    rows = [o.get_scores(l) for l in lists]
+    res = batched.bm25_topk(c1["index"], ptr, terms, 10)
+    _check_bm25_topk(res, rows, 10)
+    assert res.counts[0].item() == 0 and res.counts[1].item() == 0
+    got = batched.bm25_scores(c1["index"], ptr, terms).cpu().numpy()
+    for i, row in enumerate(rows):
+        assert got[i].tobytes() == row.tobytes()
+
+
+@pytest.mark.parametrize("n_docs", [1, 2, 8191, 8192, 8193, 20000])
+def test_bm25_ragged_sizes_and_ties(n_docs):
+    # documents duplicated pairwise -> exact score ties -> canonical order must put the higher id first
+    base = synth.make_sparse_corpus((n_docs + 1) // 2, 300, 77, mean_len=12, min_len=0, max_len=40)
+    docs = base.doc_lists()
+    docs = (docs + docs)[:n_docs]
+    tokens = torch.from_numpy(np.concatenate(docs) if sum(map(len, docs)) else np.zeros(0, np.int32)).to(torch.int32)
+    ptr = torch.tensor(np.cumsum([0] + [len(d) for d in docs]), dtype=torch.int64)
+    if tokens.numel() == 0:
+        pytest.skip("degenerate")
+    corpus = synth.SparseCorpus(tokens=tokens, doc_ptr=ptr, vocab=300)
+    o = obm.OkapiCSR(docs, 300)
+    ix = Bm25Index(Bm25Stats.from_tokens(tokens, ptr, 300), device=DEV)
+    qs = synth.make_queries(corpus, 20, 78, min_terms=1, max_terms=5)
+    rows = [o.get_scores([int(t) for t in terms]) for terms in qs.term_lists()]
+    for k in (3, 10):
+        _check_bm25_topk(batched.bm25_topk(ix, qs.term_ptr, qs.terms, k), rows, k)
+
+
+def test_bm25s_float32_bit_exact():
+    corpus = synth.make_sparse_corpus(9000, 3000, 5, mean_len=60, min_len=1, max_len=200)
+    qs = synth.make_queries(corpus, 40, 6)
+    o = obm.Bm25sLucene(corpus.doc_lists(), corpus.vocab)
+    ix = Bm25Index(Bm25Stats.from_tokens(corpus.tokens, corpus.doc_ptr, corpus.vocab, bm25_type=1), device=DEV)
+    assert ix.post_w.dtype == torch.float32
+    assert ix.post_w.cpu().numpy().tobytes() == o.post_w.tobytes()
+    rows = [o.get_scores([int(t) for t in terms]) for terms in qs.term_lists()]
+    got = batched.bm25_scores(ix, qs.term_ptr, qs.terms).cpu().numpy()
+    for i, row in enumerate(rows):
+        assert got[i].tobytes() == row.tobytes()
+    _check_bm25_topk(batched.bm25_topk(ix, qs.term_ptr, qs.terms, 10), rows, 10)
+
+
+def test_bm25_sharded_index_equals_global(c1):
+    # doc-partitioned postings with GLOBAL idf/avgdl: merging shard lists reproduces the unsharded list
+    q, k = c1["queries"], 10
+    n = c1["stats"].n_docs
+    cand_s, cand_i = [], []
+    for lo, hi in ((0, 4096), (4096, 8192), (8192, n)):
+        ix = Bm25Index(c1["stats"], device=DEV, doc_lo=lo, doc_hi=hi)
+        r = batched.bm25_topk(ix, q.term_ptr, q.terms, k)
+        cand_s.append(r.scores)
+        cand_i.append(r.ids)
+    merged = batched.merge_topk(torch.cat(cand_s, 1).contiguous(), torch.cat(cand_i, 1).contiguous(), k)
+    _check_bm25_topk(merged, c1["rows"], k)
+
+
+# --------------------------------------------------------- generic select ----
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("k", [1, 10, 33, 256, 1024])
+def test_select_rows_matches_canonical_order(dtype, k):
+    g = torch.Generator().manual_seed(k)
+    s = (torch.rand(7, 50_000, generator=g, dtype=torch.float64) * 50).round() / 50 - 0.2    # many ties, some <= 0
+    s = s.to(dtype)
+    res = batched.select_rows(s.to(DEV), k, positive_only=True)
+    _check_bm25_topk(res, [r.numpy() for r in s], k)
+    res = batched.select_rows(s.to(DEV), k, positive_only=False)
+    ids = res.ids.cpu().numpy()
+    for q in range(s.shape[0]):
+        ref = ort.canonical_order(s[q].numpy())[:k]
+        assert np.array_equal(ids[q], ref)
+
+
+def test_select_rows_single_long_row_uses_parts():
+    s = torch.rand(1, 1_000_003, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    res = batched.select_rows(s.to(DEV), 100)
+    assert np.array_equal(res.ids.cpu().numpy()[0], ort.canonical_order(s[0].numpy())[:100])
+
+
+# ----------------------------------------------------------------- dense ----
+def _dense_case(n, d, q, seed, integer=False):
+    g = torch.Generator().manual_seed(seed)
+    if integer:
+        # small integers: every product and partial sum is exact in bf16/fp32 -> any summation order agrees
+        c = torch.randint(-2, 3, (n, d), generator=g).float()
+        qq = torch.randint(-2, 3, (q, d), generator=g).float()
+    else:
+        c = synth.make_dense_corpus(n, d, seed).float()
+        qq = synth.make_dense_queries(c.to(torch.bfloat16), q, seed + 1).float()
+    return c.to(torch.bfloat16), qq.to(torch.bfloat16)
+
+
+def _check_dense(res, c, qv, k, allowed=None, exact=False, id_base=0):
+    cf, qf = c.float().numpy(), qv.float().numpy()
+    ref_i, ref_s = ort.dense_topk(cf, qf, k, allowed)
+    ids, sc, cnt = res.ids.cpu().numpy(), res.scores.cpu().numpy(), res.counts.cpu().numpy()
+    sims = qf @ cf.T
+    for q in range(qf.shape[0]):
+        n_ref = int((ref_i[q] >= 0).sum())
+        assert cnt[q] == n_ref
+        if exact:
+            assert np.array_equal(ids[q, :n_ref], ref_i[q, :n_ref] + id_base), f"query {q}"
+            assert np.array_equal(sc[q, :n_ref], ref_s[q, :n_ref])
+            continue
+        got = ids[q, :n_ref] - id_base
+        # every returned score is the true cosine of the returned id, to 1e-3
+        assert np.abs(sc[q, :n_ref] - sims[q, got]).max() <= COS_TOL
+        # sorted descending, and the set is the oracle's up to scores closer than the tolerance
+        assert (np.diff(sc[q, :n_ref]) <= 0).all()
+        if n_ref:
+            kth = ref_s[q, n_ref - 1]
+            assert (sims[q, got] >= kth - COS_TOL).all()
+            assert len(set(got.tolist())) == n_ref
+        if allowed is not None:
+            m = allowed[q] if allowed.ndim == 2 else allowed
+            assert m[got].all()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])          # 1 = generic SIMT kernel, 2 = tcgen05
+@pytest.mark.parametrize("n,d,q,k", [(5000, 128, 130, 10), (777, 768, 3, 5), (64, 64, 1, 16), (20_000, 768, 257, 10),
+                                     (100, 256, 5, 12)])
+def test_dense_exact_integer_inputs(kernel, n, d, q, k):
+    c, qv = _dense_case(n, d, q, 100 + n, integer=True)
+    L = _lib.lib()
+    _lib.check(L.ezr_dense_set_kernel(kernel))
+    try:
+        res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), k)
+        assert L.ezr_dense_last_kernel() == (b"simt" if kernel == 1 else b"tcgen05")
+    finally:
+        L.ezr_dense_set_kernel(0)
+    _check_dense(res, c, qv, k, exact=True)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_dense_unit_vectors_within_tolerance(kernel):
+    c, qv = _dense_case(30_000, 768, 200, 7)
+    L = _lib.lib()
+    _lib.check(L.ezr_dense_set_kernel(kernel))
+    try:
+        res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), 10)
+    finally:
+        L.ezr_dense_set_kernel(0)
+    _check_dense(res, c, qv, 10)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_dense_dir_filter_and_id_base(kernel):
+    c, qv = _dense_case(9000, 256, 70, 11, integer=True)
+    groups = synth.make_groups(9000, 4, 12)
+    want = torch.tensor([i % 6 - 1 for i in range(70)], dtype=torch.int32)
+    want[want == 4] = -2
+    g = groups.numpy()
+    allowed = np.stack([np.ones(9000, bool) if w == -1 else (g == w) for w in want.tolist()])
+    L = _lib.lib()
+    _lib.check(L.ezr_dense_set_kernel(kernel))
+    try:
+        res = batched.dense_topk(DenseIndex(c, device=DEV, doc_group=groups, row_lo=1000), qv.to(DEV), 10, q_group=want)
+    finally:
+        L.ezr_dense_set_kernel(0)
+    _check_dense(res, c, qv, 10, allowed=allowed, exact=True, id_base=1000)
+
+
+def test_dense_large_k_goes_through_generic_kernel():
+    c, qv = _dense_case(4000, 192, 4, 13, integer=True)       # dim 192 % 64 == 0 but k = 288 > 16
+    res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), 288)
+    assert _lib.lib().ezr_dense_last_kernel() == b"simt"
+    _check_dense(res, c, qv, 288, exact=True)
+    c, qv = _dense_case(300, 100, 4, 14, integer=True)        # odd dim
+    res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), 10)
+    _check_dense(res, c, qv, 10, exact=True)
+
+
+def test_dense_fewer_rows_than_k():
+    c, qv = _dense_case(7, 64, 3, 15, integer=True)
+    res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), 10)
+    _check_dense(res, c, qv, 10, exact=True)
+    assert (res.counts.cpu().numpy() == 7).all()
+
+
+# ---------------------------------------------------------------- fusion ----
+def _random_lists(rng, n_docs, nq, width, dup_frac=0.2):
+    canon = synth.make_duplicates(n_docs, dup_frac, int(rng.integers(1 << 30))).numpy()
+    ids_a = np.full((nq, width), -1, np.int32)
+    ids_b = np.full((nq, width), -1, np.int32)
+    cnt_a = rng.integers(0, width + 1, nq).astype(np.int32)
+    cnt_b = rng.integers(0, width + 1, nq).astype(np.int32)
+    for q in range(nq):
+        ids_a[q, :cnt_a[q]] = rng.permutation(n_docs)[:cnt_a[q]]
+        ids_b[q, :cnt_b[q]] = rng.permutation(n_docs)[:cnt_b[q]]
+    return canon, ids_a, cnt_a, ids_b, cnt_b
+
+
+@pytest.mark.parametrize("width,k_out", [(10, 10), (10, 4), (37, 256), (288, 256), (1024, 6)])
+def test_rrf_bit_exact(width, k_out):
+    rng = np.random.default_rng(width)
+    n_docs, nq = max(60, width * 2), 50
+    canon, ids_a, cnt_a, ids_b, cnt_b = _random_lists(rng, n_docs, nq, width)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    res = batched.rrf_fuse(t(ids_a), t(cnt_a), t(ids_b), t(cnt_b), k_out, K=60, canon=t(canon.astype(np.int32)))
+    ids, sc, cnt = res.ids.cpu().numpy(), res.scores.cpu().numpy(), res.counts.cpu().numpy()
+    for q in range(nq):
+        ref_i, ref_s = ort.rrf_ids([ids_a[q, :cnt_a[q]], ids_b[q, :cnt_b[q]]], canon, K=60, topk=k_out)
+        assert cnt[q] == ref_i.size
+        assert np.array_equal(ids[q, :cnt[q]], ref_i)
+        assert sc[q, :cnt[q]].tobytes() == ref_s.tobytes()
+        assert (ids[q, cnt[q]:] == -1).all()
+
+
+@pytest.mark.parametrize("width,k_out", [(10, 10), (192, 256), (50, 7)])
+def test_simple_fusion_bit_exact(width, k_out):
+    rng = np.random.default_rng(1000 + width)
+    n_docs, nq = max(60, width * 2), 40
+    canon, ids_a, cnt_a, ids_b, cnt_b = _random_lists(rng, n_docs, nq, width)
+    sa = np.round(rng.random((nq, width)) * 20, 0) / 4           # coarse -> ties between the two routes
+    sb = np.round(rng.random((nq, width)) * 20, 0) / 4
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    res = batched.fusion_simple(t(ids_a), t(sa), t(cnt_a), t(ids_b), t(sb), t(cnt_b), k_out,
+                                canon=t(canon.astype(np.int32)))
+    ids, sc, cnt = res.ids.cpu().numpy(), res.scores.cpu().numpy(), res.counts.cpu().numpy()
+    for q in range(nq):
+        ref_i, ref_s = ort.fusion_ids([ids_a[q, :cnt_a[q]], ids_b[q, :cnt_b[q]]],
+                                      [sa[q, :cnt_a[q]], sb[q, :cnt_b[q]]], canon, topk=k_out)
+        assert cnt[q] == ref_i.size
+        assert np.array_equal(ids[q, :cnt[q]], ref_i)
+        assert sc[q, :cnt[q]].tobytes() == ref_s.tobytes()
+
+
+# ------------------------------------------------------- hybrid, one GPU ----
+def test_hybrid_dense_bm25_rrf_matches_oracle(c1):
+    n, dim, k = c1["stats"].n_docs, 256, 10
+    c, qv = _dense_case(n, dim, c1["queries"].n, 31, integer=True)
+    canon = synth.make_duplicates(n, 0.05, 32)
+    ranker = batched.CoarseRanker(DenseIndex(c, device=DEV), c1["index"], canon=canon)
+    q = c1["queries"]
+    fused, sparse, dense = ranker.hybrid(qv.to(DEV), q.term_ptr.to(DEV), q.terms.to(DEV), k, k, k)
+    torch.cuda.synchronize()
+    _check_bm25_topk(sparse, c1["rows"], k)
+    _check_dense(dense, c, qv, k, exact=True)
+    d_ref, _ = ort.dense_topk(c.float().numpy(), qv.float().numpy(), k)
+    f_ids, f_sc, f_cnt = fused.ids.cpu().numpy(), fused.scores.cpu().numpy(), fused.counts.cpu().numpy()
+    for i, row in enumerate(c1["rows"]):
+        s_ref, _ = ort.bm25_topk_ids(row, k)
+        ref_i, ref_s = ort.rrf_ids([s_ref, d_ref[i]], canon.numpy(), K=60, topk=k)
+        assert np.array_equal(f_ids[i, :f_cnt[i]], ref_i)
+        assert f_sc[i, :f_cnt[i]].tobytes() == ref_s.tobytes()

@@ -1,0 +1,126 @@
+"""CPU: host-side logic of the product + the C-ABI library loads and exports every declared symbol."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25 as obm
+from easyrag_b200 import synth, _lib
+from easyrag_b200.index import Bm25Stats
+from easyrag_b200 import dist as ezdist
+from easyrag_b200 import schema
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_header_symbol(lib_built):
+    header = (ROOT / "include" / "easyrag_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(ezr_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    handle = ctypes.CDLL(str(lib_built))
+    missing = [s for s in sorted(declared) if not hasattr(handle, s)]
+    assert not missing, f"symbols declared in include/easyrag_b200.h but not exported: {missing}"
+    # and the ctypes table covers the same set
+    assert declared == set(_lib.SIGNATURES) or declared <= set(_lib.SIGNATURES)
+
+
+def test_library_loads_without_gpu(lib_built):
+    L = _lib.lib()
+    assert L.ezr_version() >= 100
+    assert isinstance(L.ezr_last_error(), bytes)
+    # pure argument validation needs no device
+    assert L.ezr_dense_set_kernel(7) == -1
+    assert b"dense_set_kernel" in L.ezr_last_error()
+    assert L.ezr_dense_set_kernel(0) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_cuda(lib_built):
+    with pytest.raises(_lib.EzrError):
+        _lib.require_cuda()
+    from easyrag_b200.retrievers import HybridRetriever
+    from easyrag_b200.schema import NodeWithScore, TextNode
+    a = [NodeWithScore(TextNode("x"), 1.0)]
+    with pytest.raises(_lib.EzrError):
+        HybridRetriever.reciprocal_rank_fusion([a, a])
+
+
+@pytest.mark.parametrize("bm25_type", [0, 1])
+def test_bm25_stats_match_oracle(bm25_type):
+    c = synth.make_sparse_corpus(500, 400, 11, mean_len=30, min_len=0, max_len=90)
+    st = Bm25Stats.from_tokens(c.tokens, c.doc_ptr, c.vocab, bm25_type=bm25_type)
+    docs = c.doc_lists()
+    if bm25_type == 0:
+        o = obm.OkapiCSR(docs, c.vocab)
+        assert st.avgdl == o.avgdl
+        assert st.average_idf == o.average_idf          # sequential float64 sum, first-seen order
+        assert st.idf.tobytes() == o.idf.tobytes()
+        assert np.array_equal(st.post_tf.numpy(), o.post_tf)
+    else:
+        o = obm.Bm25sLucene(docs, c.vocab)
+        assert np.array_equal(st.idf.astype(np.float32), o.idf32)
+    assert np.array_equal(st.indptr.numpy(), o.indptr)
+    assert np.array_equal(st.post_doc.numpy(), o.post_doc)
+    assert np.array_equal(st.df.numpy(), o.df)
+
+
+def test_bm25_stats_empty_corpus_raises_like_reference():
+    with pytest.raises(ZeroDivisionError):
+        Bm25Stats.from_tokens(torch.zeros(0, dtype=torch.int32), torch.zeros(1, dtype=torch.int64), 4)
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (0, 1, 63, 64, 1000, 125000 * 8 + 3):
+        for world in (1, 2, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = ezdist.shard_bounds(n, world, r, align=64)
+                assert lo == prev and lo <= hi <= n
+                prev = hi
+            assert prev == n
+
+
+def test_pack_unpack_roundtrip():
+    q, k, world = 5, 3, 4
+    lay = ezdist.RecordLayout(q, k, 8)
+    g = torch.Generator().manual_seed(0)
+    parts, bufs = [], []
+    for r in range(world):
+        ds = torch.rand(q, k, generator=g)
+        di = torch.randint(0, 100, (q, k), generator=g, dtype=torch.int32)
+        ss = torch.rand(q, k, generator=g, dtype=torch.float64)
+        si = torch.randint(0, 100, (q, k), generator=g, dtype=torch.int32)
+        parts.append((ds, di, ss, si))
+        bufs.append(ezdist.pack_records(lay, ds, di, ss, si))
+    gathered = torch.stack(bufs)
+    ds, di, ss, si = ezdist.unpack_records(lay, gathered, world)
+    assert ds.shape == (q, world * k) and ss.dtype == torch.float64
+    for r in range(world):
+        assert torch.equal(ds[:, r * k:(r + 1) * k], parts[r][0])
+        assert torch.equal(di[:, r * k:(r + 1) * k], parts[r][1])
+        assert torch.equal(ss[:, r * k:(r + 1) * k], parts[r][2])
+        assert torch.equal(si[:, r * k:(r + 1) * k], parts[r][3])
+
+
+def test_schema_surface():
+    n = schema.TextNode("hello", metadata={"dir": "a"})
+    s = schema.NodeWithScore(n, 1.5)
+    assert s.get_content() == "hello" and s.metadata["dir"] == "a" and s.node is n
+    s.score = 2.0                                        # rerankers overwrite it (rerankers.py:92)
+    f = schema.build_qdrant_filters("emsplus")
+    assert schema.filter_conditions(f) == {"dir": "emsplus"}
+    assert schema.filter_conditions(None) is None
+
+
+def test_get_node_content_views():
+    from easyrag_b200.retrievers import get_node_content
+    n = schema.TextNode("body", metadata={"file_path": "fp", "know_path": "kp"})
+    assert get_node_content(n, 0) == "body"
+    assert get_node_content(n, 1) == "###\nfp\n\nbody"
+    assert get_node_content(n, 2) == "###\nkp\n\nbody"
+    assert get_node_content(n, 4) == "fp" and get_node_content(n, 5) == "kp"
+    assert get_node_content(schema.TextNode("b"), 5) == ""

@@ -1,0 +1,157 @@
+"""CPU: pin the oracle against the only published vectors for this path, and its variants against each other."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import bm25 as obm
+from oracle import retrieve as ort
+from easyrag_b200 import synth
+
+KAT = json.loads((Path(__file__).parent / "golden" / "kat.json").read_text())
+
+
+def test_okapi_known_answer():
+    k = KAT["bm25_okapi"]
+    corpus = [d.split(" ") for d in k["corpus"]]
+    m = obm.OkapiLiteral(corpus, k1=k["k1"], b=k["b"], epsilon=k["epsilon"])
+    got = m.get_scores(k["query"])
+    assert np.allclose(got, k["scores"], atol=10 ** -k["decimals"])
+    assert got[0] == 0.0 and got[2] == 0.0
+
+
+def test_okapi_known_answer_csr():
+    k = KAT["bm25_okapi"]
+    corpus = [d.split(" ") for d in k["corpus"]]
+    vocab = {}
+    docs = [np.array([vocab.setdefault(w, len(vocab)) for w in d]) for d in corpus]
+    m = obm.OkapiCSR(docs, len(vocab))
+    got = m.get_scores([vocab[w] for w in k["query"]])
+    assert np.allclose(got, k["scores"], atol=1e-8)
+
+
+def _small_corpus(n=400, vocab=300, seed=3):
+    c = synth.make_sparse_corpus(n, vocab, seed, mean_len=40, min_len=0, max_len=120)
+    q = synth.make_queries(c, 25, seed + 1, min_terms=1, max_terms=9)
+    return c, q
+
+
+def test_csr_bit_identical_to_literal():
+    c, q = _small_corpus()
+    docs = c.doc_lists()
+    lit = obm.OkapiLiteral([list(map(int, d)) for d in docs])
+    csr = obm.OkapiCSR(docs, c.vocab)
+    assert lit.avgdl == csr.avgdl
+    assert lit.average_idf == csr.average_idf
+    for t, v in lit.idf.items():
+        assert csr.idf[t] == v
+    for terms in q.term_lists():
+        a = lit.get_scores([int(t) for t in terms])
+        b = csr.get_scores([int(t) for t in terms])
+        assert a.tobytes() == b.tobytes()          # bit-exact, including the float64 sum order
+
+
+def test_negative_idf_epsilon_floor():
+    # a term in more than half the documents gets epsilon * average_idf (rank_bm25 _calc_idf)
+    docs = [np.array([0, 1]), np.array([0, 2]), np.array([0, 3]), np.array([4])]
+    csr = obm.OkapiCSR(docs, 5)
+    lit = obm.OkapiLiteral([list(map(int, d)) for d in docs])
+    assert lit.idf[0] == 0.25 * lit.average_idf
+    assert csr.idf[0] == lit.idf[0]
+    assert np.array_equal(csr.get_scores([0, 4, 0]), lit.get_scores([0, 4, 0]))
+
+
+def test_rrf_known_answers():
+    r = KAT["rrf"]
+    A, B_, C = ort.ONode("a", 0), ort.ONode("b", 1), ort.ONode("c", 2)
+    sparse = [ort.OScored(A, 3.0), ort.OScored(B_, 2.0)]
+    dense = [ort.OScored(A, 0.9), ort.OScored(C, 0.8)]
+    out = ort.reciprocal_rank_fusion([sparse, dense], K=r["K"])
+    assert out[0].node is A and out[0].score == r["both_rank1"]
+    assert out[0] is dense[0]                      # last writer wins: the dense list's object (retrievers.py:264)
+    # tie between sparse-only rank 2 and dense-only rank 2 resolves sparse first (stable sort)
+    assert [o.node.text for o in out] == ["a", "b", "c"]
+    assert out[1].score == out[2].score == 1 / 62
+    assert ort.reciprocal_rank_fusion([[ort.OScored(A, 1.0)], []])[0].score == r["one_list_rank1"]
+    out = ort.reciprocal_rank_fusion([[ort.OScored(A, 1.0)], [ort.OScored(B_, 1.0), ort.OScored(A, 0.5)]])
+    assert out[0].node is A and out[0].score == r["sparse1_dense2"]
+
+
+def test_rrf_ids_matches_object_form():
+    rng = np.random.default_rng(0)
+    n = 50
+    canon = np.arange(n)
+    canon[7] = 3
+    canon[20] = 3
+    canon[31] = 30
+    nodes = [ort.ONode(f"t{canon[i]}", i) for i in range(n)]
+    for _ in range(20):
+        a = rng.permutation(n)[:rng.integers(0, 12)]
+        b = rng.permutation(n)[:rng.integers(0, 12)]
+        la = [ort.OScored(nodes[i], 1.0) for i in a]
+        lb = [ort.OScored(nodes[i], 1.0) for i in b]
+        ref = ort.reciprocal_rank_fusion([la, lb], topk=8)
+        ids, sc = ort.rrf_ids([a, b], canon, topk=8)
+        assert [o.node.idx for o in ref] == ids.tolist()
+        assert [o.score for o in ref] == sc.tolist()
+
+
+def test_fusion_ids_matches_object_form():
+    rng = np.random.default_rng(1)
+    n = 40
+    canon = np.arange(n)
+    canon[5] = 2
+    canon[9] = 2
+    nodes = [ort.ONode(f"t{canon[i]}", i) for i in range(n)]
+    for _ in range(20):
+        a = rng.permutation(n)[:rng.integers(0, 10)]
+        b = rng.permutation(n)[:rng.integers(0, 10)]
+        sa = np.round(rng.random(len(a)), 1)           # coarse scores -> ties
+        sb = np.round(rng.random(len(b)), 1)
+        la = [ort.OScored(nodes[i], float(s)) for i, s in zip(a, sa)]
+        lb = [ort.OScored(nodes[i], float(s)) for i, s in zip(b, sb)]
+        ref = ort.fusion([la, lb], topk=7)
+        ids, sc = ort.fusion_ids([a, b], [sa, sb], canon, topk=7)
+        assert [o.node.idx for o in ref] == ids.tolist()
+        assert [o.score for o in ref] == sc.tolist()
+
+
+def test_filter_semantics():
+    scores = np.array([0.0, 2.0, -1.0, 2.0, 5.0, 0.5])
+    nodes = [ort.ONode(f"n{i}", i, {"dir": "a" if i % 2 else "b"}) for i in range(6)]
+    out = ort.bm25_filter(scores, nodes, k=10)
+    assert [o.node.idx for o in out] == [4, 3, 1, 5]       # ties: higher index first; <=0 dropped
+    out = ort.bm25_filter(scores, nodes, k=2, filter_dict={"dir": "a"})
+    assert [o.node.idx for o in out] == [3, 1]
+    ids, sc = ort.bm25_topk_ids(scores, 2, np.array([i % 2 == 1 for i in range(6)]))
+    assert ids.tolist() == [3, 1] and sc.tolist() == [2.0, 2.0]
+
+
+def test_literal_argsort_agrees_outside_ties():
+    # the reference's argsort()[::-1] (retrievers.py:192) is not stable: equal only up to order inside tie groups
+    rng = np.random.default_rng(5)
+    scores = np.round(rng.random(20000), 3)
+    nodes = [ort.ONode("", i) for i in range(scores.size)]
+    a = ort.bm25_filter(scores, nodes, 50, literal_argsort=True)
+    b = ort.bm25_filter(scores, nodes, 50)
+    assert [x.score for x in a] == [x.score for x in b]
+    kth = b[-1].score
+    sa = {x.node.idx for x in a if x.score > kth}
+    sb = {x.node.idx for x in b if x.score > kth}
+    assert sa == sb
+
+
+def test_tokenizer_shim():
+    tk = synth.PseudoWordTokenizer()
+    text = synth.ids_to_text([3, 5, 3])
+    assert ort.tokenize_and_remove_stopwords(tk, text, {"w5"}) == ["w3", "w3"]
+
+
+def test_bm25s_basic_properties():
+    c, q = _small_corpus(n=200, vocab=150, seed=9)
+    m = obm.Bm25sLucene(c.doc_lists(), c.vocab)
+    for terms in q.term_lists()[:10]:
+        s = m.get_scores([int(t) for t in terms])
+        assert s.dtype == np.float32 and s.shape == (200,)
+        assert (s >= 0).all()                          # lucene idf is always positive
