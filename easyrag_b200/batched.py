@@ -188,17 +188,21 @@ def fusion_simple(ids_a: torch.Tensor, sc_a: torch.Tensor, cnt_a: torch.Tensor, 
 class CoarseRanker:
     """dense + BM25 + RRF for query batches on one GPU (``HybridRetriever._aretrieve``, retrievers.py:276-291).
 
-    The two routes are independent until the fusion, so they run on two CUDA streams; the RRF
-    kernel joins them.  All buffers are preallocated per (batch size, k) and reused.
+    The two routes are independent until the fusion.  ``overlap=True`` issues them on two CUDA streams and
+    lets the RRF kernel join them; the default issues them back to back on the caller's stream (the dense
+    kernel occupies all shared memory of every SM, so the routes cannot co-reside anyway and per-kernel
+    timing stays clean).  All buffers are preallocated per (batch size, k) and reused.
     """
 
-    def __init__(self, dense: DenseIndex, sparse: Bm25Index, canon: Optional[torch.Tensor] = None):
+    def __init__(self, dense: DenseIndex, sparse: Bm25Index, canon: Optional[torch.Tensor] = None,
+                 overlap: bool = False):
         assert dense.device == sparse.device
         self.dense, self.sparse = dense, sparse
         self.device = dense.device
         self.canon = None if canon is None else canon.to(device=self.device, dtype=torch.int32).contiguous()
-        self.s_dense = torch.cuda.Stream(device=self.device)
-        self.s_sparse = torch.cuda.Stream(device=self.device)
+        self.overlap = overlap
+        self.s_dense = torch.cuda.Stream(device=self.device) if overlap else None
+        self.s_sparse = torch.cuda.Stream(device=self.device) if overlap else None
         self.ws_dense = Workspace(self.device)
         self.ws_sparse = Workspace(self.device)
         self._bufs = {}
@@ -215,23 +219,33 @@ class CoarseRanker:
             )
         return self._bufs[key]
 
+    def routes(self, queries: torch.Tensor, q_ptr: torch.Tensor, q_terms: torch.Tensor, k: int, k_out: int,
+               q_group: Optional[torch.Tensor] = None) -> Tuple[TopK, TopK, TopK]:
+        """Both routes over this ranker's (shard of the) corpus -> (dense, sparse, fused-output buffer)."""
+        nq = queries.shape[0]
+        d_out, s_out, f_out = self._buffers(nq, k, k, k_out)
+        cur = torch.cuda.current_stream(self.device)
+        if self.overlap:
+            self.s_dense.wait_stream(cur)
+            self.s_sparse.wait_stream(cur)
+            with torch.cuda.stream(self.s_sparse):
+                bm25_topk(self.sparse, q_ptr, q_terms, k, q_group=q_group, ws=self.ws_sparse, stream=self.s_sparse,
+                          out=s_out)
+            with torch.cuda.stream(self.s_dense):
+                dense_topk(self.dense, queries, k, q_group=q_group, ws=self.ws_dense, stream=self.s_dense, out=d_out)
+            cur.wait_stream(self.s_sparse)
+            cur.wait_stream(self.s_dense)
+        else:
+            bm25_topk(self.sparse, q_ptr, q_terms, k, q_group=q_group, ws=self.ws_sparse, stream=cur, out=s_out)
+            dense_topk(self.dense, queries, k, q_group=q_group, ws=self.ws_dense, stream=cur, out=d_out)
+        return d_out, s_out, f_out
+
     def hybrid(self, queries: torch.Tensor, q_ptr: torch.Tensor, q_terms: torch.Tensor, k_dense: int = 10,
                k_sparse: int = 10, k_out: int = 10, K: int = 60, q_group: Optional[torch.Tensor] = None
                ) -> Tuple[TopK, TopK, TopK]:
         """Returns (fused, sparse, dense).  Inputs must already be on the device."""
-        nq = queries.shape[0]
         if k_dense != k_sparse:
             raise ValueError("the fused path keeps both routes at the same k (pad the shorter list upstream)")
-        d_out, s_out, f_out = self._buffers(nq, k_dense, k_sparse, k_out)
-        cur = torch.cuda.current_stream(self.device)
-        self.s_dense.wait_stream(cur)
-        self.s_sparse.wait_stream(cur)
-        with torch.cuda.stream(self.s_sparse):
-            bm25_topk(self.sparse, q_ptr, q_terms, k_sparse, q_group=q_group, ws=self.ws_sparse, stream=self.s_sparse,
-                      out=s_out)
-        with torch.cuda.stream(self.s_dense):
-            dense_topk(self.dense, queries, k_dense, q_group=q_group, ws=self.ws_dense, stream=self.s_dense, out=d_out)
-        cur.wait_stream(self.s_sparse)
-        cur.wait_stream(self.s_dense)
-        rrf_fuse(s_out.ids, s_out.counts, d_out.ids, d_out.counts, k_out, K=K, canon=self.canon, stream=cur, out=f_out)
+        d_out, s_out, f_out = self.routes(queries, q_ptr, q_terms, k_dense, k_out, q_group=q_group)
+        rrf_fuse(s_out.ids, s_out.counts, d_out.ids, d_out.counts, k_out, K=K, canon=self.canon, out=f_out)
         return f_out, s_out, d_out

@@ -109,8 +109,9 @@ static int fuse_launch(const int32_t* ids_a, const double* sc_a, const int32_t* 
     if (n_queries == 0) return EZR_OK;
     const size_t smem = (size_t)2 * stride_in * (8 + 4 * 4);
     static bool attr_done[2] = {false, false};
-    if (smem > 48 * 1024 && !attr_done[RRF ? 1 : 0]) {
-        EZR_CUDA(cudaFuncSetAttribute(fuse_kernel<RRF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFuseMaxIn * 24));
+    if (!attr_done[RRF ? 1 : 0]) {
+        EZR_CUDA(cudaFuncSetAttribute(fuse_kernel<RRF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      2 * kFuseMaxIn * 24));
         attr_done[RRF ? 1 : 0] = true;
     }
     ProfScope prof(EZR_PROF_FUSE, st);

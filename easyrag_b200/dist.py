@@ -103,16 +103,7 @@ class ShardedCoarseRanker:
         from . import batched
         r = self.ranker
         nq = queries.shape[0]
-        cur = torch.cuda.current_stream(r.device)
-        r.s_dense.wait_stream(cur)
-        r.s_sparse.wait_stream(cur)
-        d_out, s_out, f_out = r._buffers(nq, k, k, k_out)
-        with torch.cuda.stream(r.s_sparse):
-            batched.bm25_topk(r.sparse, q_ptr, q_terms, k, q_group=q_group, ws=r.ws_sparse, stream=r.s_sparse, out=s_out)
-        with torch.cuda.stream(r.s_dense):
-            batched.dense_topk(r.dense, queries, k, q_group=q_group, ws=r.ws_dense, stream=r.s_dense, out=d_out)
-        cur.wait_stream(r.s_sparse)
-        cur.wait_stream(r.s_dense)
+        d_out, s_out, f_out = r.routes(queries, q_ptr, q_terms, k, k_out, q_group=q_group)
         layout = RecordLayout(nq, k, 8 if s_out.scores.dtype == torch.float64 else 4)
         key = (nq, k, layout.sparse_bytes)
         if key not in self._pack:
