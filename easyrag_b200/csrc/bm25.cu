@@ -93,7 +93,7 @@ struct Bm25Params {
 
 // MODE 0: fused top-k (k<=32) -> per-(query,range) partial lists.  MODE 1: write the score row.
 template <typename S, int MODE>
-__global__ void __launch_bounds__(kBmThreads)
+__global__ void __launch_bounds__(kBmThreads, 3)
 bm25_score_kernel(const Bm25Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S* acc = reinterpret_cast<S*>(smem_raw);
@@ -169,9 +169,74 @@ bm25_score_kernel(const Bm25Params p) {
         return;
     }
 
-    // ---- fused top-k: per-warp lists, then warp 0 merges them ----
+    // ---- fused top-k from shared memory: threshold -> compact -> rank ----
+    // 1. every half-warp finds the best score among the 256 documents it scans; the k-th largest of those 32
+    //    group maxima is a lower bound of the range's k-th best score (they are 32 distinct documents), and a
+    //    tight one: on average only ~k/2 extra documents pass it.
+    // 2. documents with score >= that bound are appended to a small candidate list (shared-memory atomics).
+    // 3. each candidate counts how many candidates rank before it under the canonical order and writes itself
+    //    to that output slot.  No sort, no serial insertion chain.
+    // Exact ties at the bound (or fewer than k non-empty groups) can overflow the list; then the robust
+    // warp-shuffle selection below takes over.
     const int lane = tid & 31, warp = tid >> 5;
     const int want = p.q_group ? p.q_group[q] : -1;
+    __shared__ S s_thr;
+    __shared__ int s_cnt;
+    S tmax = (S)0;
+    for (int i = tid; i < rn; i += kBmThreads) {
+        const S s = acc[i];
+        if (s > tmax) {
+            if (want == -1 || p.doc_group[rbase + i] == want) tmax = s;
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const S other = __shfl_xor_sync(0xffffffffu, tmax, o);
+        tmax = other > tmax ? other : tmax;
+    }
+    if ((lane & 15) == 0) s_ws[tid >> 4] = tmax;           // 32 group maxima (0 = group has no positive score)
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    if (warp == 0) {
+        const S mine = s_ws[lane];
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const S o = s_ws[j];
+            rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
+        }
+        if (rank == p.k - 1) s_thr = mine;                 // ranks are a permutation: exactly one lane writes
+    }
+    __syncthreads();
+    const S thr = s_thr;                                   // 0 when fewer than k groups saw a positive score
+    constexpr int kCand = kBmThreads;                      // candidate capacity (s_ws / s_wi are reused)
+    __syncthreads();                                       // everyone has read s_thr / s_ws before they are reused
+    for (int i = tid; i < rn; i += kBmThreads) {
+        const S s = acc[i];
+        if (s > (S)0 && s >= thr) {
+            if (want == -1 || p.doc_group[rbase + i] == want) {
+                const int idx = atomicAdd(&s_cnt, 1);
+                if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + i; }
+            }
+        }
+    }
+    __syncthreads();
+    const int n = s_cnt;
+    const int64_t obase = ((int64_t)q * p.n_ranges + r) * p.k;
+    S* out_s = reinterpret_cast<S*>(p.out_scores);
+    if (n <= kCand) {
+        if (tid < n) {
+            const S ms = s_ws[tid];
+            const int mi = s_wi[tid];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += better<S>(s_ws[j], s_wi[j], ms, mi) ? 1 : 0;
+            if (rank < p.k) { out_s[obase + rank] = ms; p.out_ids[obase + rank] = mi; }
+        }
+        if (tid >= n && tid < p.k) { out_s[obase + tid] = ScoreTraits<S>::lowest(); p.out_ids[obase + tid] = -1; }
+        return;
+    }
+    // ---- overflow fallback: per-warp shuffle lists, then warp 0 merges them ----
+    __syncthreads();
     WarpTopK<S> tk;
     tk.init(p.k);
     for (int i0 = warp * 32; i0 < rn; i0 += kBmThreads) {
@@ -197,9 +262,8 @@ bm25_score_kernel(const Bm25Params p) {
             fin.offer(s, id, lane < p.k && id >= 0);
         }
         if (lane < p.k) {
-            const int64_t o = ((int64_t)q * p.n_ranges + r) * p.k + lane;
-            reinterpret_cast<S*>(p.out_scores)[o] = fin.s;
-            p.out_ids[o] = fin.id;      // local id, -1 = empty
+            out_s[obase + lane] = fin.s;
+            p.out_ids[obase + lane] = fin.id;      // local id, -1 = empty
         }
     }
 }

@@ -113,6 +113,7 @@ static int simt_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64
 }
 
 static thread_local int g_force_kernel = 0;
+static const int g_default_variant = 0;   // auto picks the SS kernel until the TS one is validated on hardware
 static thread_local const char* g_last_kernel = "none";
 
 }  // namespace ezr
@@ -122,7 +123,7 @@ using namespace ezr;
 extern "C" {
 
 int ezr_dense_set_kernel(int32_t which) {
-    EZR_CHECK_ARG(which >= 0 && which <= 2, "dense_set_kernel: 0 auto, 1 simt, 2 tcgen05");
+    EZR_CHECK_ARG(which >= 0 && which <= 3, "dense_set_kernel: 0 auto, 1 simt, 2 tcgen05 (SS), 3 tcgen05 (TS)");
     g_force_kernel = which;
     return EZR_OK;
 }
@@ -155,15 +156,16 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
     const __nv_bfloat16* c = reinterpret_cast<const __nv_bfloat16*>(corpus_bf16);
     const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(queries_bf16);
     const bool tc_ok = dense_tc_supported(c, n_rows, dim, ld_corpus, q, n_queries, ld_queries, k);
-    if (g_force_kernel == 2 && !tc_ok) {
+    if (g_force_kernel >= 2 && !tc_ok) {
         set_error("dense_topk: tcgen05 kernel forced but shape unsupported (dim=%d k=%d ld=%lld)", dim, k,
                   (long long)ld_corpus);
         return EZR_ERR_UNSUPPORTED;
     }
     if (tc_ok && g_force_kernel != 1) {
-        g_last_kernel = "tcgen05";
+        const int variant = g_force_kernel == 3 ? 1 : (g_force_kernel == 2 ? 0 : g_default_variant);
+        g_last_kernel = variant == 1 ? "tcgen05-ts" : "tcgen05";
         return dense_tc_topk(c, n_rows, dim, ld_corpus, q, n_queries, ld_queries, k, doc_group, q_group, id_base,
-                             out_scores, out_ids, out_counts, workspace, workspace_bytes, st);
+                             out_scores, out_ids, out_counts, workspace, workspace_bytes, st, variant);
     }
     g_last_kernel = "simt";
     return simt_topk(c, n_rows, dim, ld_corpus, q, n_queries, ld_queries, k, doc_group, q_group, id_base, out_scores,

@@ -25,14 +25,19 @@ constexpr int TC_N = 64;        // corpus rows per tile = UMMA N
 constexpr int TC_KC = 64;       // bf16 per k-chunk = one 128-byte swizzle row
 constexpr int TC_MAXD = 768;
 constexpr int TC_ACC = 4;       // TMEM accumulator stages (TC_N fp32 columns each)
-constexpr int TC_MAX_STAGES = 16;
+constexpr int TC_MAX_STAGES = 26;
 constexpr int TC_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TC_KMAX = 16;
+constexpr int TS_ACC = 2;          // TS variant: accumulator stages
+constexpr int TS_ACC_COL0 = 384;   // TS variant: first accumulator column (A occupies [0, 384))
 constexpr int TC_A_CHUNK_BYTES = TC_M * TC_KC * 2;   // 16384
 constexpr int TC_B_STAGE_BYTES = TC_N * TC_KC * 2;   // 8192
 constexpr int TC_SMEM_LIMIT = 232448;                 // 227 KB opt-in maximum per CTA
 
 struct TcParams {
+    const __nv_bfloat16* queries;   // TS variant reads the query block straight from global memory
+    int64_t ldq;
+    int dim;
     int64_t n_rows;
     int rows_per_slice;   // multiple of TC_N
     int n_queries;
@@ -229,6 +234,194 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
+// TS variant: the 128-query block lives in TENSOR MEMORY (columns [0, dim/2)) instead of shared memory; the A operand
+// of tcgen05.mma is read from TMEM.  That frees ~190 KB of shared memory for the corpus ring (26 x 8 KB in flight per
+// SM instead of 4 x 8 KB), which is what an HBM-bound stream needs.  Accumulators: 2 x 64 columns at [384, 512).
+template <bool FILTER, int KT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                const TcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 128B swizzle needs 1024-byte aligned tiles
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem_b = smem;
+    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_b + (size_t)p.n_stages * TC_B_STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int slice = blockIdx.x;
+    const int q0 = blockIdx.y * TC_M;
+    const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
+    const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
+    const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_q);
+        ptx::prefetch_tensormap(&map_c);
+        ptx::mbar_init(&bars->a_full, 4);
+        for (int i = 0; i < p.n_stages; ++i) {
+            ptx::mbar_init(&bars->b_full[i], 1);
+            ptx::mbar_init(&bars->b_empty[i], 1);
+        }
+        for (int i = 0; i < TS_ACC; ++i) {
+            ptx::mbar_init(&bars->acc_full[i], 1);
+            ptx::mbar_init(&bars->acc_empty[i], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<512>(&bars->tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int row0 = (int)(row_begin + (int64_t)t * TC_N);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&bars->b_empty[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&bars->b_full[stage], TC_B_STAGE_BYTES);
+                    ptx::tma_load_2d_hint(smem_b + (size_t)stage * TC_B_STAGE_BYTES, &map_c, &bars->b_full[stage],
+                                          kc * TC_KC, row0, ptx::kEvictFirst);
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_M, TC_N);
+            ptx::mbar_wait(&bars->a_full, 0);
+            ptx::tc_fence_after();
+            const uint32_t b_base = ptx::smem_u32(smem_b);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int as = t % TS_ACC;
+                const uint32_t aph = (uint32_t)(t / TS_ACC) & 1u;
+                ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(TS_ACC_COL0 + as * TC_N);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&bars->b_full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_tmem = tmem_base + (uint32_t)(kc * (TC_KC / 2));
+                    const uint32_t b_addr = b_base + (uint32_t)stage * TC_B_STAGE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < TC_KC / 16; ++k4) {
+                        ptx::umma_f16_ts(d_tmem, a_tmem + k4 * 8, ptx::make_desc_sw128(b_addr + k4 * 32), idesc,
+                                         (uint32_t)((kc | k4) != 0));
+                    }
+                    ptx::umma_commit(&bars->b_empty[stage]);          // frees the smem stage when the MMAs retire
+                    if (kc == p.kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: one query row per thread ----------------
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int m = quad * 32 + lane;
+        const int qg = q0 + m;
+        const bool active = qg < p.n_queries;
+        const int k = p.k;
+        int want = -1;
+        if (FILTER && active) want = p.q_group[qg];
+        float ts[KT];
+        int ti[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) { ts[j] = -INFINITY; ti[j] = -1; }
+        float thr = -INFINITY;
+
+        // stage this thread's query row into tensor memory: 64 bf16 (= 32 packed columns) per tcgen05.st
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(p.queries + (int64_t)(active ? qg : 0) * p.ldq);
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                uint32_t r[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (active) v = __ldg(src + kc * 8 + j);
+                    r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+                }
+                ptx::tmem_st_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kc * (TC_KC / 2)), r);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->a_full);
+        }
+
+        for (int t = 0; t < n_tiles; ++t) {
+            const int as = t % TS_ACC;
+            const uint32_t aph = (uint32_t)(t / TS_ACC) & 1u;
+            ptx::mbar_wait(&bars->acc_full[as], aph);
+            ptx::tc_fence_after();
+            const int64_t row0 = row_begin + (int64_t)t * TC_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TS_ACC_COL0 + as * TC_N);
+#pragma unroll
+            for (int half = 0; half < TC_N / 32; ++half) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(taddr + half * 32, r);
+                ptx::tmem_ld_wait();
+                if (half == TC_N / 32 - 1) {
+                    // accumulator stage is in registers: hand it back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float v = __uint_as_float(r[j]) + 0.0f;       // -0.0 -> +0.0
+                    const int64_t doc = row0 + half * 32 + j;
+                    bool ok = active && doc < row_end && v >= thr;
+                    if (FILTER) {
+                        if (ok && want != -1) ok = (__ldg(p.doc_group + doc) == want);
+                    }
+                    if (ok) {
+                        // candidates arrive in increasing id order, so on equal score the newcomer (higher id)
+                        // ranks first under the canonical order: ">=" everywhere.
+                        float cv = v;
+                        int ci = (int)doc + p.id_base;
+#pragma unroll
+                        for (int s = 0; s < KT; ++s) {
+                            const bool b = cv >= ts[s];
+                            const float fs = ts[s];
+                            const int is = ti[s];
+                            ts[s] = b ? cv : fs;
+                            ti[s] = b ? ci : is;
+                            cv = b ? fs : cv;
+                            ci = b ? is : ci;
+                        }
+                        thr = ts[KT - 1];
+                    }
+                }
+            }
+        }
+        if (active) {
+            const int64_t o = ((int64_t)qg * p.n_slices + slice) * k;
+#pragma unroll
+            for (int s = 0; s < KT; ++s) {
+                if (s < k) {
+                    p.part_s[o + s] = ts[s];
+                    p.part_id[o + s] = ti[s];
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------ host ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -294,13 +487,16 @@ size_t dense_tc_workspace(int64_t n_rows, int dim, int n_queries, int k) {
 int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t ldc, const __nv_bfloat16* queries,
                   int n_queries, int64_t ldq, int k, const int32_t* doc_group, const int32_t* q_group, int id_base,
                   float* out_scores, int32_t* out_ids, int32_t* out_counts, void* ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, int variant) {
     const size_t need = dense_tc_workspace(n_rows, dim, n_queries, k);
     if (ws_bytes < need || !ws) {
         set_error("dense_topk(tcgen05): workspace %zu < %zu", ws_bytes, need);
         return EZR_ERR_WORKSPACE;
     }
     TcParams p;
+    p.queries = queries;
+    p.ldq = ldq;
+    p.dim = dim;
     p.n_rows = n_rows;
     p.n_slices = tc_slices(n_rows);
     p.rows_per_slice = tc_rows_per_slice(n_rows, p.n_slices);
@@ -312,7 +508,7 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     p.id_base = id_base;
     p.doc_group = doc_group;
     p.q_group = q_group;
-    const size_t a_bytes = (size_t)p.kchunks * TC_A_CHUNK_BYTES;
+    const size_t a_bytes = variant == 1 ? 0 : (size_t)p.kchunks * TC_A_CHUNK_BYTES;
     const size_t fixed = 1024 /*alignment slack*/ + sizeof(TcBarriers) + 64;
     int stages = (int)((TC_SMEM_LIMIT - fixed - a_bytes) / TC_B_STAGE_BYTES);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -334,15 +530,18 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
 
     const bool filter = (q_group != nullptr);
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const TcParams);
-    static const kern_t table[2][4] = {
-        {dense_tc_kernel<false, 4>, dense_tc_kernel<false, 8>, dense_tc_kernel<false, 12>, dense_tc_kernel<false, 16>},
-        {dense_tc_kernel<true, 4>, dense_tc_kernel<true, 8>, dense_tc_kernel<true, 12>, dense_tc_kernel<true, 16>}};
+    static const kern_t table[2][2][4] = {
+        {{dense_tc_kernel<false, 4>, dense_tc_kernel<false, 8>, dense_tc_kernel<false, 12>, dense_tc_kernel<false, 16>},
+         {dense_tc_kernel<true, 4>, dense_tc_kernel<true, 8>, dense_tc_kernel<true, 12>, dense_tc_kernel<true, 16>}},
+        {{dense_ts_kernel<false, 4>, dense_ts_kernel<false, 8>, dense_ts_kernel<false, 12>, dense_ts_kernel<false, 16>},
+         {dense_ts_kernel<true, 4>, dense_ts_kernel<true, 8>, dense_ts_kernel<true, 12>, dense_ts_kernel<true, 16>}}};
     const int kt = (k + 3) / 4 - 1;
-    kern_t kern = table[filter ? 1 : 0][kt];
-    static bool attr_done[2][4] = {{false, false, false, false}, {false, false, false, false}};
-    if (!attr_done[filter ? 1 : 0][kt]) {
+    const int vi = variant == 1 ? 1 : 0;
+    kern_t kern = table[vi][filter ? 1 : 0][kt];
+    static bool attr_done[2][2][4] = {};
+    if (!attr_done[vi][filter ? 1 : 0][kt]) {
         EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-        attr_done[filter ? 1 : 0][kt] = true;
+        attr_done[vi][filter ? 1 : 0][kt] = true;
     }
     dim3 grid(p.n_slices, (n_queries + TC_M - 1) / TC_M);
     {

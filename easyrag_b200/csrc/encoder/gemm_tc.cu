@@ -1,0 +1,256 @@
+// bf16 GEMM on tcgen05 / TMEM with fused epilogues, for the chunk-embedding forward pass.
+//
+//   out[M, N'] = epilogue( A[M, K] . W[N, K]^T + bias[N] ) (+ residual[M, N'])
+//
+// A = activations (tokens x features, row-major), W = an nn.Linear weight ([out, in], row-major), so both
+// operands are K-major and load straight into 128B-swizzled shared-memory tiles by TMA.  Replaces the
+// cuBLAS calls behind the reference's projections: Qwen2 q/k/v/o and SwiGLU MLP (modeling_qwen.py:261-263,
+// 319,186) and the BERT-shaped encoder's dense layers behind SentenceTransformer.encode (hf_embeddings.py:118-123).
+//
+// Persistent, warp-specialised: warp 0 = TMA producer (6-stage ring of 128x64 A and 128x64 W tiles),
+// warp 1 = single-thread tcgen05.mma issuer (128x128x16, fp32 accumulate into one of two 128-column TMEM
+// stages), warps 2-5 = epilogue (tcgen05.ld, one output row per thread, bias / GELU / SwiGLU / residual in
+// fp32, bf16 pack, 16-byte global stores) overlapping the next tile's MMAs.
+#include "../ezr_common.cuh"
+#include "../ptx.cuh"
+
+namespace ezr {
+
+constexpr int GM = 128, GN = 128, GK = 64;
+constexpr int G_STAGES = 6;
+constexpr int G_ACC = 2;
+constexpr int G_THREADS = 192;
+constexpr int G_A_BYTES = GM * GK * 2;   // 16 KB
+constexpr int G_B_BYTES = GN * GK * 2;   // 16 KB
+
+enum { EPI_NONE = 0, EPI_GELU = 1, EPI_SWIGLU = 2 };
+
+struct GemmParams {
+    int M, N, K;
+    int tiles_m, tiles_n;
+    const __nv_bfloat16* bias;       // [N] or null
+    const __nv_bfloat16* residual;   // [M, ldr] or null
+    int64_t ldr;
+    __nv_bfloat16* out;              // [M, ldo]
+    int64_t ldo;
+};
+
+struct GemmBarriers {
+    uint64_t full[G_STAGES];
+    uint64_t empty[G_STAGES];
+    uint64_t acc_full[G_ACC];
+    uint64_t acc_empty[G_ACC];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const GemmParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem_a = smem;
+    unsigned char* smem_b = smem + (size_t)G_STAGES * G_A_BYTES;
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_b + (size_t)G_STAGES * G_B_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = p.tiles_m * p.tiles_n;
+    const int kchunks = p.K / GK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_w);
+        for (int i = 0; i < G_STAGES; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); }
+        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<G_ACC * GN>(&bars->tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int tm = t % p.tiles_m, tn = t / p.tiles_m;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&bars->full[stage], G_A_BYTES + G_B_BYTES);
+                    ptx::tma_load_2d(smem_a + (size_t)stage * G_A_BYTES, &map_a, &bars->full[stage], kc * GK, tm * GM);
+                    ptx::tma_load_2d_hint(smem_b + (size_t)stage * G_B_BYTES, &map_w, &bars->full[stage], kc * GK,
+                                          tn * GN, ptx::kEvictLast);
+                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(GM, GN);
+            const uint32_t a_base = ptx::smem_u32(smem_a), b_base = ptx::smem_u32(smem_b);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const int as = it % G_ACC;
+                const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
+                ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * GN);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    ptx::mbar_wait(&bars->full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = a_base + (uint32_t)stage * G_A_BYTES;
+                    const uint32_t b_addr = b_base + (uint32_t)stage * G_B_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < GK / 16; ++k4)
+                        ptx::umma_f16_ss(d_tmem, ptx::make_desc_sw128(a_addr + k4 * 32),
+                                         ptx::make_desc_sw128(b_addr + k4 * 32), idesc, (uint32_t)((kc | k4) != 0));
+                    ptx::umma_commit(&bars->empty[stage]);
+                    if (kc == kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
+                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        int it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int tm = t % p.tiles_m, tn = t / p.tiles_m;
+            const int as = it % G_ACC;
+            const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
+            ptx::mbar_wait(&bars->acc_full[as], aph);
+            ptx::tc_fence_after();
+            const int row = tm * GM + quad * 32 + lane;
+            const bool row_ok = row < p.M;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * GN);
+            constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? 2 : 4;     // 32 output columns per chunk
+#pragma unroll
+            for (int c = 0; c < n_out_chunks; ++c) {
+                uint32_t r[32];
+                float v[32];
+                ptx::tmem_ld_32x32(taddr + c * 32, r);
+                if (EPI == EPI_SWIGLU) {
+                    uint32_t r2[32];
+                    ptx::tmem_ld_32x32(taddr + 64 + c * 32, r2);
+                    ptx::tmem_ld_wait();
+                    const int gcol = tn * GN + c * 32;           // gate columns; up columns are gcol + 64
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float g = __uint_as_float(r[j]), u = __uint_as_float(r2[j]);
+                        if (p.bias) {
+                            g += __bfloat162float(__ldg(p.bias + min(gcol + j, p.N - 1)));
+                            u += __bfloat162float(__ldg(p.bias + min(gcol + 64 + j, p.N - 1)));
+                        }
+                        v[j] = silu(g) * u;
+                    }
+                } else {
+                    ptx::tmem_ld_wait();
+                    const int gcol = tn * GN + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(r[j]);
+                        if (p.bias) x += __bfloat162float(__ldg(p.bias + min(gcol + j, p.N - 1)));
+                        if (EPI == EPI_GELU) x = gelu_erf(x);
+                        v[j] = x;
+                    }
+                }
+                if (c == n_out_chunks - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
+                }
+                const int ocol = (EPI == EPI_SWIGLU) ? (tn * (GN / 2) + c * 32) : (tn * GN + c * 32);
+                const int n_out = (EPI == EPI_SWIGLU) ? p.N / 2 : p.N;
+                if (row_ok && ocol < n_out) {
+                    if (p.residual) {
+                        const __nv_bfloat16* rr = p.residual + (int64_t)row * p.ldr + ocol;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (ocol + j < n_out) v[j] += __bfloat162float(__ldg(rr + j));
+                    }
+                    __nv_bfloat16* op = p.out + (int64_t)row * p.ldo + ocol;
+                    if (ocol + 32 <= n_out && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            pk.x = pack_bf16(v[j], v[j + 1]);
+                            pk.y = pack_bf16(v[j + 2], v[j + 3]);
+                            pk.z = pack_bf16(v[j + 4], v[j + 5]);
+                            pk.w = pack_bf16(v[j + 6], v[j + 7]);
+                            *reinterpret_cast<uint4*>(op + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (ocol + j < n_out) op[j] = __float2bfloat16(v[j]);
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<G_ACC * GN>(tmem_base);
+    }
+}
+
+static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const __nv_bfloat16* W, int N, int64_t ldw,
+                       const __nv_bfloat16* bias, const __nv_bfloat16* residual, int64_t ldr, __nv_bfloat16* out,
+                       int64_t ldo, int epi, cudaStream_t st) {
+    EZR_CHECK_ARG(M >= 0 && N >= 1 && K >= GK && K % GK == 0, "gemm: need K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+    EZR_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "gemm: row strides must be multiples of 8 and >= K");
+    EZR_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0, "gemm: A/W must be 16-byte aligned");
+    EZR_CHECK_ARG(epi >= EPI_NONE && epi <= EPI_SWIGLU, "gemm: bad epilogue %d", epi);
+    EZR_CHECK_ARG(epi != EPI_SWIGLU || N % GN == 0, "gemm: SwiGLU epilogue needs N %% 128 == 0 (interleaved gate/up)");
+    if (M == 0) return EZR_OK;
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.tiles_m = (M + GM - 1) / GM;
+    p.tiles_n = (N + GN - 1) / GN;
+    p.bias = bias; p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo;
+    CUtensorMap map_a, map_w;
+    int rc = encode_tmap_2d_bf16(&map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GK, GM);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&map_w, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GK, GN);
+    if (rc) return rc;
+    const size_t smem = 1024 + (size_t)G_STAGES * (G_A_BYTES + G_B_BYTES) + sizeof(GemmBarriers) + 64;
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const GemmParams);
+    static const kern_t table[3] = {gemm_tc_kernel<EPI_NONE>, gemm_tc_kernel<EPI_GELU>, gemm_tc_kernel<EPI_SWIGLU>};
+    static bool attr_done[3] = {false, false, false};
+    if (!attr_done[epi]) {
+        EZR_CUDA(cudaFuncSetAttribute(table[epi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[epi] = true;
+    }
+    const int n_tiles = p.tiles_m * p.tiles_n;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    {
+        ProfScope prof(EZR_PROF_ENC_GEMM, st);
+        table[epi]<<<grid, G_THREADS, smem, st>>>(map_a, map_w, p);
+    }
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+}  // namespace ezr
+
+extern "C" int ezr_gemm_bf16(const void* a, int32_t m, int32_t k, int64_t lda, const void* w, int32_t n, int64_t ldw,
+                             const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo,
+                             int32_t epilogue, void* stream) {
+    using namespace ezr;
+    return gemm_launch((const __nv_bfloat16*)a, m, k, lda, (const __nv_bfloat16*)w, n, ldw, (const __nv_bfloat16*)bias,
+                       (const __nv_bfloat16*)residual, ldr, (__nv_bfloat16*)out, ldo, epilogue, (cudaStream_t)stream);
+}

@@ -127,9 +127,10 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
                    const int32_t* doc_group, const int32_t* q_group, int32_t id_base, float* out_scores,
                    int32_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes,
                    void* stream);
-/* 0 = pick automatically, 1 = force the generic SIMT kernel, 2 = force tcgen05 (error if unsupported) */
+/* 0 = pick automatically, 1 = force the generic SIMT kernel, 2 = force tcgen05 with the query block in shared
+ * memory (SS), 3 = force tcgen05 with the query block in tensor memory (TS); 2/3 error if the shape is unsupported */
 int ezr_dense_set_kernel(int32_t which);
-/* name of the kernel the last ezr_dense_topk call on this thread launched ("tcgen05" / "simt") */
+/* name of the kernel the last ezr_dense_topk call on this thread launched ("tcgen05" / "tcgen05-ts" / "simt") */
 const char* ezr_dense_last_kernel(void);
 
 /* ------------------------------------------------------------- fusion ---
@@ -148,6 +149,44 @@ int ezr_fusion_simple(const int32_t* ids_a, const double* scores_a, const int32_
                       const double* scores_b, const int32_t* cnt_b, int32_t n_queries, int32_t stride_in,
                       const int32_t* canon, int32_t canon_base, int32_t k_out, int32_t* out_ids,
                       double* out_scores, int32_t* out_counts, void* stream);
+
+/* ------------------------------------------------------------ encoder ---
+ * Building blocks of the chunk/query embedding forward pass (GTEEmbedding._embed, gte_embeddings.py:59-72 ->
+ * Qwen2Model.forward, modeling_qwen.py:956-1116; HuggingFaceEmbedding._embed, hf_embeddings.py:112-123 ->
+ * a BERT-shaped encoder).  Activations are bf16, row-major, PACKED: sequence b owns rows
+ * [cu_seqlens[b], cu_seqlens[b+1]) -- no padding tokens.  The Python classes in easyrag_b200/encoder.py chain
+ * these per layer on one stream. */
+
+/* out[M,N'] = epi(A[M,K] . W[N,K]^T + bias) (+ residual); tcgen05/TMEM/TMA.  epilogue: 0 none, 1 GELU(erf),
+ * 2 SwiGLU (W rows interleaved per 128: 64 gate rows then the matching 64 up rows; N' = N/2).  K % 64 == 0. */
+int ezr_gemm_bf16(const void* a, int32_t m, int32_t k, int64_t lda, const void* w, int32_t n, int64_t ldw,
+                  const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo, int32_t epilogue,
+                  void* stream);
+/* non-causal attention over packed q|k|v rows ([T, (H + 2*KV) * hd]); head_dim 64 or 128; GQA via n_kv_heads */
+int ezr_attn_bidir(const void* qkv, int64_t ld, const int32_t* cu_seqlens, int32_t n_seq, int32_t max_len,
+                   int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, float softmax_scale, void* out, int64_t ldo,
+                   void* stream);
+int ezr_embed_gather(const int32_t* ids, int32_t n_tokens, const void* table, int64_t ldt, int32_t vocab, int32_t dim,
+                     void* out, int64_t ldo, void* stream);
+/* BERT embeddings: LayerNorm(word[id] + type[0] + position[pos]) */
+int ezr_bert_embed(const int32_t* ids, const int32_t* positions, int32_t n_tokens, const void* word, const void* pos,
+                   const void* type0, const void* gamma, const void* beta, float eps, int32_t vocab, int32_t max_pos,
+                   int32_t dim, void* out, void* stream);
+/* Qwen2RMSNorm (modeling_qwen.py:91-96) */
+int ezr_rmsnorm(const void* x, int64_t ldx, const void* gamma, float eps, int32_t n_rows, int32_t dim, void* out,
+                int64_t ldo, void* stream);
+int ezr_layernorm(const void* x, int64_t ldx, const void* gamma, const void* beta, float eps, int32_t n_rows,
+                  int32_t dim, void* out, int64_t ldo, void* stream);
+/* rotary embedding in place on the q and k heads of packed qkv rows (modeling_qwen.py:137-169); bf16 cos/sin tables
+ * [max_pos, head_dim/2] */
+int ezr_rope(void* qkv, int64_t ld, const int32_t* positions, const void* cos_table, const void* sin_table,
+             int32_t max_pos, int32_t n_heads_qk, int32_t head_dim, int32_t n_tokens, void* stream);
+/* pooling (0 last token, 1 first/CLS, 2 mean) + optional final RMSNorm of the pooled row + L2 normalisation
+ * (l2_mode 0 none, 1 bf16 semantics of gte_embeddings.py:70, 2 fp32 semantics); writes bf16 [n_seq, dim] and,
+ * if out_f32 != NULL, the float copy the embedding API returns */
+int ezr_pool_normalize(const void* hidden, int64_t ldh, const int32_t* cu_seqlens, int32_t n_seq, int32_t pool,
+                       int32_t final_norm, const void* gamma, float eps, int32_t l2_mode, int32_t dim, void* out_bf16,
+                       float* out_f32, void* stream);
 
 /* ----------------------------------------------------------- profiling ---
  * Per-kernel CUDA-event timing on the launching stream, for bench.py's roofline figures.

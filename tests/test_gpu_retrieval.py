@@ -148,6 +148,24 @@ def test_bm25_ragged_sizes_and_ties(n_docs):
         _check_bm25_topk(batched.bm25_topk(ix, qs.term_ptr, qs.terms, k), rows, k)
 
 
+def test_bm25_massive_ties_take_overflow_path():
+    # thousands of identical documents: every score ties, the candidate list overflows and the kernel's
+    # warp-shuffle fallback must still return the highest ids first
+    one = np.array([1, 2, 3, 4, 5, 1], dtype=np.int32)
+    other = np.array([7, 8, 9], dtype=np.int32)
+    docs = [one if i % 3 else other for i in range(20_000)]
+    tokens = torch.from_numpy(np.concatenate(docs)).to(torch.int32)
+    ptr = torch.tensor(np.cumsum([0] + [len(d) for d in docs]), dtype=torch.int64)
+    o = obm.OkapiCSR(docs, 12)
+    ix = Bm25Index(Bm25Stats.from_tokens(tokens, ptr, 12), device=DEV)
+    lists = [[1, 2], [7], [1, 7, 9, 11], [5, 5, 5]]
+    qp = torch.tensor(np.cumsum([0] + [len(l) for l in lists]), dtype=torch.int32)
+    qt = torch.tensor([t for l in lists for t in l], dtype=torch.int32)
+    rows = [o.get_scores(l) for l in lists]
+    for k in (1, 10, 32):
+        _check_bm25_topk(batched.bm25_topk(ix, qp, qt, k), rows, k)
+
+
 def test_bm25s_float32_bit_exact():
     corpus = synth.make_sparse_corpus(9000, 3000, 5, mean_len=60, min_len=1, max_len=200)
     qs = synth.make_queries(corpus, 40, 6)
@@ -237,7 +255,7 @@ def _check_dense(res, c, qv, k, allowed=None, exact=False, id_base=0):
             assert m[got].all()
 
 
-@pytest.mark.parametrize("kernel", [1, 2])          # 1 = generic SIMT kernel, 2 = tcgen05
+@pytest.mark.parametrize("kernel", [1, 2, 3])       # 1 = generic SIMT, 2 = tcgen05 (queries in smem), 3 = tcgen05 (queries in TMEM)
 @pytest.mark.parametrize("n,d,q,k", [(5000, 128, 130, 10), (777, 768, 3, 5), (64, 64, 1, 16), (20_000, 768, 257, 10),
                                      (100, 256, 5, 12)])
 def test_dense_exact_integer_inputs(kernel, n, d, q, k):
@@ -246,13 +264,13 @@ def test_dense_exact_integer_inputs(kernel, n, d, q, k):
     _lib.check(L.ezr_dense_set_kernel(kernel))
     try:
         res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), k)
-        assert L.ezr_dense_last_kernel() == (b"simt" if kernel == 1 else b"tcgen05")
+        assert L.ezr_dense_last_kernel() == {1: b"simt", 2: b"tcgen05", 3: b"tcgen05-ts"}[kernel]
     finally:
         L.ezr_dense_set_kernel(0)
     _check_dense(res, c, qv, k, exact=True)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_dense_unit_vectors_within_tolerance(kernel):
     c, qv = _dense_case(30_000, 768, 200, 7)
     L = _lib.lib()
@@ -264,7 +282,7 @@ def test_dense_unit_vectors_within_tolerance(kernel):
     _check_dense(res, c, qv, 10)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_dense_dir_filter_and_id_base(kernel):
     c, qv = _dense_case(9000, 256, 70, 11, integer=True)
     groups = synth.make_groups(9000, 4, 12)
