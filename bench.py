@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-queries", type=int, default=32, help="bounded sample for the CPU baseline")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--dense-kernel", type=int, default=0, help="0 auto, 1 simt, 2 tcgen05 SS, 3 tcgen05 TS")
     return ap.parse_args()
 
 
@@ -212,6 +213,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_cuda()
     L = _lib.lib()
+    _lib.check(L.ezr_dense_set_kernel(args.dense_kernel))
 
     data = make_data(args, dev)
     lo, hi = ezdist.shard_bounds(args.rows, world, rank, align=8192)

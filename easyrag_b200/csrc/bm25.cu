@@ -91,16 +91,28 @@ struct Bm25Params {
     int32_t* out_ids;   // fused: partial ids
 };
 
+// Integer sort key of a non-negative score: IEEE-754 ordering of non-negative floats equals the ordering of their
+// bit patterns, so the high word of a float64 (all of a float32) is a monotone, slightly coarse key.
+template <typename S> struct KeyOf;
+template <> struct KeyOf<double> {
+    static __device__ __forceinline__ int load(const double* acc, int i) { return reinterpret_cast<const int*>(acc)[2 * i + 1]; }
+};
+template <> struct KeyOf<float> {
+    static __device__ __forceinline__ int load(const float* acc, int i) { return reinterpret_cast<const int*>(acc)[i]; }
+};
+
 // MODE 0: fused top-k (k<=32) -> per-(query,range) partial lists.  MODE 1: write the score row.
 template <typename S, int MODE>
 __global__ void __launch_bounds__(kBmThreads, 3)
 bm25_score_kernel(const Bm25Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S* acc = reinterpret_cast<S*>(smem_raw);
-    __shared__ int64_t s_beg[kBmMaxT];
-    __shared__ int64_t s_end[kBmMaxT];
-    __shared__ S s_ws[(kBmThreads / 32) * 32];
-    __shared__ int s_wi[(kBmThreads / 32) * 32];
+    __shared__ int s_beg[kBmMaxT];
+    __shared__ int s_len[kBmMaxT];
+    __shared__ S s_ws[kBmThreads];
+    __shared__ int s_wi[kBmThreads];
+    __shared__ int s_thr;
+    __shared__ int s_cnt;
 
     const int q = blockIdx.x;
     const int r = blockIdx.y;
@@ -110,56 +122,61 @@ bm25_score_kernel(const Bm25Params p) {
     const int qs = p.q_ptr[q];
     const int m = p.q_ptr[q + 1] - qs;
     const S* __restrict__ post_w = reinterpret_cast<const S*>(p.post_w);
+    const int32_t* __restrict__ post_doc = p.post_doc;
+    constexpr int kVec = 16 / sizeof(S);                        // scores per 128-bit shared-memory access
 
     for (int tb = 0; tb < m; tb += kBmMaxT) {
         const int mt = min(kBmMaxT, m - tb);
         if (tid < mt) {
             const int t = p.q_terms[qs + tb + tid];
-            int64_t beg = 0, end = 0;
+            int beg = 0, len = 0;
             if (t >= 0 && t < p.vocab) {
-                const int64_t base = p.indptr[t];
                 const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
-                beg = base + ro[0];
-                end = base + ro[1];
+                const uint32_t o0 = ro[0], o1 = ro[1];
+                beg = (int)(p.indptr[t] + o0);                  // n_postings < 2^31 (checked on the host)
+                len = (int)(o1 - o0);
             }
             s_beg[tid] = beg;
-            s_end[tid] = end;
+            s_len[tid] = len;
         }
         __syncthreads();
-        // issue the first posting of every term before touching shared memory:
-        // all loads of the round are in flight together
+        // issue the first posting of every term before touching shared memory: all loads of the round are in
+        // flight together
         int d[kBmMaxT];
         S w[kBmMaxT];
 #pragma unroll
         for (int j = 0; j < kBmMaxT; ++j) {
             d[j] = -1;
             w[j] = (S)0;
-            if (j < mt) {
-                const int64_t pp = s_beg[j] + tid;
-                if (pp < s_end[j]) {
-                    d[j] = __ldg(p.post_doc + pp);
-                    w[j] = __ldg(post_w + pp);
-                }
+            if (j < mt && tid < s_len[j]) {
+                const int pp = s_beg[j] + tid;
+                d[j] = __ldg(post_doc + pp);
+                w[j] = __ldg(post_w + pp);
             }
         }
         if (tb == 0) {
-            for (int i = tid; i < kBmRange; i += kBmThreads) acc[i] = (S)0;
+            uint4* a4 = reinterpret_cast<uint4*>(acc);
+#pragma unroll
+            for (int i = 0; i < kBmRange / kVec / kBmThreads; ++i) a4[tid + i * kBmThreads] = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();
         }
 #pragma unroll
         for (int j = 0; j < kBmMaxT; ++j) {
             if (j < mt) {   // block-uniform
                 if (d[j] >= 0) acc[d[j] - rbase] += w[j];
-                for (int64_t pp = s_beg[j] + tid + kBmThreads; pp < s_end[j]; pp += kBmThreads) {
-                    const int dd = __ldg(p.post_doc + pp);
-                    acc[dd - rbase] += __ldg(post_w + pp);
+                const int len = s_len[j];
+                for (int o = tid + kBmThreads; o < len; o += kBmThreads) {        // segments longer than the CTA
+                    const int pp = s_beg[j] + o;
+                    acc[__ldg(post_doc + pp) - rbase] += __ldg(post_w + pp);
                 }
                 __syncthreads();   // term j fully applied before term j+1: float sum order of the reference
             }
         }
     }
     if (m == 0) {
-        for (int i = tid; i < kBmRange; i += kBmThreads) acc[i] = (S)0;
+        uint4* a4 = reinterpret_cast<uint4*>(acc);
+#pragma unroll
+        for (int i = 0; i < kBmRange / kVec / kBmThreads; ++i) a4[tid + i * kBmThreads] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
     }
 
@@ -170,53 +187,59 @@ bm25_score_kernel(const Bm25Params p) {
     }
 
     // ---- fused top-k from shared memory: threshold -> compact -> rank ----
-    // 1. every half-warp finds the best score among the 256 documents it scans; the k-th largest of those 32
-    //    group maxima is a lower bound of the range's k-th best score (they are 32 distinct documents), and a
-    //    tight one: on average only ~k/2 extra documents pass it.
-    // 2. documents with score >= that bound are appended to a small candidate list (shared-memory atomics).
-    // 3. each candidate counts how many candidates rank before it under the canonical order and writes itself
-    //    to that output slot.  No sort, no serial insertion chain.
+    // 1. every half-warp finds the best key among the documents it scans; the k-th largest of those 32 group
+    //    maxima is a lower bound of the range's k-th best score (they belong to 32 distinct documents), and a tight
+    //    one: on average only ~k/2 extra documents pass it.  Keys are the high words of the scores (see KeyOf).
+    // 2. documents whose key reaches the bound are appended to a small candidate list (shared-memory atomics).
+    // 3. each candidate counts how many candidates rank before it under the canonical order and writes itself to
+    //    that output slot.  No sort, no serial insertion chain.
     // Exact ties at the bound (or fewer than k non-empty groups) can overflow the list; then the robust
-    // warp-shuffle selection below takes over.
+    // warp-shuffle selection at the end takes over.  Rows >= rn of the last range hold zeros and never qualify.
     const int lane = tid & 31, warp = tid >> 5;
     const int want = p.q_group ? p.q_group[q] : -1;
-    __shared__ S s_thr;
-    __shared__ int s_cnt;
-    S tmax = (S)0;
-    for (int i = tid; i < rn; i += kBmThreads) {
-        const S s = acc[i];
-        if (s > tmax) {
-            if (want == -1 || p.doc_group[rbase + i] == want) tmax = s;
+    constexpr int kPer = kBmRange / kBmThreads;                 // documents scanned per thread
+    int tmax = 0;
+    if (want == -1) {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) tmax = max(tmax, KeyOf<S>::load(acc, tid + i * kBmThreads));
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < kPer; ++i) {
+            const int doc = tid + i * kBmThreads;
+            const int key = KeyOf<S>::load(acc, doc);
+            if (key > tmax && p.doc_group[rbase + doc] == want) tmax = key;
         }
     }
+    int gmax = tmax;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        const S other = __shfl_xor_sync(0xffffffffu, tmax, o);
-        tmax = other > tmax ? other : tmax;
-    }
-    if ((lane & 15) == 0) s_ws[tid >> 4] = tmax;           // 32 group maxima (0 = group has no positive score)
+    for (int o = 8; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if ((lane & 15) == 0) s_wi[tid >> 4] = gmax;            // 32 group maxima (0: group saw no positive score)
     if (tid == 0) s_cnt = 0;
     __syncthreads();
     if (warp == 0) {
-        const S mine = s_ws[lane];
+        const int mine = s_wi[lane];
         int rank = 0;
-#pragma unroll 8
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const S o = s_ws[j];
+            const int o = s_wi[j];
             rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
         }
-        if (rank == p.k - 1) s_thr = mine;                 // ranks are a permutation: exactly one lane writes
+        if (rank == p.k - 1) s_thr = mine;                  // ranks are a permutation: exactly one lane writes
     }
     __syncthreads();
-    const S thr = s_thr;                                   // 0 when fewer than k groups saw a positive score
-    constexpr int kCand = kBmThreads;                      // candidate capacity (s_ws / s_wi are reused)
-    __syncthreads();                                       // everyone has read s_thr / s_ws before they are reused
-    for (int i = tid; i < rn; i += kBmThreads) {
-        const S s = acc[i];
-        if (s > (S)0 && s >= thr) {
-            if (want == -1 || p.doc_group[rbase + i] == want) {
-                const int idx = atomicAdd(&s_cnt, 1);
-                if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + i; }
+    const int thr = s_thr;                                  // 0 when fewer than k groups saw a positive score
+    constexpr int kCand = kBmThreads;                       // candidate capacity (s_ws / s_wi are reused)
+    __syncthreads();                                        // s_thr / s_wi have been read by everyone: reuse them
+    if (tmax >= thr) {                                      // only threads that own a qualifying document re-scan
+#pragma unroll 4
+        for (int i = 0; i < kPer; ++i) {
+            const int doc = tid + i * kBmThreads;
+            if (KeyOf<S>::load(acc, doc) >= thr) {
+                const S s = acc[doc];
+                if (s > (S)0 && (want == -1 || p.doc_group[rbase + doc] == want)) {
+                    const int idx = atomicAdd(&s_cnt, 1);
+                    if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + doc; }
+                }
             }
         }
     }
@@ -250,6 +273,7 @@ bm25_score_kernel(const Bm25Params p) {
         }
         tk.offer(s, rbase + i, ok);
     }
+    __syncthreads();
     s_ws[warp * 32 + lane] = tk.s;
     s_wi[warp * 32 + lane] = tk.id;
     __syncthreads();
@@ -447,6 +471,8 @@ static int check_index(const ezr_bm25_index* ix) {
     EZR_CHECK_ARG(ix->n_ranges == ceil_div(ix->n_docs, kBmRange), "bm25: n_ranges != ceil(n_docs/range_size)");
     EZR_CHECK_ARG(ix->n_ranges <= 65535, "bm25: too many ranges (%d) for one shard", ix->n_ranges);
     EZR_CHECK_ARG(ix->score_type == EZR_F64 || ix->score_type == EZR_F32, "bm25: bad score_type");
+    EZR_CHECK_ARG(ix->n_postings >= 0 && ix->n_postings < ((int64_t)1 << 31),
+                  "bm25: %lld postings in one index; shard the corpus (limit 2^31-1 per shard)", (long long)ix->n_postings);
     return EZR_OK;
 }
 

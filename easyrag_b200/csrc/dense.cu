@@ -113,7 +113,7 @@ static int simt_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64
 }
 
 static thread_local int g_force_kernel = 0;
-static const int g_default_variant = 0;   // auto picks the SS kernel until the TS one is validated on hardware
+static const int g_default_variant = 1;   // auto: persistent TS kernel (queries in TMEM); 2 forces the SS kernel
 static thread_local const char* g_last_kernel = "none";
 
 }  // namespace ezr

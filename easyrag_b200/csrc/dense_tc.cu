@@ -50,6 +50,7 @@ struct TcParams {
     float* part_s;        // [n_queries][n_slices][k]
     int32_t* part_id;
     int n_slices;
+    int n_qblocks;        // TS variant: units = n_slices x n_qblocks, walked by persistent CTAs
 };
 
 struct TcBarriers {
@@ -234,29 +235,27 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
-// TS variant: the 128-query block lives in TENSOR MEMORY (columns [0, dim/2)) instead of shared memory; the A operand
-// of tcgen05.mma is read from TMEM.  That frees ~190 KB of shared memory for the corpus ring (26 x 8 KB in flight per
-// SM instead of 4 x 8 KB), which is what an HBM-bound stream needs.  Accumulators: 2 x 64 columns at [384, 512).
+// TS variant (default): the 128-query block lives in TENSOR MEMORY (columns [0, dim/2)); the A operand of
+// tcgen05.mma is read from TMEM, which frees ~190 KB of shared memory for the corpus ring (26 x 8 KB in flight).
+// Persistent CTAs walk work units (corpus split s, query block b), ordered split-major: a CTA keeps ONE query block
+// for a LONG run of corpus rows (n_rows / n_splits), so the per-thread top-k lists warm up once per unit and
+// almost nothing passes the threshold afterwards, and the query blocks that are resident at the same time stream
+// the SAME corpus split, so every corpus tile is fetched from HBM once and served to the other CTAs from L2.
+// TMEM: A at columns [0, 384), two 64-column accumulator stages at [384, 512).
 template <bool FILTER, int KT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                 const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    // 128B swizzle needs 1024-byte aligned tiles
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_b = smem;
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_b + (size_t)p.n_stages * TC_B_STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int slice = blockIdx.x;
-    const int q0 = blockIdx.y * TC_M;
-    const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
-    const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
-    const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+    const int n_units = p.n_slices * p.n_qblocks;
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&map_q);
         ptx::prefetch_tensormap(&map_c);
         ptx::mbar_init(&bars->a_full, 4);
         for (int i = 0; i < p.n_stages; ++i) {
@@ -277,17 +276,23 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---------------- TMA producer ----------------
+            // ---------------- TMA producer: corpus tiles of every unit of this CTA, back to back ----------------
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int row0 = (int)(row_begin + (int64_t)t * TC_N);
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    ptx::mbar_wait(&bars->b_empty[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&bars->b_full[stage], TC_B_STAGE_BYTES);
-                    ptx::tma_load_2d_hint(smem_b + (size_t)stage * TC_B_STAGE_BYTES, &map_c, &bars->b_full[stage],
-                                          kc * TC_KC, row0, ptx::kEvictFirst);
-                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int slice = u / p.n_qblocks;
+                const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
+                const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
+                const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int row0 = (int)(row_begin + (int64_t)t * TC_N);
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        ptx::mbar_wait(&bars->b_empty[stage], phase ^ 1);
+                        ptx::mbar_expect_tx(&bars->b_full[stage], TC_B_STAGE_BYTES);
+                        ptx::tma_load_2d(smem_b + (size_t)stage * TC_B_STAGE_BYTES, &map_c, &bars->b_full[stage],
+                                         kc * TC_KC, row0);
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -295,120 +300,140 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
             constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_M, TC_N);
-            ptx::mbar_wait(&bars->a_full, 0);
-            ptx::tc_fence_after();
             const uint32_t b_base = ptx::smem_u32(smem_b);
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int as = t % TS_ACC;
-                const uint32_t aph = (uint32_t)(t / TS_ACC) & 1u;
-                ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+            int it = 0;           // tiles issued by this CTA so far (accumulator stage / phase)
+            int ui = 0;           // units started (phase of a_full)
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+                const int slice = u / p.n_qblocks;
+                const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
+                const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
+                const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+                ptx::mbar_wait(&bars->a_full, (uint32_t)ui & 1u);      // this unit's query block is in TMEM
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(TS_ACC_COL0 + as * TC_N);
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    ptx::mbar_wait(&bars->b_full[stage], phase);
+                for (int t = 0; t < n_tiles; ++t, ++it) {
+                    const int as = it % TS_ACC;
+                    const uint32_t aph = (uint32_t)(it / TS_ACC) & 1u;
+                    ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
                     ptx::tc_fence_after();
-                    const uint32_t a_tmem = tmem_base + (uint32_t)(kc * (TC_KC / 2));
-                    const uint32_t b_addr = b_base + (uint32_t)stage * TC_B_STAGE_BYTES;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(TS_ACC_COL0 + as * TC_N);
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        ptx::mbar_wait(&bars->b_full[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t a_tmem = tmem_base + (uint32_t)(kc * (TC_KC / 2));
+                        const uint32_t b_addr = b_base + (uint32_t)stage * TC_B_STAGE_BYTES;
 #pragma unroll
-                    for (int k4 = 0; k4 < TC_KC / 16; ++k4) {
-                        ptx::umma_f16_ts(d_tmem, a_tmem + k4 * 8, ptx::make_desc_sw128(b_addr + k4 * 32), idesc,
-                                         (uint32_t)((kc | k4) != 0));
+                        for (int k4 = 0; k4 < TC_KC / 16; ++k4) {
+                            ptx::umma_f16_ts(d_tmem, a_tmem + k4 * 8, ptx::make_desc_sw128(b_addr + k4 * 32), idesc,
+                                             (uint32_t)((kc | k4) != 0));
+                        }
+                        ptx::umma_commit(&bars->b_empty[stage]);
+                        if (kc == p.kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
-                    ptx::umma_commit(&bars->b_empty[stage]);          // frees the smem stage when the MMAs retire
-                    if (kc == p.kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
-                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else {
-        // ---------------- epilogue: one query row per thread ----------------
-        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        // ---------------- epilogue warps: stage the query block, then one query row per thread ----------------
+        const int quad = warp & 3;
         const int m = quad * 32 + lane;
-        const int qg = q0 + m;
-        const bool active = qg < p.n_queries;
         const int k = p.k;
-        int want = -1;
-        if (FILTER && active) want = p.q_group[qg];
-        float ts[KT];
-        int ti[KT];
+        int it = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int slice = u / p.n_qblocks;
+            const int q0 = (u % p.n_qblocks) * TC_M;
+            const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
+            const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
+            const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+            const int qg = q0 + m;
+            const bool active = qg < p.n_queries;
+            int want = -1;
+            if (FILTER && active) want = p.q_group[qg];
+            // All MMAs of the previous unit have retired (its last acc_full was waited on below), so the A
+            // columns may be overwritten: 64 bf16 (= 32 packed 32-bit columns) per tcgen05.st.
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(p.queries + (int64_t)(active ? qg : 0) * p.ldq);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    uint32_t r[32];
 #pragma unroll
-        for (int j = 0; j < KT; ++j) { ts[j] = -INFINITY; ti[j] = -1; }
-        float thr = -INFINITY;
-
-        // stage this thread's query row into tensor memory: 64 bf16 (= 32 packed columns) per tcgen05.st
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(p.queries + (int64_t)(active ? qg : 0) * p.ldq);
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-                uint32_t r[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (active) v = __ldg(src + kc * 8 + j);
-                    r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
-                }
-                ptx::tmem_st_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kc * (TC_KC / 2)), r);
-            }
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bars->a_full);
-        }
-
-        for (int t = 0; t < n_tiles; ++t) {
-            const int as = t % TS_ACC;
-            const uint32_t aph = (uint32_t)(t / TS_ACC) & 1u;
-            ptx::mbar_wait(&bars->acc_full[as], aph);
-            ptx::tc_fence_after();
-            const int64_t row0 = row_begin + (int64_t)t * TC_N;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TS_ACC_COL0 + as * TC_N);
-#pragma unroll
-            for (int half = 0; half < TC_N / 32; ++half) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr + half * 32, r);
-                ptx::tmem_ld_wait();
-                if (half == TC_N / 32 - 1) {
-                    // accumulator stage is in registers: hand it back to the MMA warp
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float v = __uint_as_float(r[j]) + 0.0f;       // -0.0 -> +0.0
-                    const int64_t doc = row0 + half * 32 + j;
-                    bool ok = active && doc < row_end && v >= thr;
-                    if (FILTER) {
-                        if (ok && want != -1) ok = (__ldg(p.doc_group + doc) == want);
+                    for (int j = 0; j < 8; ++j) {
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (active) v = __ldg(src + kc * 8 + j);
+                        r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
                     }
-                    if (ok) {
-                        // candidates arrive in increasing id order, so on equal score the newcomer (higher id)
-                        // ranks first under the canonical order: ">=" everywhere.
-                        float cv = v;
-                        int ci = (int)doc + p.id_base;
+                    ptx::tmem_st_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kc * (TC_KC / 2)), r);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars->a_full);
+            }
+            float ts[KT];
+            int ti[KT];
 #pragma unroll
-                        for (int s = 0; s < KT; ++s) {
-                            const bool b = cv >= ts[s];
-                            const float fs = ts[s];
-                            const int is = ti[s];
-                            ts[s] = b ? cv : fs;
-                            ti[s] = b ? ci : is;
-                            cv = b ? fs : cv;
-                            ci = b ? is : ci;
+            for (int j = 0; j < KT; ++j) { ts[j] = -INFINITY; ti[j] = -1; }
+            float thr = -INFINITY;
+
+            for (int t = 0; t < n_tiles; ++t, ++it) {
+                const int as = it % TS_ACC;
+                const uint32_t aph = (uint32_t)(it / TS_ACC) & 1u;
+                ptx::mbar_wait(&bars->acc_full[as], aph);
+                ptx::tc_fence_after();
+                const int64_t row0 = row_begin + (int64_t)t * TC_N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TS_ACC_COL0 + as * TC_N);
+#pragma unroll
+                for (int half = 0; half < TC_N / 32; ++half) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(taddr + half * 32, r);
+                    ptx::tmem_ld_wait();
+                    if (half == TC_N / 32 - 1) {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
+                    }
+                    // cheap pre-test on the 32 values: most tiles contain nothing above the threshold
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    if (!(active && mx >= thr)) continue;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]) + 0.0f;       // -0.0 -> +0.0
+                        const int64_t doc = row0 + half * 32 + j;
+                        bool ok = doc < row_end && v >= thr;
+                        if (FILTER) {
+                            if (ok && want != -1) ok = (__ldg(p.doc_group + doc) == want);
                         }
-                        thr = ts[KT - 1];
+                        if (ok) {
+                            // candidates arrive in increasing id order, so on equal score the newcomer (higher id)
+                            // ranks first under the canonical order: ">=" everywhere.
+                            float cv = v;
+                            int ci = (int)doc + p.id_base;
+#pragma unroll
+                            for (int s = 0; s < KT; ++s) {
+                                const bool b = cv >= ts[s];
+                                const float fs = ts[s];
+                                const int is = ti[s];
+                                ts[s] = b ? cv : fs;
+                                ti[s] = b ? ci : is;
+                                cv = b ? fs : cv;
+                                ci = b ? is : ci;
+                            }
+                            thr = ts[KT - 1];
+                        }
                     }
                 }
             }
-        }
-        if (active) {
-            const int64_t o = ((int64_t)qg * p.n_slices + slice) * k;
+            if (active) {
+                const int64_t o = ((int64_t)qg * p.n_slices + slice) * k;
 #pragma unroll
-            for (int s = 0; s < KT; ++s) {
-                if (s < k) {
-                    p.part_s[o + s] = ts[s];
-                    p.part_id[o + s] = ti[s];
+                for (int s = 0; s < KT; ++s) {
+                    if (s < k) {
+                        p.part_s[o + s] = ts[s];
+                        p.part_id[o + s] = ti[s];
+                    }
                 }
             }
         }
@@ -467,6 +492,27 @@ static int tc_rows_per_slice(int64_t n_rows, int slices) {
     return (int)((tiles + slices - 1) / slices) * TC_N;
 }
 
+// TS variant: number of corpus splits.  Units = splits x query blocks are walked by `sms` persistent CTAs.
+// Cost model: makespan = waves x (unit length + re-warm time of the per-thread top-k lists), in units of the time
+// one CTA needs to stream the whole corpus (~45 GB/s per SM); re-warming costs ~20 us per unit.
+static int ts_choose_splits(int qblocks, int64_t n_rows, int dim, int sms) {
+    const int64_t tiles = (n_rows + TC_N - 1) / TC_N;
+    int64_t max_s = tiles / 4;                 // at least 4 tiles per unit
+    if (max_s > sms) max_s = sms;
+    if (max_s < 1) max_s = 1;
+    const double t_corpus = (double)n_rows * dim * 2 / 45e9;
+    const double eps = 20e-6 / (t_corpus > 1e-9 ? t_corpus : 1e-9);
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= (int)max_s; ++s) {
+        const int64_t units = (int64_t)qblocks * s;
+        const int64_t waves = (units + sms - 1) / sms;
+        const double cost = (double)waves * (1.0 / s + eps);
+        if (cost < best_cost * (1 - 1e-9)) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
 bool dense_tc_supported(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t ldc, const __nv_bfloat16* queries,
                         int n_queries, int64_t ldq, int k) {
     if (dim % TC_KC != 0 || dim > TC_MAXD || dim <= 0) return false;
@@ -498,9 +544,10 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     p.ldq = ldq;
     p.dim = dim;
     p.n_rows = n_rows;
-    p.n_slices = tc_slices(n_rows);
+    p.n_qblocks = (n_queries + TC_M - 1) / TC_M;
+    p.n_slices = variant == 1 ? ts_choose_splits(p.n_qblocks, n_rows, dim, sm_count()) : tc_slices(n_rows);
     p.rows_per_slice = tc_rows_per_slice(n_rows, p.n_slices);
-    // with the rounded-up slice size the last slices may be empty: shrink the grid to non-empty ones
+    // with the rounded-up slice size the last slices may be empty: shrink to the non-empty ones
     p.n_slices = (int)((n_rows + p.rows_per_slice - 1) / p.rows_per_slice);
     p.n_queries = n_queries;
     p.kchunks = dim / TC_KC;
@@ -543,7 +590,11 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
         EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
         attr_done[vi][filter ? 1 : 0][kt] = true;
     }
-    dim3 grid(p.n_slices, (n_queries + TC_M - 1) / TC_M);
+    dim3 grid(p.n_slices, p.n_qblocks);
+    if (variant == 1) {
+        const int units = p.n_slices * p.n_qblocks;
+        grid = dim3(units < sm_count() ? units : sm_count(), 1);
+    }
     {
         ProfScope prof(EZR_PROF_DENSE_TC, st);
         kern<<<grid, TC_THREADS, smem, st>>>(map_q, map_c, p);

@@ -1,0 +1,186 @@
+"""GPU: embedding forward pass (tcgen05 GEMMs, attention, norms, pooling) vs PyTorch fp32 and vs the reference model.
+
+Tolerances: the north star allows 1e-3 on cosine scores for the bf16 embedding path; per-op checks compare the
+bf16 kernels with an fp32 evaluation of the same bf16 inputs (error budget = bf16 output rounding, 2^-8 relative).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import encoder as oenc
+from easyrag_b200 import _lib, encoder as enc
+from easyrag_b200.encoder import BertConfig, BertEncoder, PackedBatch, Qwen2Config, Qwen2Encoder, random_state
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = Path(__file__).parent / "golden" / "qwen2_tiny.npz"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _ready(lib_built):
+    _lib.require_cuda()
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16)
+
+
+def _close(got, ref, rtol=2e-2, atol=2e-2):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    assert (err <= tol).all(), f"max err {err.max().item():.4g} (ref scale {ref.abs().max().item():.3g})"
+
+
+# ----------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("m,n,k", [(300, 256, 128), (1000, 768, 768), (4099, 3072, 768), (77, 2304, 768), (128, 128, 64),
+                                   (33, 200, 192)])
+def test_gemm_bias(m, n, k):
+    a, w, b = _rand(m, k, seed=1), _rand(n, k, seed=2, scale=0.05), _rand(n, seed=3)
+    got = enc.gemm(a.to(DEV), w.to(DEV), bias=b.to(DEV))
+    ref = a.float() @ w.float().T + b.float()
+    _close(got, ref)
+
+
+def test_gemm_exact_small_integers():
+    # integer-valued operands: every partial sum is exact, so the tensor-core result must be bit-exact
+    g = torch.Generator().manual_seed(5)
+    a = torch.randint(-3, 4, (513, 256), generator=g).to(torch.bfloat16)
+    w = torch.randint(-3, 4, (384, 256), generator=g).to(torch.bfloat16)
+    got = enc.gemm(a.to(DEV), w.to(DEV)).float().cpu()
+    ref = (a.float() @ w.float().T).to(torch.bfloat16).float()
+    assert torch.equal(got, ref)
+
+
+def test_gemm_gelu_and_residual():
+    m, n, k = 700, 1024, 256
+    a, w, b, r = _rand(m, k, seed=1), _rand(n, k, seed=2, scale=0.05), _rand(n, seed=3), _rand(m, n, seed=4)
+    got = enc.gemm(a.to(DEV), w.to(DEV), bias=b.to(DEV), epilogue=enc.EPI_GELU)
+    _close(got, F.gelu(a.float() @ w.float().T + b.float()))
+    x = r.to(DEV).clone()
+    got = enc.gemm(a.to(DEV), w.to(DEV), bias=b.to(DEV), residual=x, out=x)       # in place, as the layers use it
+    _close(got, a.float() @ w.float().T + b.float() + r.float())
+
+
+def test_gemm_swiglu_interleaved():
+    m, ffn, d = 500, 512, 256
+    x, wg, wu = _rand(m, d, seed=1), _rand(ffn, d, seed=2, scale=0.08), _rand(ffn, d, seed=3, scale=0.08)
+    wgu = enc._interleave_gate_up(wg.float(), wu.float()).to(torch.bfloat16)
+    got = enc.gemm(x.to(DEV), wgu.to(DEV), epilogue=enc.EPI_SWIGLU)
+    assert got.shape == (m, ffn)
+    ref = F.silu(x.float() @ wg.float().T) * (x.float() @ wu.float().T)
+    _close(got, ref)
+
+
+# ------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("hd,H,KV", [(64, 4, 4), (64, 6, 2), (128, 2, 1)])
+def test_attention_packed_bidirectional(hd, H, KV):
+    lens = [1, 5, 64, 65, 200, 37, 128]
+    t = sum(lens)
+    qkv = _rand(t, (H + 2 * KV) * hd, seed=hd + H, scale=0.7)
+    cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=DEV)
+    got = enc.attention(qkv.to(DEV), cu, max(lens), H, KV, hd).float().cpu()
+    q = qkv.float()[:, :H * hd].view(t, H, hd)
+    k = qkv.float()[:, H * hd:(H + KV) * hd].view(t, KV, hd).repeat_interleave(H // KV, 1)
+    v = qkv.float()[:, (H + KV) * hd:].view(t, KV, hd).repeat_interleave(H // KV, 1)
+    o = 0
+    for n in lens:
+        qq, kk, vv = (z[o:o + n].transpose(0, 1) for z in (q, k, v))
+        ref = torch.softmax(qq @ kk.transpose(1, 2) / hd ** 0.5, -1) @ vv             # [H, n, hd], non-causal
+        _close(got[o:o + n].view(n, H, hd).transpose(0, 1), ref, rtol=2e-2, atol=1e-2)
+        o += n
+
+
+# ------------------------------------------------------------------------- norms, rope, pool
+def test_rmsnorm_layernorm():
+    x, g, b = _rand(333, 768, seed=1, scale=3), 1 + _rand(768, seed=2, scale=0.1), _rand(768, seed=3)
+    _close(enc.rmsnorm(x.to(DEV), g.to(DEV), 1e-6), oenc._rms(x.float(), g.float(), 1e-6), rtol=1e-2, atol=1e-2)
+    _close(enc.layernorm(x.to(DEV), g.to(DEV), b.to(DEV), 1e-12),
+           F.layer_norm(x.float(), (768,), g.float(), b.float(), 1e-12), rtol=1e-2, atol=1e-2)
+
+
+def test_pool_normalize_modes():
+    L = _lib.lib()
+    lens = [3, 1, 17]
+    h = _rand(sum(lens), 256, seed=9)
+    cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=DEV)
+    hd = h.to(DEV)
+    for pool, pick in ((enc.POOL_LAST, lambda s: s[-1]), (enc.POOL_CLS, lambda s: s[0]), (enc.POOL_MEAN, lambda s: s.mean(0))):
+        ob = torch.empty(3, 256, dtype=torch.bfloat16, device=DEV)
+        of = torch.empty(3, 256, dtype=torch.float32, device=DEV)
+        _lib.check(L.ezr_pool_normalize(_lib.ptr(hd), 256, _lib.ptr(cu), 3, pool, 0, None, 0.0, 2, 256, _lib.ptr(ob),
+                                        _lib.ptr(of), _lib.stream_ptr()))
+        o = 0
+        for i, n in enumerate(lens):
+            ref = F.normalize(pick(h.float()[o:o + n]), dim=0)
+            assert (of[i].cpu() - ref).abs().max() < 1e-5
+            o += n
+
+
+# ------------------------------------------------------------------------ whole encoders
+def _golden():
+    z = np.load(GOLD)
+    c = z["cfg"]
+    cfg = Qwen2Config(vocab_size=int(c[0]), hidden_size=int(c[1]), intermediate_size=int(c[2]),
+                      num_hidden_layers=int(c[3]), num_attention_heads=int(c[4]), num_key_value_heads=int(c[5]),
+                      max_position_embeddings=int(c[6]), rms_norm_eps=float(z["rms_norm_eps"][0]),
+                      rope_theta=float(z["rope_theta"][0]))
+    state = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
+    return z, cfg, state
+
+
+def _cos_rows(a, b):
+    a, b = torch.as_tensor(a).float(), torch.as_tensor(b).float()
+    return F.cosine_similarity(a, b, dim=1)
+
+
+def test_qwen2_encoder_matches_reference_model_golden():
+    """CUDA path vs vectors produced by the reference's own vendored Qwen2Model (tests/golden/qwen2_tiny.npz)."""
+    z, cfg, state = _golden()
+    model = Qwen2Encoder(cfg, state, device=DEV)
+    batch = PackedBatch.from_padded(torch.from_numpy(z["input_ids"]), torch.from_numpy(z["attention_mask"]), DEV)
+    eb, ef = model.embed_packed(batch)
+    ef = ef.cpu()
+    assert (_cos_rows(ef, z["emb_fp32"]) > 1 - 1e-3).all()          # vs the fp32 evaluation of the reference
+    assert (_cos_rows(ef, z["emb_bf16"]) > 1 - 1e-3).all()          # vs the reference run in its own dtype (bf16)
+    assert (ef - torch.from_numpy(z["emb_fp32"])).abs().max() < 2e-2
+    # scores a retriever would see: query x chunk cosine within 1e-3 of the reference's
+    ref = torch.from_numpy(z["emb_fp32"])
+    assert ((ef @ ef.T) - (ref @ ref.T)).abs().max() < 1e-3 * 3     # both factors carry bf16 error
+    assert torch.equal(eb.float().cpu(), ef)                          # API floats are exactly the bf16 index rows
+
+
+def test_qwen2_encoder_768d_vs_oracle_ragged():
+    cfg = Qwen2Config(vocab_size=2000, hidden_size=768, intermediate_size=3072, num_hidden_layers=3,
+                      num_attention_heads=12, num_key_value_heads=4, max_position_embeddings=1024)
+    state = random_state("qwen2", cfg, 11, std=0.03)
+    g = torch.Generator().manual_seed(12)
+    lens = [8, 48, 64, 129, 300, 511, 17, 1]
+    seqs = [torch.randint(1, cfg.vocab_size, (n,), generator=g).tolist() for n in lens]
+    ids, mask = oenc.pad_left(seqs)
+    ref = oenc.gte_embed(state, cfg, ids, mask)
+    model = Qwen2Encoder(cfg, state, device=DEV)
+    _, ef = model.embed_packed(PackedBatch.from_padded(ids, mask, DEV))
+    assert (_cos_rows(ef.cpu(), ref) > 1 - 1e-3).all()
+    # packed with positions from 0 (right-padding view): RoPE is relative, same vectors
+    _, ef0 = model.embed_packed(PackedBatch.from_lists(seqs, DEV))
+    assert (_cos_rows(ef0.cpu(), ref) > 1 - 1e-3).all()
+
+
+@pytest.mark.parametrize("pooling", ["cls", "mean"])
+def test_bert_encoder_vs_transformers(pooling):
+    cfg = BertConfig(vocab_size=3000, hidden_size=768, intermediate_size=3072, num_hidden_layers=3,
+                     num_attention_heads=12, max_position_embeddings=512)
+    state = random_state("bert", cfg, 21, std=0.03)
+    g = torch.Generator().manual_seed(22)
+    lens = [5, 33, 64, 200, 512, 1]
+    seqs = [torch.randint(1, cfg.vocab_size, (n,), generator=g).tolist() for n in lens]
+    ref = oenc.bert_embed(state, cfg, seqs, pooling=pooling)
+    model = BertEncoder(cfg, state, device=DEV, pooling=pooling)
+    _, ef = model.embed_packed(PackedBatch.from_lists(seqs, DEV))
+    assert (_cos_rows(ef.cpu(), ref) > 1 - 1e-3).all()
+    assert (ef.cpu() - ref).abs().max() < 2e-2
