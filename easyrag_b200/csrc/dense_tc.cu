@@ -393,35 +393,42 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
                     }
-                    // cheap pre-test on the 32 values: most tiles contain nothing above the threshold
+                    // Fast path (straight-line, static register indices): the maximum of the 32 scores.  After the
+                    // lists have warmed up almost every batch of 32 ends here.
                     float mx = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-                    if (!(active && mx >= thr)) continue;
+                    if (active && mx >= thr) {
+                        // Slow path: ONE copy of the insertion code, walked with a runtime index over a local copy of
+                        // the scores (an unrolled version is ~100 KB of SASS and thrashes the instruction cache).
+                        float tmp[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float v = __uint_as_float(r[j]) + 0.0f;       // -0.0 -> +0.0
-                        const int64_t doc = row0 + half * 32 + j;
-                        bool ok = doc < row_end && v >= thr;
-                        if (FILTER) {
-                            if (ok && want != -1) ok = (__ldg(p.doc_group + doc) == want);
-                        }
-                        if (ok) {
-                            // candidates arrive in increasing id order, so on equal score the newcomer (higher id)
-                            // ranks first under the canonical order: ">=" everywhere.
-                            float cv = v;
-                            int ci = (int)doc + p.id_base;
-#pragma unroll
-                            for (int s = 0; s < KT; ++s) {
-                                const bool b = cv >= ts[s];
-                                const float fs = ts[s];
-                                const int is = ti[s];
-                                ts[s] = b ? cv : fs;
-                                ti[s] = b ? ci : is;
-                                cv = b ? fs : cv;
-                                ci = b ? is : ci;
+                        for (int j = 0; j < 32; ++j) tmp[j] = __uint_as_float(r[j]);
+#pragma unroll 1
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = tmp[j] + 0.0f;                      // -0.0 -> +0.0
+                            const int64_t doc = row0 + half * 32 + j;
+                            bool ok = doc < row_end && v >= thr;
+                            if (FILTER) {
+                                if (ok && want != -1) ok = (__ldg(p.doc_group + doc) == want);
                             }
-                            thr = ts[KT - 1];
+                            if (ok) {
+                                // candidates arrive in increasing id order, so on equal score the newcomer (higher
+                                // id) ranks first under the canonical order: ">=" everywhere.
+                                float cv = v;
+                                int ci = (int)doc + p.id_base;
+#pragma unroll
+                                for (int s = 0; s < KT; ++s) {
+                                    const bool b = cv >= ts[s];
+                                    const float fs = ts[s];
+                                    const int is = ti[s];
+                                    ts[s] = b ? cv : fs;
+                                    ti[s] = b ? ci : is;
+                                    cv = b ? fs : cv;
+                                    ci = b ? is : ci;
+                                }
+                                thr = ts[KT - 1];
+                            }
                         }
                     }
                 }

@@ -148,9 +148,16 @@ def test_qwen2_encoder_matches_reference_model_golden():
     assert (_cos_rows(ef, z["emb_fp32"]) > 1 - 1e-3).all()          # vs the fp32 evaluation of the reference
     assert (_cos_rows(ef, z["emb_bf16"]) > 1 - 1e-3).all()          # vs the reference run in its own dtype (bf16)
     assert (ef - torch.from_numpy(z["emb_fp32"])).abs().max() < 2e-2
-    # scores a retriever would see: query x chunk cosine within 1e-3 of the reference's
+    # Scores a retriever would see (qdrant re-normalises for COSINE): pairwise cosines vs the reference's fp32 run.
+    # This fixture is a stress case (weights ~ N(0, 0.06^2)): the reference's OWN bf16 run deviates from its fp32
+    # run by 1.9e-3 here (and by 5.1e-3 before re-normalisation: F.normalize divides by a bf16-rounded norm), so
+    # that is the noise floor; we must stay within it plus the 1e-3 budget of the north star.
     ref = torch.from_numpy(z["emb_fp32"])
-    assert ((ef @ ef.T) - (ref @ ref.T)).abs().max() < 1e-3 * 3     # both factors carry bf16 error
+    refb = F.normalize(torch.from_numpy(z["emb_bf16"]), dim=1)
+    floor = ((refb @ refb.T) - (ref @ ref.T)).abs().max().item()
+    mine = F.normalize(ef, dim=1)
+    err = ((mine @ mine.T) - (ref @ ref.T)).abs().max().item()
+    assert err <= floor + 1e-3, (err, floor)
     assert torch.equal(eb.float().cpu(), ef)                          # API floats are exactly the bf16 index rows
 
 
@@ -166,6 +173,9 @@ def test_qwen2_encoder_768d_vs_oracle_ragged():
     model = Qwen2Encoder(cfg, state, device=DEV)
     _, ef = model.embed_packed(PackedBatch.from_padded(ids, mask, DEV))
     assert (_cos_rows(ef.cpu(), ref) > 1 - 1e-3).all()
+    mine = F.normalize(ef.cpu(), dim=1)
+    err = ((mine @ mine.T) - (ref @ ref.T)).abs().max().item()
+    assert err < 1e-3, f"pairwise cosine error {err:.2e} vs the fp32 oracle exceeds the 1e-3 budget"
     # packed with positions from 0 (right-padding view): RoPE is relative, same vectors
     _, ef0 = model.embed_packed(PackedBatch.from_lists(seqs, DEV))
     assert (_cos_rows(ef0.cpu(), ref) > 1 - 1e-3).all()
