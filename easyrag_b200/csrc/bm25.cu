@@ -72,6 +72,7 @@ __global__ void bm25_range_index_kernel(const int64_t* __restrict__ indptr, cons
 constexpr int kBmRange = 8192;   // documents per CTA: 64 KB of float64 accumulators
 constexpr int kBmThreads = 512;
 constexpr int kBmMaxT = 12;      // query terms preloaded per round (queries are 4-12 terms; longer ones loop)
+constexpr int kBmRpc = 4;        // document ranges per CTA (software-pipelined)
 
 struct Bm25Params {
     const int64_t* indptr;
@@ -102,192 +103,233 @@ template <> struct KeyOf<float> {
 };
 
 // MODE 0: fused top-k (k<=32) -> per-(query,range) partial lists.  MODE 1: write the score row.
+// A CTA owns one query and kBmRpc consecutive document ranges.  Range i+1's first postings are issued right after
+// range i's accumulation, so their latency hides behind range i's selection phases; term ids / indptr / range
+// offsets are fetched once per CTA.
 template <typename S, int MODE>
 __global__ void __launch_bounds__(kBmThreads, 3)
 bm25_score_kernel(const Bm25Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S* acc = reinterpret_cast<S*>(smem_raw);
-    __shared__ int s_beg[kBmMaxT];
-    __shared__ int s_len[kBmMaxT];
+    __shared__ int s_off[kBmRpc + 1][kBmMaxT];      // first-chunk terms: absolute posting offset at each range boundary
+    __shared__ int s_lo[kBmMaxT], s_len2[kBmMaxT];  // later chunks of long queries (> kBmMaxT terms), per range
     __shared__ S s_ws[kBmThreads];
     __shared__ int s_wi[kBmThreads];
     __shared__ int s_thr;
     __shared__ int s_cnt;
 
     const int q = blockIdx.x;
-    const int r = blockIdx.y;
+    const int r0 = blockIdx.y * kBmRpc;
+    const int n_r = min(kBmRpc, p.n_ranges - r0);
     const int tid = threadIdx.x;
-    const int rbase = r * kBmRange;
-    const int rn = (int)min((int64_t)kBmRange, p.n_docs - rbase);
+    const int lane = tid & 31, warp = tid >> 5;
     const int qs = p.q_ptr[q];
     const int m = p.q_ptr[q + 1] - qs;
+    const int m0 = min(m, kBmMaxT);
     const S* __restrict__ post_w = reinterpret_cast<const S*>(p.post_w);
     const int32_t* __restrict__ post_doc = p.post_doc;
     constexpr int kVec = 16 / sizeof(S);                        // scores per 128-bit shared-memory access
+    constexpr int kPer = kBmRange / kBmThreads;                 // documents scanned per thread
+    const int want = (MODE == 0 && p.q_group) ? p.q_group[q] : -1;
 
-    for (int tb = 0; tb < m; tb += kBmMaxT) {
-        const int mt = min(kBmMaxT, m - tb);
-        if (tid < mt) {
-            const int t = p.q_terms[qs + tb + tid];
-            int beg = 0, len = 0;
-            if (t >= 0 && t < p.vocab) {
-                const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
-                const uint32_t o0 = ro[0], o1 = ro[1];
-                beg = (int)(p.indptr[t] + o0);                  // n_postings < 2^31 (checked on the host)
-                len = (int)(o1 - o0);
-            }
-            s_beg[tid] = beg;
-            s_len[tid] = len;
+    if (tid < m0) {
+        const int t = p.q_terms[qs + tid];
+        if (t >= 0 && t < p.vocab) {
+            const int base = (int)p.indptr[t];                  // n_postings < 2^31 (checked on the host)
+            const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r0;
+#pragma unroll
+            for (int i = 0; i <= kBmRpc; ++i) s_off[i][tid] = base + (int)ro[min(i, n_r)];
+        } else {
+#pragma unroll
+            for (int i = 0; i <= kBmRpc; ++i) s_off[i][tid] = 0;
         }
-        __syncthreads();
-        // issue the first posting of every term before touching shared memory: all loads of the round are in
-        // flight together
-        int d[kBmMaxT];
-        S w[kBmMaxT];
+    }
+    __syncthreads();
+
+    int d[kBmMaxT];
+    S w[kBmMaxT];
+    // first posting of every (first-chunk) term of range 0: all loads in flight together
+#pragma unroll
+    for (int j = 0; j < kBmMaxT; ++j) {
+        d[j] = -1;
+        w[j] = (S)0;
+        if (j < m0) {
+            const int beg = s_off[0][j];
+            if (tid < s_off[1][j] - beg) { d[j] = __ldg(post_doc + beg + tid); w[j] = __ldg(post_w + beg + tid); }
+        }
+    }
+    {
+        uint4* a4 = reinterpret_cast<uint4*>(acc);
+#pragma unroll
+        for (int i = 0; i < kBmRange / kVec / kBmThreads; ++i) a4[tid + i * kBmThreads] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+
+    for (int ri = 0; ri < n_r; ++ri) {
+        const int r = r0 + ri;
+        const int rbase = r * kBmRange;
+        const int rn = (int)min((int64_t)kBmRange, p.n_docs - rbase);
+
+        // ---- accumulate: terms strictly in token order, one barrier per term (float sum order of the reference)
 #pragma unroll
         for (int j = 0; j < kBmMaxT; ++j) {
-            d[j] = -1;
-            w[j] = (S)0;
-            if (j < mt && tid < s_len[j]) {
-                const int pp = s_beg[j] + tid;
-                d[j] = __ldg(post_doc + pp);
-                w[j] = __ldg(post_w + pp);
+            if (j < m0) {   // block-uniform
+                if (d[j] >= 0) acc[d[j] - rbase] += w[j];
+                const int beg = s_off[ri][j];
+                const int len = s_off[ri + 1][j] - beg;
+                for (int o = tid + kBmThreads; o < len; o += kBmThreads)           // segments longer than the CTA
+                    acc[__ldg(post_doc + beg + o) - rbase] += __ldg(post_w + beg + o);
+                __syncthreads();
             }
         }
-        if (tb == 0) {
+        for (int tb = kBmMaxT; tb < m; tb += kBmMaxT) {          // queries longer than kBmMaxT terms (rare)
+            const int mt = min(kBmMaxT, m - tb);
+            if (tid < mt) {
+                const int t = p.q_terms[qs + tb + tid];
+                int beg = 0, len = 0;
+                if (t >= 0 && t < p.vocab) {
+                    const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
+                    const uint32_t o0 = ro[0], o1 = ro[1];
+                    beg = (int)p.indptr[t] + (int)o0;
+                    len = (int)(o1 - o0);
+                }
+                s_lo[tid] = beg;
+                s_len2[tid] = len;
+            }
+            __syncthreads();
+            for (int j = 0; j < mt; ++j) {
+                const int beg = s_lo[j], len = s_len2[j];
+                for (int o = tid; o < len; o += kBmThreads)
+                    acc[__ldg(post_doc + beg + o) - rbase] += __ldg(post_w + beg + o);
+                __syncthreads();
+            }
+        }
+
+        // ---- prefetch the next range's first postings: they land while this range is being selected from
+        const bool more = ri + 1 < n_r;
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < kBmMaxT; ++j) {
+                d[j] = -1;
+                if (j < m0) {
+                    const int beg = s_off[ri + 1][j];
+                    if (tid < s_off[ri + 2][j] - beg) { d[j] = __ldg(post_doc + beg + tid); w[j] = __ldg(post_w + beg + tid); }
+                }
+            }
+        }
+
+        if (MODE == 1) {
+            S* out = reinterpret_cast<S*>(p.out_scores) + (int64_t)q * p.n_docs + rbase;
+            for (int i = tid; i < rn; i += kBmThreads) out[i] = acc[i];
+        } else {
+            // ---- fused top-k from shared memory: threshold -> compact -> rank ----
+            // 1. every half-warp finds the best key among the documents it scans; the k-th largest of those 32 group
+            //    maxima is a lower bound of the range's k-th best score (32 distinct documents), and a tight one: on
+            //    average only ~k/2 extra documents pass it.  Keys = high words of the scores (KeyOf).
+            // 2. documents whose key reaches the bound are appended to a small candidate list (smem atomics).
+            // 3. each candidate counts how many candidates rank before it under the canonical order and writes
+            //    itself to that output slot.  No sort, no serial insertion chain.
+            // Exact ties at the bound (or fewer than k non-empty groups) can overflow the list; then the robust
+            // warp-shuffle selection takes over.  Rows >= rn of the last range hold zeros and never qualify.
+            int tmax = 0;
+            if (want == -1) {
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) tmax = max(tmax, KeyOf<S>::load(acc, tid + i * kBmThreads));
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < kPer; ++i) {
+                    const int doc = tid + i * kBmThreads;
+                    const int key = KeyOf<S>::load(acc, doc);
+                    if (key > tmax && p.doc_group[rbase + doc] == want) tmax = key;
+                }
+            }
+            int gmax = tmax;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+            if ((lane & 15) == 0) s_wi[tid >> 4] = gmax;        // 32 group maxima (0: no positive score in the group)
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            if (warp == 0) {
+                const int mine = s_wi[lane];
+                int rank = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int o = s_wi[j];
+                    rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
+                }
+                if (rank == p.k - 1) s_thr = mine;              // ranks are a permutation: exactly one lane writes
+            }
+            __syncthreads();
+            const int thr = s_thr;                              // 0 when fewer than k groups saw a positive score
+            constexpr int kCand = kBmThreads;                   // candidate capacity (s_ws / s_wi are reused)
+            __syncthreads();                                    // s_thr / s_wi read by everyone: reuse them
+            if (tmax >= thr) {                                  // only threads owning a qualifying document re-scan
+#pragma unroll 4
+                for (int i = 0; i < kPer; ++i) {
+                    const int doc = tid + i * kBmThreads;
+                    if (KeyOf<S>::load(acc, doc) >= thr) {
+                        const S s = acc[doc];
+                        if (s > (S)0 && (want == -1 || p.doc_group[rbase + doc] == want)) {
+                            const int idx = atomicAdd(&s_cnt, 1);
+                            if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + doc; }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            const int n = s_cnt;
+            const int64_t obase = ((int64_t)q * p.n_ranges + r) * p.k;
+            S* out_s = reinterpret_cast<S*>(p.out_scores);
+            if (n <= kCand) {
+                if (tid < n) {
+                    const S ms = s_ws[tid];
+                    const int mi = s_wi[tid];
+                    int rank = 0;
+                    for (int j = 0; j < n; ++j) rank += better<S>(s_ws[j], s_wi[j], ms, mi) ? 1 : 0;
+                    if (rank < p.k) { out_s[obase + rank] = ms; p.out_ids[obase + rank] = mi; }
+                }
+                if (tid >= n && tid < p.k) { out_s[obase + tid] = ScoreTraits<S>::lowest(); p.out_ids[obase + tid] = -1; }
+            } else {
+                // ---- overflow fallback: per-warp shuffle lists, then warp 0 merges them ----
+                __syncthreads();
+                WarpTopK<S> tk;
+                tk.init(p.k);
+                for (int i0 = warp * 32; i0 < rn; i0 += kBmThreads) {
+                    const int i = i0 + lane;
+                    S s = (S)0;
+                    bool ok = false;
+                    if (i < rn) {
+                        s = acc[i];
+                        ok = s > (S)0 && better<S>(s, rbase + i, tk.kth_s, tk.kth_id);
+                        if (ok && want != -1) ok = (p.doc_group[rbase + i] == want);
+                    }
+                    tk.offer(s, rbase + i, ok);
+                }
+                __syncthreads();
+                s_ws[warp * 32 + lane] = tk.s;
+                s_wi[warp * 32 + lane] = tk.id;
+                __syncthreads();
+                if (warp == 0) {
+                    WarpTopK<S> fin;
+                    fin.init(p.k);
+                    for (int w2 = 0; w2 < kBmThreads / 32; ++w2) {
+                        const S s = s_ws[w2 * 32 + lane];
+                        const int id = s_wi[w2 * 32 + lane];
+                        fin.offer(s, id, lane < p.k && id >= 0);
+                    }
+                    if (lane < p.k) {
+                        out_s[obase + lane] = fin.s;
+                        p.out_ids[obase + lane] = fin.id;      // local id, -1 = empty
+                    }
+                }
+            }
+        }
+        if (more) {
+            __syncthreads();                                    // everyone is done with acc / s_ws / s_wi of this range
             uint4* a4 = reinterpret_cast<uint4*>(acc);
 #pragma unroll
             for (int i = 0; i < kBmRange / kVec / kBmThreads; ++i) a4[tid + i * kBmThreads] = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();
-        }
-#pragma unroll
-        for (int j = 0; j < kBmMaxT; ++j) {
-            if (j < mt) {   // block-uniform
-                if (d[j] >= 0) acc[d[j] - rbase] += w[j];
-                const int len = s_len[j];
-                for (int o = tid + kBmThreads; o < len; o += kBmThreads) {        // segments longer than the CTA
-                    const int pp = s_beg[j] + o;
-                    acc[__ldg(post_doc + pp) - rbase] += __ldg(post_w + pp);
-                }
-                __syncthreads();   // term j fully applied before term j+1: float sum order of the reference
-            }
-        }
-    }
-    if (m == 0) {
-        uint4* a4 = reinterpret_cast<uint4*>(acc);
-#pragma unroll
-        for (int i = 0; i < kBmRange / kVec / kBmThreads; ++i) a4[tid + i * kBmThreads] = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
-    }
-
-    if (MODE == 1) {
-        S* out = reinterpret_cast<S*>(p.out_scores) + (int64_t)q * p.n_docs + rbase;
-        for (int i = tid; i < rn; i += kBmThreads) out[i] = acc[i];
-        return;
-    }
-
-    // ---- fused top-k from shared memory: threshold -> compact -> rank ----
-    // 1. every half-warp finds the best key among the documents it scans; the k-th largest of those 32 group
-    //    maxima is a lower bound of the range's k-th best score (they belong to 32 distinct documents), and a tight
-    //    one: on average only ~k/2 extra documents pass it.  Keys are the high words of the scores (see KeyOf).
-    // 2. documents whose key reaches the bound are appended to a small candidate list (shared-memory atomics).
-    // 3. each candidate counts how many candidates rank before it under the canonical order and writes itself to
-    //    that output slot.  No sort, no serial insertion chain.
-    // Exact ties at the bound (or fewer than k non-empty groups) can overflow the list; then the robust
-    // warp-shuffle selection at the end takes over.  Rows >= rn of the last range hold zeros and never qualify.
-    const int lane = tid & 31, warp = tid >> 5;
-    const int want = p.q_group ? p.q_group[q] : -1;
-    constexpr int kPer = kBmRange / kBmThreads;                 // documents scanned per thread
-    int tmax = 0;
-    if (want == -1) {
-#pragma unroll
-        for (int i = 0; i < kPer; ++i) tmax = max(tmax, KeyOf<S>::load(acc, tid + i * kBmThreads));
-    } else {
-#pragma unroll 4
-        for (int i = 0; i < kPer; ++i) {
-            const int doc = tid + i * kBmThreads;
-            const int key = KeyOf<S>::load(acc, doc);
-            if (key > tmax && p.doc_group[rbase + doc] == want) tmax = key;
-        }
-    }
-    int gmax = tmax;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    if ((lane & 15) == 0) s_wi[tid >> 4] = gmax;            // 32 group maxima (0: group saw no positive score)
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    if (warp == 0) {
-        const int mine = s_wi[lane];
-        int rank = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int o = s_wi[j];
-            rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
-        }
-        if (rank == p.k - 1) s_thr = mine;                  // ranks are a permutation: exactly one lane writes
-    }
-    __syncthreads();
-    const int thr = s_thr;                                  // 0 when fewer than k groups saw a positive score
-    constexpr int kCand = kBmThreads;                       // candidate capacity (s_ws / s_wi are reused)
-    __syncthreads();                                        // s_thr / s_wi have been read by everyone: reuse them
-    if (tmax >= thr) {                                      // only threads that own a qualifying document re-scan
-#pragma unroll 4
-        for (int i = 0; i < kPer; ++i) {
-            const int doc = tid + i * kBmThreads;
-            if (KeyOf<S>::load(acc, doc) >= thr) {
-                const S s = acc[doc];
-                if (s > (S)0 && (want == -1 || p.doc_group[rbase + doc] == want)) {
-                    const int idx = atomicAdd(&s_cnt, 1);
-                    if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + doc; }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const int n = s_cnt;
-    const int64_t obase = ((int64_t)q * p.n_ranges + r) * p.k;
-    S* out_s = reinterpret_cast<S*>(p.out_scores);
-    if (n <= kCand) {
-        if (tid < n) {
-            const S ms = s_ws[tid];
-            const int mi = s_wi[tid];
-            int rank = 0;
-            for (int j = 0; j < n; ++j) rank += better<S>(s_ws[j], s_wi[j], ms, mi) ? 1 : 0;
-            if (rank < p.k) { out_s[obase + rank] = ms; p.out_ids[obase + rank] = mi; }
-        }
-        if (tid >= n && tid < p.k) { out_s[obase + tid] = ScoreTraits<S>::lowest(); p.out_ids[obase + tid] = -1; }
-        return;
-    }
-    // ---- overflow fallback: per-warp shuffle lists, then warp 0 merges them ----
-    __syncthreads();
-    WarpTopK<S> tk;
-    tk.init(p.k);
-    for (int i0 = warp * 32; i0 < rn; i0 += kBmThreads) {
-        const int i = i0 + lane;
-        S s = (S)0;
-        bool ok = false;
-        if (i < rn) {
-            s = acc[i];
-            ok = s > (S)0 && better<S>(s, rbase + i, tk.kth_s, tk.kth_id);
-            if (ok && want != -1) ok = (p.doc_group[rbase + i] == want);
-        }
-        tk.offer(s, rbase + i, ok);
-    }
-    __syncthreads();
-    s_ws[warp * 32 + lane] = tk.s;
-    s_wi[warp * 32 + lane] = tk.id;
-    __syncthreads();
-    if (warp == 0) {
-        WarpTopK<S> fin;
-        fin.init(p.k);
-        for (int w2 = 0; w2 < kBmThreads / 32; ++w2) {
-            const S s = s_ws[w2 * 32 + lane];
-            const int id = s_wi[w2 * 32 + lane];
-            fin.offer(s, id, lane < p.k && id >= 0);
-        }
-        if (lane < p.k) {
-            out_s[obase + lane] = fin.s;
-            p.out_ids[obase + lane] = fin.id;      // local id, -1 = empty
         }
     }
 }
@@ -457,7 +499,7 @@ static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int
         EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[which] = true;
     }
-    dim3 grid(n_queries, ix->n_ranges);
+    dim3 grid(n_queries, (ix->n_ranges + kBmRpc - 1) / kBmRpc);
     ProfScope prof(EZR_PROF_BM25_SCORE, st);
     kern<<<grid, kBmThreads, smem, st>>>(p);
     EZR_LAUNCH_CHECK();
@@ -469,7 +511,7 @@ static int check_index(const ezr_bm25_index* ix) {
     EZR_CHECK_ARG(ix->range_size == kBmRange, "bm25: range_size must be %d (got %d)", kBmRange, ix->range_size);
     EZR_CHECK_ARG(ix->n_docs >= 0 && ix->n_docs < ((int64_t)1 << 31), "bm25: n_docs out of range");
     EZR_CHECK_ARG(ix->n_ranges == ceil_div(ix->n_docs, kBmRange), "bm25: n_ranges != ceil(n_docs/range_size)");
-    EZR_CHECK_ARG(ix->n_ranges <= 65535, "bm25: too many ranges (%d) for one shard", ix->n_ranges);
+    EZR_CHECK_ARG(ix->n_ranges <= 65535 * kBmRpc, "bm25: too many ranges (%d) for one shard", ix->n_ranges);
     EZR_CHECK_ARG(ix->score_type == EZR_F64 || ix->score_type == EZR_F32, "bm25: bad score_type");
     EZR_CHECK_ARG(ix->n_postings >= 0 && ix->n_postings < ((int64_t)1 << 31),
                   "bm25: %lld postings in one index; shard the corpus (limit 2^31-1 per shard)", (long long)ix->n_postings);
