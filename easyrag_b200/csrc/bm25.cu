@@ -72,7 +72,7 @@ __global__ void bm25_range_index_kernel(const int64_t* __restrict__ indptr, cons
 constexpr int kBmRange = 8192;   // documents per CTA: 64 KB of float64 accumulators
 constexpr int kBmThreads = 512;
 constexpr int kBmMaxT = 12;      // query terms preloaded per round (queries are 4-12 terms; longer ones loop)
-constexpr int kBmRpc = 4;        // document ranges per CTA (software-pipelined)
+constexpr int kBmRpc = 1;        // document ranges per CTA (1: measured faster than 4 on B200)
 
 struct Bm25Params {
     const int64_t* indptr;

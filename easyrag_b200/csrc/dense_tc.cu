@@ -297,41 +297,43 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_M, TC_N);
-            const uint32_t b_base = ptx::smem_u32(smem_b);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;           // tiles issued by this CTA so far (accumulator stage / phase)
-            int ui = 0;           // units started (phase of a_full)
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-                const int slice = u / p.n_qblocks;
-                const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
-                const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
-                const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
-                ptx::mbar_wait(&bars->a_full, (uint32_t)ui & 1u);      // this unit's query block is in TMEM
+        // ---------------- MMA issuer ----------------
+        // The whole warp walks the loop (warp-uniform control flow, so descriptor arithmetic stays on the uniform
+        // datapath); only the tcgen05 instructions themselves are issued by one elected lane.
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_M, TC_N);
+        const uint64_t b_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_b));
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;           // tiles issued by this CTA so far (accumulator stage / phase)
+        int ui = 0;           // units started (phase of a_full)
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+            const int slice = u / p.n_qblocks;
+            const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
+            const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
+            const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+            ptx::mbar_wait(&bars->a_full, (uint32_t)ui & 1u);      // this unit's query block is in TMEM
+            ptx::tc_fence_after();
+            for (int t = 0; t < n_tiles; ++t, ++it) {
+                const int as = it % TS_ACC;
+                const uint32_t aph = (uint32_t)(it / TS_ACC) & 1u;
+                ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
                 ptx::tc_fence_after();
-                for (int t = 0; t < n_tiles; ++t, ++it) {
-                    const int as = it % TS_ACC;
-                    const uint32_t aph = (uint32_t)(it / TS_ACC) & 1u;
-                    ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(TS_ACC_COL0 + as * TC_N);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&bars->b_full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(TS_ACC_COL0 + as * TC_N);
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        ptx::mbar_wait(&bars->b_full[stage], phase);
-                        ptx::tc_fence_after();
-                        const uint32_t a_tmem = tmem_base + (uint32_t)(kc * (TC_KC / 2));
-                        const uint32_t b_addr = b_base + (uint32_t)stage * TC_B_STAGE_BYTES;
+                    const uint32_t a_tmem = tmem_base + (uint32_t)(kc * (TC_KC / 2));
+                    const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (TC_B_STAGE_BYTES >> 4));
+                    if (ptx::elect_one()) {
 #pragma unroll
-                        for (int k4 = 0; k4 < TC_KC / 16; ++k4) {
-                            ptx::umma_f16_ts(d_tmem, a_tmem + k4 * 8, ptx::make_desc_sw128(b_addr + k4 * 32), idesc,
+                        for (int k4 = 0; k4 < TC_KC / 16; ++k4)
+                            ptx::umma_f16_ts(d_tmem, a_tmem + k4 * 8, b_desc + (uint64_t)(k4 * 2), idesc,
                                              (uint32_t)((kc | k4) != 0));
-                        }
                         ptx::umma_commit(&bars->b_empty[stage]);
                         if (kc == p.kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
-                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }

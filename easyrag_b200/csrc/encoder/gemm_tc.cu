@@ -95,31 +95,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(GM, GN);
-            const uint32_t a_base = ptx::smem_u32(smem_a), b_base = ptx::smem_u32(smem_b);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                const int as = it % G_ACC;
-                const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
-                ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+        // whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05 instructions
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(GM, GN);
+        const uint64_t a_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_a));
+        const uint64_t b_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_b));
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int as = it % G_ACC;
+            const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
+            ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * GN);
+            for (int kc = 0; kc < kchunks; ++kc) {
+                ptx::mbar_wait(&bars->full[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * GN);
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    ptx::mbar_wait(&bars->full[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = a_base + (uint32_t)stage * G_A_BYTES;
-                    const uint32_t b_addr = b_base + (uint32_t)stage * G_B_BYTES;
+                const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (G_A_BYTES >> 4));
+                const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (G_B_BYTES >> 4));
+                if (ptx::elect_one()) {
 #pragma unroll
                     for (int k4 = 0; k4 < GK / 16; ++k4)
-                        ptx::umma_f16_ss(d_tmem, ptx::make_desc_sw128(a_addr + k4 * 32),
-                                         ptx::make_desc_sw128(b_addr + k4 * 32), idesc, (uint32_t)((kc | k4) != 0));
+                        ptx::umma_f16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc,
+                                         (uint32_t)((kc | k4) != 0));
                     ptx::umma_commit(&bars->empty[stage]);
                     if (kc == kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
-                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
