@@ -90,6 +90,7 @@ struct Bm25Params {
     int32_t id_base;
     void* out_scores;   // fused: partial [Q][n_ranges][k]; rows: [Q][n_docs]
     int32_t* out_ids;   // fused: partial ids
+    int32_t* thr_key;   // fused: [Q] running lower bound (integer key) of each query's k-th best score, zeroed per call
 };
 
 // Integer sort key of a non-negative score: IEEE-754 ordering of non-negative floats equals the ordering of their
@@ -131,6 +132,11 @@ bm25_score_kernel(const Bm25Params p) {
     constexpr int kVec = 16 / sizeof(S);                        // scores per 128-bit shared-memory access
     constexpr int kPer = kBmRange / kBmThreads;                 // documents scanned per thread
     const int want = (MODE == 0 && p.q_group) ? p.q_group[q] : -1;
+    // Lower bound of this query's k-th best score established by CTAs of earlier document ranges (range-major grid:
+    // they finished long ago).  Anything below it cannot reach the final top-k, so it may be dropped here already.
+    // ONE thread reads it (other CTAs raise it concurrently; the branch below must be block-uniform).
+    __shared__ int s_gthr;
+    if (MODE == 0 && tid == kBmThreads - 1) s_gthr = *reinterpret_cast<const volatile int32_t*>(p.thr_key + q);
 
     if (tid < m0) {
         const int t = p.q_terms[qs + tid];
@@ -146,6 +152,7 @@ bm25_score_kernel(const Bm25Params p) {
     }
     __syncthreads();
 
+    const int shared_thr = (MODE == 0) ? s_gthr : 0;
     int d[kBmMaxT];
     S w[kBmMaxT];
     // first posting of every (first-chunk) term of range 0: all loads in flight together
@@ -231,33 +238,38 @@ bm25_score_kernel(const Bm25Params p) {
             //    itself to that output slot.  No sort, no serial insertion chain.
             // Exact ties at the bound (or fewer than k non-empty groups) can overflow the list; then the robust
             // warp-shuffle selection takes over.  Rows >= rn of the last range hold zeros and never qualify.
-            int tmax = 0;
-            if (want == -1) {
-#pragma unroll
-                for (int i = 0; i < kPer; ++i) tmax = max(tmax, KeyOf<S>::load(acc, tid + i * kBmThreads));
-            } else {
-#pragma unroll 4
-                for (int i = 0; i < kPer; ++i) {
-                    const int doc = tid + i * kBmThreads;
-                    const int key = KeyOf<S>::load(acc, doc);
-                    if (key > tmax && p.doc_group[rbase + doc] == want) tmax = key;
-                }
-            }
-            int gmax = tmax;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-            if ((lane & 15) == 0) s_wi[tid >> 4] = gmax;        // 32 group maxima (0: no positive score in the group)
+            int tmax = 0x7fffffff;                              // "this thread must re-scan" when phase 1 is skipped
             if (tid == 0) s_cnt = 0;
-            __syncthreads();
-            if (warp == 0) {
-                const int mine = s_wi[lane];
-                int rank = 0;
+            if (shared_thr > 0) {
+                if (tid == 0) s_thr = shared_thr;               // single pass: the shared bound replaces phase 1
+            } else {
+                tmax = 0;
+                if (want == -1) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int o = s_wi[j];
-                    rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
+                    for (int i = 0; i < kPer; ++i) tmax = max(tmax, KeyOf<S>::load(acc, tid + i * kBmThreads));
+                } else {
+#pragma unroll 4
+                    for (int i = 0; i < kPer; ++i) {
+                        const int doc = tid + i * kBmThreads;
+                        const int key = KeyOf<S>::load(acc, doc);
+                        if (key > tmax && p.doc_group[rbase + doc] == want) tmax = key;
+                    }
                 }
-                if (rank == p.k - 1) s_thr = mine;              // ranks are a permutation: exactly one lane writes
+                int gmax = tmax;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+                if ((lane & 15) == 0) s_wi[tid >> 4] = gmax;    // 32 group maxima (0: no positive score in the group)
+                __syncthreads();
+                if (warp == 0) {
+                    const int mine = s_wi[lane];
+                    int rank = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int o = s_wi[j];
+                        rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
+                    }
+                    if (rank == p.k - 1) s_thr = mine;          // ranks are a permutation: exactly one lane writes
+                }
             }
             __syncthreads();
             const int thr = s_thr;                              // 0 when fewer than k groups saw a positive score
@@ -287,6 +299,10 @@ bm25_score_kernel(const Bm25Params p) {
                     int rank = 0;
                     for (int j = 0; j < n; ++j) rank += better<S>(s_ws[j], s_wi[j], ms, mi) ? 1 : 0;
                     if (rank < p.k) { out_s[obase + rank] = ms; p.out_ids[obase + rank] = mi; }
+                    if (rank == p.k - 1) {                      // this range alone has k documents at or above ms
+                        const int key = KeyOf<S>::load(s_ws, tid);
+                        if (key > shared_thr) atomicMax(p.thr_key + q, key);
+                    }
                 }
                 if (tid >= n && tid < p.k) { out_s[obase + tid] = ScoreTraits<S>::lowest(); p.out_ids[obase + tid] = -1; }
             } else {
@@ -485,12 +501,12 @@ static int merge_impl(const S* cs, const int32_t* cid, int n_rows, int n_cand, i
 template <typename S>
 static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t* q_terms, int n_queries,
                        int k, const int32_t* q_group, int id_base, int mode, void* out_scores, int32_t* out_ids,
-                       cudaStream_t st) {
+                       int32_t* thr_key, cudaStream_t st) {
     Bm25Params p;
     p.indptr = ix->indptr; p.post_doc = ix->post_doc; p.post_w = ix->post_w; p.range_off = ix->range_off;
     p.doc_group = ix->doc_group; p.q_ptr = q_ptr; p.q_terms = q_terms; p.q_group = q_group;
     p.n_docs = ix->n_docs; p.vocab = ix->vocab; p.n_ranges = ix->n_ranges; p.k = k; p.id_base = id_base;
-    p.out_scores = out_scores; p.out_ids = out_ids;
+    p.out_scores = out_scores; p.out_ids = out_ids; p.thr_key = thr_key;
     const size_t smem = (size_t)kBmRange * sizeof(S);
     static bool attr_done[4] = {false, false, false, false};
     const int which = (sizeof(S) == 8 ? 0 : 2) + mode;
@@ -567,7 +583,7 @@ size_t ezr_bm25_topk_workspace(const ezr_bm25_index* ix, int32_t n_queries, int3
     const size_t ss = ix->score_type == EZR_F64 ? 8 : 4;
     if (k <= 32) {
         const size_t n = (size_t)n_queries * ix->n_ranges * k;
-        return align_up(n * ss, 256) + align_up(n * 4, 256);
+        return align_up(n * ss, 256) + align_up(n * 4, 256) + align_up((size_t)n_queries * 4, 256);
     }
     // score rows, one query block at a time is the caller's job: here all rows at once
     size_t rows = align_up((size_t)n_queries * ix->n_docs * ss, 256);
@@ -601,8 +617,10 @@ int ezr_bm25_topk(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t*
         const size_t n = (size_t)n_queries * ix->n_ranges * k;
         void* ps = workspace;
         int32_t* pi = reinterpret_cast<int32_t*>((char*)workspace + align_up(n * ss, 256));
-        rc = f64 ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, st)
-                 : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, st);
+        int32_t* thr = reinterpret_cast<int32_t*>((char*)workspace + align_up(n * ss, 256) + align_up(n * 4, 256));
+        EZR_CUDA(cudaMemsetAsync(thr, 0, (size_t)n_queries * 4, st));
+        rc = f64 ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, thr, st)
+                 : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, thr, st);
         if (rc) return rc;
         const int n_cand = ix->n_ranges * k;
         return f64 ? merge_impl<double>((const double*)ps, pi, n_queries, n_cand, n_cand, k, id_base,
@@ -613,8 +631,8 @@ int ezr_bm25_topk(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t*
     void* rows = workspace;
     void* sel_ws = (char*)workspace + align_up((size_t)n_queries * ix->n_docs * ss, 256);
     const size_t sel_bytes = workspace_bytes - align_up((size_t)n_queries * ix->n_docs * ss, 256);
-    rc = f64 ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, k, nullptr, 0, 1, rows, nullptr, st)
-             : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, k, nullptr, 0, 1, rows, nullptr, st);
+    rc = f64 ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, k, nullptr, 0, 1, rows, nullptr, nullptr, st)
+             : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, k, nullptr, 0, 1, rows, nullptr, nullptr, st);
     if (rc) return rc;
     return f64 ? select_rows_impl<double>((const double*)rows, n_queries, ix->n_docs, ix->n_docs, k, 1,
                                           ix->doc_group, q_group, id_base, (double*)out_scores, out_ids,
@@ -630,9 +648,9 @@ int ezr_bm25_scores(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_
     if (rc) return rc;
     if (n_queries == 0 || ix->n_docs == 0) return EZR_OK;
     return ix->score_type == EZR_F64
-               ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, 1, nullptr, 0, 1, out_scores, nullptr,
+               ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, 1, nullptr, 0, 1, out_scores, nullptr, nullptr,
                                      (cudaStream_t)stream)
-               : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, 1, nullptr, 0, 1, out_scores, nullptr,
+               : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, 1, nullptr, 0, 1, out_scores, nullptr, nullptr,
                                     (cudaStream_t)stream);
 }
 

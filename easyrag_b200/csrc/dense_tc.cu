@@ -51,6 +51,7 @@ struct TcParams {
     int32_t* part_id;
     int n_slices;
     int n_qblocks;        // TS variant: units = n_slices x n_qblocks, walked by persistent CTAs
+    int kps;              // TS variant: k-chunks (TMA boxes) per pipeline stage: 1, 2 or 4
 };
 
 struct TcBarriers {
@@ -249,7 +250,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_b = smem;
-    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_b + (size_t)p.n_stages * TC_B_STAGE_BYTES);
+    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_b + (size_t)p.n_stages * p.kps * TC_B_STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -286,11 +287,13 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
                 for (int t = 0; t < n_tiles; ++t) {
                     const int row0 = (int)(row_begin + (int64_t)t * TC_N);
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int kc = 0; kc < p.kchunks; kc += p.kps) {
                         ptx::mbar_wait(&bars->b_empty[stage], phase ^ 1);
-                        ptx::mbar_expect_tx(&bars->b_full[stage], TC_B_STAGE_BYTES);
-                        ptx::tma_load_2d(smem_b + (size_t)stage * TC_B_STAGE_BYTES, &map_c, &bars->b_full[stage],
-                                         kc * TC_KC, row0);
+                        ptx::mbar_expect_tx(&bars->b_full[stage], (uint32_t)(p.kps * TC_B_STAGE_BYTES));
+                        unsigned char* dst = smem_b + (size_t)stage * (size_t)(p.kps * TC_B_STAGE_BYTES);
+                        for (int j = 0; j < p.kps; ++j)
+                            ptx::tma_load_2d(dst + (size_t)j * TC_B_STAGE_BYTES, &map_c, &bars->b_full[stage],
+                                             (kc + j) * TC_KC, row0);
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -319,18 +322,21 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(TS_ACC_COL0 + as * TC_N);
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                for (int kc = 0; kc < p.kchunks; kc += p.kps) {
                     ptx::mbar_wait(&bars->b_full[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t a_tmem = tmem_base + (uint32_t)(kc * (TC_KC / 2));
-                    const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (TC_B_STAGE_BYTES >> 4));
+                    const uint64_t b_desc = b_desc0 + (uint64_t)(stage * p.kps * (TC_B_STAGE_BYTES >> 4));
                     if (ptx::elect_one()) {
+                        for (int j = 0; j < p.kps; ++j) {
 #pragma unroll
-                        for (int k4 = 0; k4 < TC_KC / 16; ++k4)
-                            ptx::umma_f16_ts(d_tmem, a_tmem + k4 * 8, b_desc + (uint64_t)(k4 * 2), idesc,
-                                             (uint32_t)((kc | k4) != 0));
+                            for (int k4 = 0; k4 < TC_KC / 16; ++k4)
+                                ptx::umma_f16_ts(d_tmem, a_tmem + j * (TC_KC / 2) + k4 * 8,
+                                                 b_desc + (uint64_t)(j * (TC_B_STAGE_BYTES >> 4) + k4 * 2), idesc,
+                                                 (uint32_t)((kc | j | k4) != 0));
+                        }
                         ptx::umma_commit(&bars->b_empty[stage]);
-                        if (kc == p.kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
+                        if (kc + p.kps >= p.kchunks) ptx::umma_commit(&bars->acc_full[as]);
                     }
                     __syncwarp();
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -566,14 +572,16 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     p.q_group = q_group;
     const size_t a_bytes = variant == 1 ? 0 : (size_t)p.kchunks * TC_A_CHUNK_BYTES;
     const size_t fixed = 1024 /*alignment slack*/ + sizeof(TcBarriers) + 64;
-    int stages = (int)((TC_SMEM_LIMIT - fixed - a_bytes) / TC_B_STAGE_BYTES);
+    p.kps = 1;
+    if (variant == 1) p.kps = (p.kchunks % 4 == 0) ? 4 : ((p.kchunks % 2 == 0) ? 2 : 1);
+    int stages = (int)((TC_SMEM_LIMIT - fixed - a_bytes) / ((size_t)p.kps * TC_B_STAGE_BYTES));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) {
         set_error("dense_topk(tcgen05): dim=%d leaves no room for a TMA ring", dim);
         return EZR_ERR_UNSUPPORTED;
     }
     p.n_stages = stages;
-    const size_t smem = fixed + a_bytes + (size_t)stages * TC_B_STAGE_BYTES;
+    const size_t smem = fixed + a_bytes + (size_t)stages * p.kps * TC_B_STAGE_BYTES;
     const size_t n_part = (size_t)n_queries * p.n_slices * k;
     p.part_s = reinterpret_cast<float*>(ws);
     p.part_id = reinterpret_cast<int32_t*>((char*)ws + align_up(n_part * 4, 256));

@@ -27,6 +27,8 @@ enum { EPI_NONE = 0, EPI_GELU = 1, EPI_SWIGLU = 2 };
 
 struct GemmParams {
     int M, N, K;
+    int kps;                         // k-chunks (64-wide TMA boxes) per pipeline stage: 1 or 2
+    int n_stages;                    // G_STAGES / kps
     int tiles_m, tiles_n;
     const __nv_bfloat16* bias;       // [N] or null
     const __nv_bfloat16* residual;   // [M, ldr] or null
@@ -43,7 +45,18 @@ struct GemmBarriers {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution) with the hardware exp/rcp units;
+// libdevice erff costs ~3x the instructions and made the FFN GEMM epilogue-bound.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = 1.0f - poly * t * __expf(-z * z);        // erf(|x|/sqrt2)
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -84,13 +97,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int tm = t % p.tiles_m, tn = t / p.tiles_m;
-                for (int kc = 0; kc < kchunks; ++kc) {
+                for (int kc = 0; kc < kchunks; kc += p.kps) {
                     ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&bars->full[stage], G_A_BYTES + G_B_BYTES);
-                    ptx::tma_load_2d(smem_a + (size_t)stage * G_A_BYTES, &map_a, &bars->full[stage], kc * GK, tm * GM);
-                    ptx::tma_load_2d_hint(smem_b + (size_t)stage * G_B_BYTES, &map_w, &bars->full[stage], kc * GK,
-                                          tn * GN, ptx::kEvictLast);
-                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+                    ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(p.kps * (G_A_BYTES + G_B_BYTES)));
+                    for (int j = 0; j < p.kps; ++j) {
+                        ptx::tma_load_2d(smem_a + (size_t)(stage * p.kps + j) * G_A_BYTES, &map_a, &bars->full[stage],
+                                         (kc + j) * GK, tm * GM);
+                        ptx::tma_load_2d_hint(smem_b + (size_t)(stage * p.kps + j) * G_B_BYTES, &map_w,
+                                              &bars->full[stage], (kc + j) * GK, tn * GN, ptx::kEvictLast);
+                    }
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -108,21 +124,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * GN);
-            for (int kc = 0; kc < kchunks; ++kc) {
+            for (int kc = 0; kc < kchunks; kc += p.kps) {
                 ptx::mbar_wait(&bars->full[stage], phase);
                 ptx::tc_fence_after();
-                const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (G_A_BYTES >> 4));
-                const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (G_B_BYTES >> 4));
+                const uint64_t a_desc = a_desc0 + (uint64_t)(stage * p.kps * (G_A_BYTES >> 4));
+                const uint64_t b_desc = b_desc0 + (uint64_t)(stage * p.kps * (G_B_BYTES >> 4));
                 if (ptx::elect_one()) {
+                    for (int j = 0; j < p.kps; ++j) {
 #pragma unroll
-                    for (int k4 = 0; k4 < GK / 16; ++k4)
-                        ptx::umma_f16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc,
-                                         (uint32_t)((kc | k4) != 0));
+                        for (int k4 = 0; k4 < GK / 16; ++k4)
+                            ptx::umma_f16_ss(d_tmem, a_desc + (uint64_t)(j * (G_A_BYTES >> 4) + k4 * 2),
+                                             b_desc + (uint64_t)(j * (G_B_BYTES >> 4) + k4 * 2), idesc,
+                                             (uint32_t)((kc | j | k4) != 0));
+                    }
                     ptx::umma_commit(&bars->empty[stage]);
-                    if (kc == kchunks - 1) ptx::umma_commit(&bars->acc_full[as]);
+                    if (kc + p.kps >= kchunks) ptx::umma_commit(&bars->acc_full[as]);
                 }
                 __syncwarp();
-                if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -158,12 +177,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         v[j] = silu(g) * u;
                     }
                 } else {
-                    ptx::tmem_ld_wait();
                     const int gcol = tn * GN + c * 32;
+                    // bias for these 32 columns: four 16-byte loads (same address in every thread -> broadcast)
+                    uint4 bv[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u),
+                                   make_uint4(0u, 0u, 0u, 0u)};
+                    const bool bias_vec = p.bias && gcol + 32 <= p.N &&
+                                          ((reinterpret_cast<uintptr_t>(p.bias + gcol) & 15) == 0);
+                    if (bias_vec) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const uint4*>(p.bias + gcol) + j);
+                    }
+                    ptx::tmem_ld_wait();
+                    const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(bv);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float x = __uint_as_float(r[j]);
-                        if (p.bias) x += __bfloat162float(__ldg(p.bias + min(gcol + j, p.N - 1)));
+                        if (bias_vec) x += __bfloat162float(bh[j]);
+                        else if (p.bias) x += __bfloat162float(__ldg(p.bias + min(gcol + j, p.N - 1)));
                         if (EPI == EPI_GELU) x = gelu_erf(x);
                         v[j] = x;
                     }
@@ -178,9 +208,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (row_ok && ocol < n_out) {
                     if (p.residual) {
                         const __nv_bfloat16* rr = p.residual + (int64_t)row * p.ldr + ocol;
+                        if (ocol + 32 <= n_out && ((reinterpret_cast<uintptr_t>(rr) & 15) == 0)) {
+                            uint4 rv[4];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (ocol + j < n_out) v[j] += __bfloat162float(__ldg(rr + j));
+                            for (int j = 0; j < 4; ++j) rv[j] = *(reinterpret_cast<const uint4*>(rr) + j);
+                            const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(rv);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(rh[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (ocol + j < n_out) v[j] += __bfloat162float(rr[j]);
+                        }
                     }
                     __nv_bfloat16* op = p.out + (int64_t)row * p.ldo + ocol;
                     if (ocol + 32 <= n_out && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
@@ -225,6 +264,8 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     p.tiles_m = (M + GM - 1) / GM;
     p.tiles_n = (N + GN - 1) / GN;
     p.bias = bias; p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo;
+    p.kps = ((K / GK) % 2 == 0) ? 2 : 1;
+    p.n_stages = G_STAGES / p.kps;
     CUtensorMap map_a, map_w;
     int rc = encode_tmap_2d_bf16(&map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GK, GM);
     if (rc) return rc;

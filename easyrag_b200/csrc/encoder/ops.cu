@@ -117,6 +117,90 @@ __global__ void norm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, co
     }
 }
 
+// Warp-per-row variant for dim % 8 == 0 and dim <= 256 * MAXC: the row lives in registers (MAXC 16-byte chunks per
+// lane), statistics by warp shuffles only, 8 rows per 256-thread CTA.  Same rounding points as norm_kernel.
+template <int MODE, int MAXC>
+__global__ void __launch_bounds__(256)
+norm_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gamma,
+                 const __nv_bfloat16* __restrict__ beta, float eps, int dim, __nv_bfloat16* __restrict__ out,
+                 int64_t ldo, int n_rows) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int n_chunks = dim >> 3;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)r * ldx);
+    float v[MAXC][8];
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int ci = lane + c * 32;
+        if (ci < n_chunks) {
+            const uint4 u = __ldg(xr + ci);
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[c][j] = __bfloat162float(h[j]); s += v[c][j]; q += v[c][j] * v[c][j]; }
+        }
+    }
+    float mean = 0.f, rstd;
+    if (MODE == 0) {
+        rstd = rsqrtf(warp_sum(q) / dim + eps);
+    } else {
+        mean = warp_sum(s) / dim;
+        float q2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            if (lane + c * 32 < n_chunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; q2 += d * d; }
+            }
+        }
+        rstd = rsqrtf(warp_sum(q2) / dim + eps);
+    }
+    uint4* orow = reinterpret_cast<uint4*>(out + (int64_t)r * ldo);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int ci = lane + c * 32;
+        if (ci < n_chunks) {
+            const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gamma) + ci);
+            const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&g4);
+            uint4 b4 = make_uint4(0u, 0u, 0u, 0u);
+            if (MODE == 1) b4 = __ldg(reinterpret_cast<const uint4*>(beta) + ci);
+            const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(&b4);
+            uint4 o4;
+            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&o4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (MODE == 0) {
+                    const float y = __bfloat162float(__float2bfloat16(v[c][j] * rstd));      // .to(input_dtype)
+                    oh[j] = __float2bfloat16(__bfloat162float(gh[j]) * y);
+                } else {
+                    oh[j] = __float2bfloat16((v[c][j] - mean) * rstd * __bfloat162float(gh[j]) + __bfloat162float(bh[j]));
+                }
+            }
+            orow[ci] = o4;
+        }
+    }
+}
+
+template <int MODE>
+static bool launch_norm_warp(const void* x, int64_t ldx, const void* gamma, const void* beta, float eps, int n_rows,
+                             int dim, void* out, int64_t ldo, cudaStream_t st) {
+    const bool aligned = (dim % 8 == 0) && (ldx % 8 == 0) && (ldo % 8 == 0) &&
+                         (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                            reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0);
+    if (!aligned || dim > 4096) return false;
+    const int grid = (n_rows + 7) / 8;
+    if (dim <= 1024)
+        norm_warp_kernel<MODE, 4><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)gamma,
+                                                        (const __nv_bfloat16*)beta, eps, dim, (__nv_bfloat16*)out, ldo,
+                                                        n_rows);
+    else
+        norm_warp_kernel<MODE, 16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)gamma,
+                                                         (const __nv_bfloat16*)beta, eps, dim, (__nv_bfloat16*)out, ldo,
+                                                         n_rows);
+    return true;
+}
+
 // ---------------------------------------------------------------- RoPE (K4), in place on packed q|k|v rows
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const int32_t* __restrict__ positions,
                             const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
@@ -231,6 +315,10 @@ int ezr_rmsnorm(const void* x, int64_t ldx, const void* gamma, float eps, int32_
     if (n_rows == 0) return EZR_OK;
     EZR_CHECK_ARG(dim <= 8192, "rmsnorm: dim too large");
     ProfScope prof(EZR_PROF_ENC_OTHER, (cudaStream_t)stream);
+    if (launch_norm_warp<0>(x, ldx, gamma, nullptr, eps, n_rows, dim, out, ldo, (cudaStream_t)stream)) {
+        EZR_LAUNCH_CHECK();
+        return EZR_OK;
+    }
     norm_kernel<0><<<n_rows, norm_threads(dim), (dim + 40) * sizeof(float), (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)gamma, nullptr, eps, dim, (__nv_bfloat16*)out, ldo, n_rows);
     EZR_LAUNCH_CHECK();
@@ -242,6 +330,10 @@ int ezr_layernorm(const void* x, int64_t ldx, const void* gamma, const void* bet
     if (n_rows == 0) return EZR_OK;
     EZR_CHECK_ARG(dim <= 8192, "layernorm: dim too large");
     ProfScope prof(EZR_PROF_ENC_OTHER, (cudaStream_t)stream);
+    if (launch_norm_warp<1>(x, ldx, gamma, beta, eps, n_rows, dim, out, ldo, (cudaStream_t)stream)) {
+        EZR_LAUNCH_CHECK();
+        return EZR_OK;
+    }
     norm_kernel<1><<<n_rows, norm_threads(dim), (dim + 40) * sizeof(float), (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps, dim,
         (__nv_bfloat16*)out, ldo, n_rows);
