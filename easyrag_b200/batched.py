@@ -249,3 +249,28 @@ class CoarseRanker:
         d_out, s_out, f_out = self.routes(queries, q_ptr, q_terms, k_dense, k_out, q_group=q_group)
         rrf_fuse(s_out.ids, s_out.counts, d_out.ids, d_out.counts, k_out, K=K, canon=self.canon, out=f_out)
         return f_out, s_out, d_out
+
+
+def dual_sparse_fusion(chunk_index: Bm25Index, path_index: Bm25Index, q_ptr: torch.Tensor, q_terms: torch.Tensor,
+                       path_q_ptr: torch.Tensor, path_q_terms: torch.Tensor, k_chunk: int, k_path: int, k_out: int,
+                       canon: Optional[torch.Tensor] = None, q_group: Optional[torch.Tensor] = None,
+                       ws: Optional[Workspace] = None) -> TopK:
+    """The reference's maintained coarse ranker as one batched op (pipeline.py:357-365): chunk-text BM25
+    (k = f_topk_2) and knowledge-path BM25 (k = f_topk_3) over the same nodes, merged by ``HybridRetriever.fusion``
+    (text-dedup, stable sort by raw score).  The two indexes have their own vocabularies, hence two term lists."""
+    dev = chunk_index.device
+    a = bm25_topk(chunk_index, q_ptr, q_terms, k_chunk, q_group=q_group, ws=ws)
+    b = bm25_topk(path_index, path_q_ptr, path_q_terms, k_path, q_group=q_group, ws=ws)
+    width = max(k_chunk, k_path)
+
+    def pad(t: TopK, k: int):
+        if k == width:
+            return t.ids, t.scores.to(torch.float64)
+        ids = torch.full((t.ids.shape[0], width), -1, dtype=torch.int32, device=dev)
+        sc = torch.zeros(t.ids.shape[0], width, dtype=torch.float64, device=dev)
+        ids[:, :k] = t.ids
+        sc[:, :k] = t.scores
+        return ids, sc
+    ia, sa = pad(a, k_chunk)
+    ib, sb = pad(b, k_path)
+    return fusion_simple(ia, sa, a.counts, ib, sb, b.counts, k_out, canon=canon)

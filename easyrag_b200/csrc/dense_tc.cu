@@ -29,6 +29,7 @@ constexpr int TC_MAX_STAGES = 26;
 constexpr int TC_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TC_KMAX = 16;
 constexpr int TS_ACC = 2;          // TS variant: accumulator stages
+constexpr int TS_THREADS = 320;    // TS variant: TMA warp, MMA warp, 8 epilogue warps
 constexpr int TS_ACC_COL0 = 384;   // TS variant: first accumulator column (A occupies [0, 384))
 constexpr int TC_A_CHUNK_BYTES = TC_M * TC_KC * 2;   // 16384
 constexpr int TC_B_STAGE_BYTES = TC_N * TC_KC * 2;   // 8192
@@ -244,7 +245,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // the SAME corpus split, so every corpus tile is fetched from HBM once and served to the other CTAs from L2.
 // TMEM: A at columns [0, 384), two 64-column accumulator stages at [384, 512).
 template <bool FILTER, int KT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TS_THREADS, 1)
 dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                 const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -265,7 +266,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         for (int i = 0; i < TS_ACC; ++i) {
             ptx::mbar_init(&bars->acc_full[i], 1);
-            ptx::mbar_init(&bars->acc_empty[i], 4);
+            ptx::mbar_init(&bars->acc_empty[i], 8);
         }
         ptx::fence_barrier_init();
     }
@@ -344,8 +345,12 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
         }
     } else {
-        // ---------------- epilogue warps: stage the query block, then one query row per thread ----------------
+        // ---------------- epilogue: 8 warps, two per TMEM lane quadrant ----------------
+        // Thread (quad, lane) owns query row quad*32+lane; the two warps of a quadrant split every 64-row corpus tile
+        // into rows [0,32) and [32,64) and each keeps its own sorted list, so a query ends a unit with two lists
+        // (both go to the merge).  The first four warps also stage the query block into tensor memory.
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;          // 0: tile rows 0..31, 1: tile rows 32..63
         const int m = quad * 32 + lane;
         const int k = p.k;
         int it = 0;
@@ -361,7 +366,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             if (FILTER && active) want = p.q_group[qg];
             // All MMAs of the previous unit have retired (its last acc_full was waited on below), so the A
             // columns may be overwritten: 64 bf16 (= 32 packed 32-bit columns) per tcgen05.st.
-            {
+            if (half == 0) {
                 const uint4* src = reinterpret_cast<const uint4*>(p.queries + (int64_t)(active ? qg : 0) * p.ldq);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     uint32_t r[32];
@@ -389,60 +394,64 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const uint32_t aph = (uint32_t)(it / TS_ACC) & 1u;
                 ptx::mbar_wait(&bars->acc_full[as], aph);
                 ptx::tc_fence_after();
-                const int64_t row0 = row_begin + (int64_t)t * TC_N;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TS_ACC_COL0 + as * TC_N);
+                const int64_t doc0 = row_begin + (int64_t)t * TC_N + half * 32;
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                       (uint32_t)(TS_ACC_COL0 + as * TC_N + half * 32), r);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);   // scores are in registers: stage is free
+                // Fast path (straight-line, static register indices): the maximum of the 32 scores.  After the
+                // lists have warmed up most batches of 32 end here.
+                float mx = -INFINITY;
 #pragma unroll
-                for (int half = 0; half < TC_N / 32; ++half) {
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32(taddr + half * 32, r);
-                    ptx::tmem_ld_wait();
-                    if (half == TC_N / 32 - 1) {
-                        ptx::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                if (active && mx >= thr) {
+                    // Slow path: which of the 32 reach the threshold (bit mask, static indices), then ONE copy of the
+                    // insertion code over the set bits, in increasing document order (a fully unrolled version is
+                    // ~100 KB of SASS and thrashes the instruction cache).
+                    float tmp[32];
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        tmp[j] = v;
+                        mask |= (v >= thr ? 1u : 0u) << j;
                     }
-                    // Fast path (straight-line, static register indices): the maximum of the 32 scores.  After the
-                    // lists have warmed up almost every batch of 32 ends here.
-                    float mx = -INFINITY;
+                    const int64_t left = row_end - doc0;                      // rows of this batch inside the unit
+                    if (left < 32) mask &= (left <= 0) ? 0u : ((1u << (int)left) - 1u);
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float v = tmp[j] + 0.0f;                        // -0.0 -> +0.0
+                        const int64_t doc = doc0 + j;
+                        bool ok = v >= thr;                                   // thr may have risen inside this batch
+                        if (FILTER) {
+                            if (ok && want != -1) ok = (__ldg(p.doc_group + doc) == want);
+                        }
+                        if (ok) {
+                            // candidates arrive in increasing id order, so on equal score the newcomer (higher id)
+                            // ranks first under the canonical order: ">=" everywhere.
+                            float cv = v;
+                            int ci = (int)doc + p.id_base;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-                    if (active && mx >= thr) {
-                        // Slow path: ONE copy of the insertion code, walked with a runtime index over a local copy of
-                        // the scores (an unrolled version is ~100 KB of SASS and thrashes the instruction cache).
-                        float tmp[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) tmp[j] = __uint_as_float(r[j]);
-#pragma unroll 1
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = tmp[j] + 0.0f;                      // -0.0 -> +0.0
-                            const int64_t doc = row0 + half * 32 + j;
-                            bool ok = doc < row_end && v >= thr;
-                            if (FILTER) {
-                                if (ok && want != -1) ok = (__ldg(p.doc_group + doc) == want);
+                            for (int s = 0; s < KT; ++s) {
+                                const bool b = cv >= ts[s];
+                                const float fs = ts[s];
+                                const int is = ti[s];
+                                ts[s] = b ? cv : fs;
+                                ti[s] = b ? ci : is;
+                                cv = b ? fs : cv;
+                                ci = b ? is : ci;
                             }
-                            if (ok) {
-                                // candidates arrive in increasing id order, so on equal score the newcomer (higher
-                                // id) ranks first under the canonical order: ">=" everywhere.
-                                float cv = v;
-                                int ci = (int)doc + p.id_base;
-#pragma unroll
-                                for (int s = 0; s < KT; ++s) {
-                                    const bool b = cv >= ts[s];
-                                    const float fs = ts[s];
-                                    const int is = ti[s];
-                                    ts[s] = b ? cv : fs;
-                                    ti[s] = b ? ci : is;
-                                    cv = b ? fs : cv;
-                                    ci = b ? is : ci;
-                                }
-                                thr = ts[KT - 1];
-                            }
+                            thr = ts[KT - 1];
                         }
                     }
                 }
             }
             if (active) {
-                const int64_t o = ((int64_t)qg * p.n_slices + slice) * k;
+                const int64_t o = (((int64_t)qg * p.n_slices + slice) * 2 + half) * k;
 #pragma unroll
                 for (int s = 0; s < KT; ++s) {
                     if (s < k) {
@@ -541,7 +550,7 @@ bool dense_tc_supported(const __nv_bfloat16* corpus, int64_t n_rows, int dim, in
 size_t dense_tc_workspace(int64_t n_rows, int dim, int n_queries, int k) {
     if (dim % TC_KC != 0 || dim > TC_MAXD || k > TC_KMAX || n_rows < 1) return 0;
     const int slices = tc_slices(n_rows);
-    const size_t n = (size_t)n_queries * slices * k;
+    const size_t n = (size_t)n_queries * slices * k * 2;      // TS variant: two lists per (query, split)
     return align_up(n * 4, 256) * 2;
 }
 
@@ -582,7 +591,8 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     }
     p.n_stages = stages;
     const size_t smem = fixed + a_bytes + (size_t)stages * p.kps * TC_B_STAGE_BYTES;
-    const size_t n_part = (size_t)n_queries * p.n_slices * k;
+    const int lists = variant == 1 ? 2 : 1;
+    const size_t n_part = (size_t)n_queries * p.n_slices * k * lists;
     p.part_s = reinterpret_cast<float*>(ws);
     p.part_id = reinterpret_cast<int32_t*>((char*)ws + align_up(n_part * 4, 256));
 
@@ -614,10 +624,10 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     }
     {
         ProfScope prof(EZR_PROF_DENSE_TC, st);
-        kern<<<grid, TC_THREADS, smem, st>>>(map_q, map_c, p);
+        kern<<<grid, variant == 1 ? TS_THREADS : TC_THREADS, smem, st>>>(map_q, map_c, p);
     }
     EZR_LAUNCH_CHECK();
-    const int n_cand = p.n_slices * k;
+    const int n_cand = p.n_slices * k * lists;
     return ezr_merge_topk(p.part_s, p.part_id, EZR_F32, n_queries, n_cand, n_cand, k, out_scores, out_ids, out_counts,
                           nullptr, 0, st);
 }

@@ -7,21 +7,21 @@
 // cuBLAS calls behind the reference's projections: Qwen2 q/k/v/o and SwiGLU MLP (modeling_qwen.py:261-263,
 // 319,186) and the BERT-shaped encoder's dense layers behind SentenceTransformer.encode (hf_embeddings.py:118-123).
 //
-// Persistent, warp-specialised: warp 0 = TMA producer (6-stage ring of 128x64 A and 128x64 W tiles),
-// warp 1 = single-thread tcgen05.mma issuer (128x128x16, fp32 accumulate into one of two 128-column TMEM
-// stages), warps 2-5 = epilogue (tcgen05.ld, one output row per thread, bias / GELU / SwiGLU / residual in
+// Persistent, warp-specialised: warp 0 = TMA producer (4-stage ring of 128x64 A and 256x64 W tiles),
+// warp 1 = tcgen05.mma issuer (128x256x16, fp32 accumulate into one of two 256-column TMEM stages; the 128x256
+// tile halves L2->SM operand traffic per flop versus 128x128, which measured L2-bound), warps 2-5 = epilogue (tcgen05.ld, one output row per thread, bias / GELU / SwiGLU / residual in
 // fp32, bf16 pack, 16-byte global stores) overlapping the next tile's MMAs.
 #include "../ezr_common.cuh"
 #include "../ptx.cuh"
 
 namespace ezr {
 
-constexpr int GM = 128, GN = 128, GK = 64;
-constexpr int G_STAGES = 6;
+constexpr int GM = 128, GN = 256, GK = 64;
+constexpr int G_STAGES = 4;
 constexpr int G_ACC = 2;
 constexpr int G_THREADS = 192;
 constexpr int G_A_BYTES = GM * GK * 2;   // 16 KB
-constexpr int G_B_BYTES = GN * GK * 2;   // 16 KB
+constexpr int G_B_BYTES = GN * GK * 2;   // 32 KB
 
 enum { EPI_NONE = 0, EPI_GELU = 1, EPI_SWIGLU = 2 };
 
@@ -45,18 +45,9 @@ struct GemmBarriers {
     uint32_t tmem_base;
 };
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution) with the hardware exp/rcp units;
-// libdevice erff costs ~3x the instructions and made the FFN GEMM epilogue-bound.
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = 1.0f - poly * t * __expf(-z * z);        // erf(|x|/sqrt2)
-    return 0.5f * x * (1.0f + copysignf(e, x));
-}
+// exact-erf GELU (HF "gelu").  libdevice erff is pure FMA polynomials; an exp/rcp based approximation was tried and
+// was 2x slower here: it is bound by the 16-per-cycle MUFU unit at 128x256 values per tile.
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -156,7 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int row = tm * GM + quad * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * GN);
-            constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? 2 : 4;     // 32 output columns per chunk
+            constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? GN / 64 : GN / 32;   // 32 output columns per chunk
 #pragma unroll
             for (int c = 0; c < n_out_chunks; ++c) {
                 uint32_t r[32];
@@ -164,15 +155,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 ptx::tmem_ld_32x32(taddr + c * 32, r);
                 if (EPI == EPI_SWIGLU) {
                     uint32_t r2[32];
-                    ptx::tmem_ld_32x32(taddr + 64 + c * 32, r2);
+                    ptx::tmem_ld_32x32(taddr + GN / 2 + c * 32, r2);
                     ptx::tmem_ld_wait();
-                    const int gcol = tn * GN + c * 32;           // gate columns; up columns are gcol + 64
+                    const int gcol = tn * GN + c * 32;           // gate columns; up columns are gcol + GN/2
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float g = __uint_as_float(r[j]), u = __uint_as_float(r2[j]);
                         if (p.bias) {
                             g += __bfloat162float(__ldg(p.bias + min(gcol + j, p.N - 1)));
-                            u += __bfloat162float(__ldg(p.bias + min(gcol + 64 + j, p.N - 1)));
+                            u += __bfloat162float(__ldg(p.bias + min(gcol + GN / 2 + j, p.N - 1)));
                         }
                         v[j] = silu(g) * u;
                     }
@@ -257,14 +248,14 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     EZR_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "gemm: row strides must be multiples of 8 and >= K");
     EZR_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0, "gemm: A/W must be 16-byte aligned");
     EZR_CHECK_ARG(epi >= EPI_NONE && epi <= EPI_SWIGLU, "gemm: bad epilogue %d", epi);
-    EZR_CHECK_ARG(epi != EPI_SWIGLU || N % GN == 0, "gemm: SwiGLU epilogue needs N %% 128 == 0 (interleaved gate/up)");
+    EZR_CHECK_ARG(epi != EPI_SWIGLU || N % GN == 0, "gemm: SwiGLU epilogue needs N %% 256 == 0 (gate/up interleaved in blocks of 128 rows)");
     if (M == 0) return EZR_OK;
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
     p.tiles_m = (M + GM - 1) / GM;
     p.tiles_n = (N + GN - 1) / GN;
     p.bias = bias; p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo;
-    p.kps = ((K / GK) % 2 == 0) ? 2 : 1;
+    p.kps = 1;            // 2 chunks per stage was measured slower (coarser producer/consumer hand-off)
     p.n_stages = G_STAGES / p.kps;
     CUtensorMap map_a, map_w;
     int rc = encode_tmap_2d_bf16(&map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GK, GM);

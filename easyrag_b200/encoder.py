@@ -141,12 +141,13 @@ def _bf16(t: torch.Tensor, device) -> torch.Tensor:
 
 
 def _interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
-    """[ffn, d] x2 -> [2*ffn, d] in blocks of 64 gate rows followed by the matching 64 up rows (SwiGLU epilogue)."""
+    """[ffn, d] x2 -> [2*ffn, d] in blocks of 128 gate rows followed by the matching 128 up rows (SwiGLU epilogue:
+    one 256-column GEMM tile holds both halves of the same 128 outputs)."""
     ffn, d = gate.shape
-    if ffn % 64:
-        raise ValueError("intermediate_size must be a multiple of 64")
-    g = gate.view(ffn // 64, 64, d)
-    u = up.view(ffn // 64, 64, d)
+    if ffn % 128:
+        raise ValueError("intermediate_size must be a multiple of 128")
+    g = gate.view(ffn // 128, 128, d)
+    u = up.view(ffn // 128, 128, d)
     return torch.stack([g, u], dim=1).reshape(2 * ffn, d).contiguous()
 
 

@@ -13,7 +13,9 @@
 """
 from __future__ import annotations
 
+import json
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -90,6 +92,33 @@ class Bm25Stats:
         return Bm25Stats(n_docs=n, vocab=vocab, bm25_type=bm25_type, avgdl=avgdl, doc_len=lens.to(torch.int32),
                          df=df, idf=idf, indptr=indptr, post_doc=post_doc, post_tf=post_tf,
                          average_idf=average_idf)
+
+
+INDEX_FORMAT_VERSION = 1
+
+
+def _save_arrays(path: str, meta: dict, arrays: dict) -> None:
+    os.makedirs(path, exist_ok=True)
+    for name, t in arrays.items():
+        np.save(os.path.join(path, name + ".npy"), t.detach().cpu().view(torch.int16).numpy()
+                if t.dtype == torch.bfloat16 else t.detach().cpu().numpy())
+    meta = dict(meta, format_version=INDEX_FORMAT_VERSION,
+                bf16=[n for n, t in arrays.items() if t.dtype == torch.bfloat16])
+    with open(os.path.join(path, "meta.json"), "w") as f:
+        json.dump(meta, f)
+
+
+def _load_arrays(path: str):
+    with open(os.path.join(path, "meta.json")) as f:
+        meta = json.load(f)
+    if meta.get("format_version") != INDEX_FORMAT_VERSION:
+        raise ValueError(f"{path}: index format {meta.get('format_version')} != {INDEX_FORMAT_VERSION}")
+
+    def get(name):
+        a = np.load(os.path.join(path, name + ".npy"), mmap_mode="r")     # start-up is an mmap, not a re-tokenise
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.view(torch.bfloat16) if name in meta.get("bf16", []) else t
+    return meta, get
 
 
 class Bm25Index:
@@ -175,6 +204,39 @@ class Bm25Index:
         return (self.post_doc.numel() * 4 + self.post_w.numel() * self.post_w.element_size()
                 + self.range_off.numel() * 4 + self.indptr.numel() * 8)
 
+    # ---- on-disk format (the reference rebuilds the BM25 index in RAM on every start,
+    # retrievers.py:98-118).  A directory of .npy arrays + meta.json; loading needs no tokenisation and no log().
+    def save(self, path: str) -> None:
+        arrays = dict(indptr=self.indptr, post_doc=self.post_doc, post_w=self.post_w, range_off=self.range_off)
+        if self.doc_group is not None:
+            arrays["doc_group"] = self.doc_group
+        _save_arrays(path, dict(kind="bm25", n_docs=self.n_docs, vocab=self.vocab, score_type=self.score_type,
+                                doc_lo=self.doc_lo, doc_hi=self.doc_hi, n_ranges=self.n_ranges,
+                                range_size=_lib.BM25_RANGE), arrays)
+
+    @classmethod
+    def load(cls, path: str, device=None) -> "Bm25Index":
+        _lib.require_cuda()
+        meta, get = _load_arrays(path)
+        if meta["kind"] != "bm25" or meta["range_size"] != _lib.BM25_RANGE:
+            raise ValueError(f"{path}: not a BM25 index of this build")
+        self = cls.__new__(cls)
+        device = torch.device(device if device is not None else "cuda")
+        self.stats = None
+        self.device = device
+        self.n_docs, self.vocab, self.score_type = meta["n_docs"], meta["vocab"], meta["score_type"]
+        self.doc_lo, self.doc_hi, self.n_ranges = meta["doc_lo"], meta["doc_hi"], meta["n_ranges"]
+        self.score_dtype = torch.float64 if self.score_type == _lib.F64 else torch.float32
+        self.indptr = get("indptr").to(device)
+        self.post_doc = get("post_doc").to(device)
+        self.post_w = get("post_w").to(device)
+        self.range_off = get("range_off").to(device)
+        self.n_postings = int(self.post_doc.numel())
+        self.doc_group = get("doc_group").to(device) if os.path.exists(os.path.join(path, "doc_group.npy")) else None
+        self._struct = None
+        self.refresh_struct()
+        return self
+
 
 class DenseIndex:
     """Row-major bf16 matrix of L2-normalised chunk embeddings (rows ``[row_lo, row_hi)`` of the corpus)."""
@@ -191,3 +253,17 @@ class DenseIndex:
         self.row_lo = row_lo
         self.device = device
         self.doc_group = None if doc_group is None else doc_group.to(device=device, dtype=torch.int32).contiguous()
+
+    def save(self, path: str) -> None:
+        arrays = dict(vectors=self.vectors)
+        if self.doc_group is not None:
+            arrays["doc_group"] = self.doc_group
+        _save_arrays(path, dict(kind="dense", n_rows=self.n_rows, dim=self.dim, row_lo=self.row_lo), arrays)
+
+    @classmethod
+    def load(cls, path: str, device=None) -> "DenseIndex":
+        meta, get = _load_arrays(path)
+        if meta["kind"] != "dense":
+            raise ValueError(f"{path}: not a dense index")
+        dg = get("doc_group") if os.path.exists(os.path.join(path, "doc_group.npy")) else None
+        return cls(get("vectors"), device=device, row_lo=meta["row_lo"], doc_group=dg)

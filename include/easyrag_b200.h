@@ -158,7 +158,7 @@ int ezr_fusion_simple(const int32_t* ids_a, const double* scores_a, const int32_
  * these per layer on one stream. */
 
 /* out[M,N'] = epi(A[M,K] . W[N,K]^T + bias) (+ residual); tcgen05/TMEM/TMA.  epilogue: 0 none, 1 GELU(erf),
- * 2 SwiGLU (W rows interleaved per 128: 64 gate rows then the matching 64 up rows; N' = N/2).  K % 64 == 0. */
+ * 2 SwiGLU (W rows interleaved per 256: 128 gate rows then the matching 128 up rows; N' = N/2).  K % 64 == 0. */
 int ezr_gemm_bf16(const void* a, int32_t m, int32_t k, int64_t lda, const void* w, int32_t n, int64_t ldw,
                   const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo, int32_t epilogue,
                   void* stream);

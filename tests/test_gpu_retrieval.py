@@ -382,3 +382,45 @@ def test_hybrid_dense_bm25_rrf_matches_oracle(c1):
         ref_i, ref_s = ort.rrf_ids([s_ref, d_ref[i]], canon.numpy(), K=60, topk=k)
         assert np.array_equal(f_ids[i, :f_cnt[i]], ref_i)
         assert f_sc[i, :f_cnt[i]].tobytes() == ref_s.tobytes()
+
+
+# ----------------------------------------------------- widening ----
+def test_index_save_load_roundtrip(c1, tmp_path):
+    ix = c1["index"]
+    ix.save(str(tmp_path / "bm25"))
+    ix2 = Bm25Index.load(str(tmp_path / "bm25"), device=DEV)
+    q = c1["queries"]
+    a = batched.bm25_topk(ix, q.term_ptr, q.terms, 10)
+    b = batched.bm25_topk(ix2, q.term_ptr, q.terms, 10)
+    assert torch.equal(a.ids, b.ids) and torch.equal(a.scores, b.scores)
+    c, qv = _dense_case(3000, 128, 9, 3, integer=True)
+    d = DenseIndex(c, device=DEV, row_lo=5)
+    d.save(str(tmp_path / "dense"))
+    d2 = DenseIndex.load(str(tmp_path / "dense"), device=DEV)
+    x, y = batched.dense_topk(d, qv.to(DEV), 10), batched.dense_topk(d2, qv.to(DEV), 10)
+    assert torch.equal(x.ids, y.ids) and torch.equal(x.scores, y.scores)
+
+
+def test_dual_sparse_route_fusion(c1):
+    # pipeline.py:357-365: chunk BM25 (k=192) + path BM25 (k=6) -> HybridRetriever.fusion(topk=256)
+    corpus = c1["corpus"]
+    n = corpus.n_docs
+    # a second, much shorter "knowledge path" text per node: its first 4 tokens
+    docs = corpus.doc_lists()
+    p_tokens = torch.from_numpy(np.concatenate([d[:4] for d in docs])).to(torch.int32)
+    p_ptr = torch.tensor(np.cumsum([0] + [min(4, len(d)) for d in docs]), dtype=torch.int64)
+    p_or = obm.OkapiCSR([d[:4] for d in docs], corpus.vocab)
+    p_ix = Bm25Index(Bm25Stats.from_tokens(p_tokens, p_ptr, corpus.vocab), device=DEV)
+    canon = synth.make_duplicates(n, 0.02, 3)
+    q = c1["queries"]
+    nq = 20
+    qp, qt = q.term_ptr[:nq + 1], q.terms
+    res = batched.dual_sparse_fusion(c1["index"], p_ix, qp, qt, qp, qt, 192, 6, 256, canon=canon)
+    ids, sc, cnt = res.ids.cpu().numpy(), res.scores.cpu().numpy(), res.counts.cpu().numpy()
+    for i, terms in enumerate(q.term_lists()[:nq]):
+        a_i, a_s = ort.bm25_topk_ids(c1["rows"][i], 192)
+        b_i, b_s = ort.bm25_topk_ids(p_or.get_scores([int(t) for t in terms]), 6)
+        ref_i, ref_s = ort.fusion_ids([a_i, b_i], [a_s, b_s], canon.numpy(), topk=256)
+        assert cnt[i] == ref_i.size
+        assert np.array_equal(ids[i, :cnt[i]], ref_i)
+        assert sc[i, :cnt[i]].tobytes() == ref_s.tobytes()
