@@ -148,7 +148,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * GN);
             constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? GN / 64 : GN / 32;   // 32 output columns per chunk
-#pragma unroll
+            // NOT unrolled: eight inlined copies of the 32-wide body are >130 KB of SASS (230 KB with GELU), which
+            // streams through the instruction cache on every tile and made the epilogue the bottleneck.
+#pragma unroll 1
             for (int c = 0; c < n_out_chunks; ++c) {
                 uint32_t r[32];
                 float v[32];
