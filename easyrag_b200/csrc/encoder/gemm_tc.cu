@@ -19,7 +19,7 @@ namespace ezr {
 constexpr int GM = 128, GN = 256, GK = 64;
 constexpr int G_STAGES = 4;
 constexpr int G_ACC = 2;
-constexpr int G_THREADS = 192;
+constexpr int G_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int G_A_BYTES = GM * GK * 2;   // 16 KB
 constexpr int G_B_BYTES = GN * GK * 2;   // 32 KB
 
@@ -65,6 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     unsigned char* smem_b = smem + (size_t)G_STAGES * G_A_BYTES;
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_b + (size_t)G_STAGES * G_B_BYTES);
 
+    __shared__ float s_bias[8][GN];          // per epilogue warp: bias of its column half (x2 rows for SwiGLU)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.tiles_m * p.tiles_n;
     const int kchunks = p.K / GK;
@@ -73,7 +74,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_w);
         for (int i = 0; i < G_STAGES; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); }
-        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], 4); }
+        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], 8); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc<G_ACC * GN>(&bars->tmem_base);
@@ -136,79 +137,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
+        // ---------------- epilogue: 8 warps, two per TMEM lane quadrant, each owning half of the tile's columns.
+        // Global-memory latency is kept off the critical path: the bias slice is staged in shared memory BEFORE the
+        // accumulator wait, and the residual of chunk c+1 is in flight while chunk c is processed.
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? GN / 64 : GN / 32;   // 32 output columns per chunk
+        constexpr int cpw = n_out_chunks / 2;                                   // chunks per warp
+        float* sb = s_bias[warp - 2];                                           // this warp's bias slice
+        const int n_out = (EPI == EPI_SWIGLU) ? p.N / 2 : p.N;
         int it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int tm = t % p.tiles_m, tn = t / p.tiles_m;
             const int as = it % G_ACC;
             const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
-            ptx::mbar_wait(&bars->acc_full[as], aph);
-            ptx::tc_fence_after();
             const int row = tm * GM + quad * 32 + lane;
             const bool row_ok = row < p.M;
+            const int c0 = half * cpw;
+            // bias: columns [gc0, gc0 + cpw*32) (and the matching "up" columns for SwiGLU) -> sb[0 .. cpw*32 (*2))
+            if (p.bias) {
+                __syncwarp();
+                for (int i = lane; i < cpw * 32; i += 32) {
+                    const int col = tn * GN + c0 * 32 + i;
+                    sb[i] = col < p.N ? __bfloat162float(__ldg(p.bias + col)) : 0.f;
+                    if (EPI == EPI_SWIGLU) {
+                        const int col2 = col + GN / 2;
+                        sb[cpw * 32 + i] = col2 < p.N ? __bfloat162float(__ldg(p.bias + col2)) : 0.f;
+                    }
+                }
+                __syncwarp();
+            }
+            // residual of the first chunk
+            uint4 rv[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u),
+                           make_uint4(0u, 0u, 0u, 0u)};
+            const int ocol_base = (EPI == EPI_SWIGLU) ? tn * (GN / 2) : tn * GN;
+            const bool res_vec = p.residual && row_ok && (p.ldr % 8 == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+            auto load_res = [&](int c, uint4 (&dst)[4]) {
+                const int oc = ocol_base + c * 32;
+                if (res_vec && oc + 32 <= n_out) {
+                    const uint4* rr = reinterpret_cast<const uint4*>(p.residual + (int64_t)row * p.ldr + oc);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = rr[j];
+                }
+            };
+            load_res(c0, rv);
+
+            ptx::mbar_wait(&bars->acc_full[as], aph);
+            ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * GN);
-            constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? GN / 64 : GN / 32;   // 32 output columns per chunk
-            // NOT unrolled: eight inlined copies of the 32-wide body are >130 KB of SASS (230 KB with GELU), which
-            // streams through the instruction cache on every tile and made the epilogue the bottleneck.
+            // NOT unrolled: inlined copies of the 32-wide body are >130 KB of SASS (230 KB with GELU) and stream
+            // through the instruction cache on every tile.
 #pragma unroll 1
-            for (int c = 0; c < n_out_chunks; ++c) {
+            for (int ci = 0; ci < cpw; ++ci) {
+                const int c = c0 + ci;
                 uint32_t r[32];
                 float v[32];
+                uint4 rn[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u),
+                               make_uint4(0u, 0u, 0u, 0u)};
                 ptx::tmem_ld_32x32(taddr + c * 32, r);
+                if (ci + 1 < cpw) load_res(c + 1, rn);                 // next chunk's residual: in flight from here
                 if (EPI == EPI_SWIGLU) {
                     uint32_t r2[32];
                     ptx::tmem_ld_32x32(taddr + GN / 2 + c * 32, r2);
                     ptx::tmem_ld_wait();
-                    const int gcol = tn * GN + c * 32;           // gate columns; up columns are gcol + GN/2
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float g = __uint_as_float(r[j]), u = __uint_as_float(r2[j]);
-                        if (p.bias) {
-                            g += __bfloat162float(__ldg(p.bias + min(gcol + j, p.N - 1)));
-                            u += __bfloat162float(__ldg(p.bias + min(gcol + GN / 2 + j, p.N - 1)));
-                        }
+                        if (p.bias) { g += sb[ci * 32 + j]; u += sb[cpw * 32 + ci * 32 + j]; }
                         v[j] = silu(g) * u;
                     }
                 } else {
-                    const int gcol = tn * GN + c * 32;
-                    // bias for these 32 columns: four 16-byte loads (same address in every thread -> broadcast)
-                    uint4 bv[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u),
-                                   make_uint4(0u, 0u, 0u, 0u)};
-                    const bool bias_vec = p.bias && gcol + 32 <= p.N &&
-                                          ((reinterpret_cast<uintptr_t>(p.bias + gcol) & 15) == 0);
-                    if (bias_vec) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const uint4*>(p.bias + gcol) + j);
-                    }
                     ptx::tmem_ld_wait();
-                    const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(bv);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float x = __uint_as_float(r[j]);
-                        if (bias_vec) x += __bfloat162float(bh[j]);
-                        else if (p.bias) x += __bfloat162float(__ldg(p.bias + min(gcol + j, p.N - 1)));
+                        if (p.bias) x += sb[ci * 32 + j];
                         if (EPI == EPI_GELU) x = gelu_erf(x);
                         v[j] = x;
                     }
                 }
-                if (c == n_out_chunks - 1) {
+                if (ci == cpw - 1) {
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
                 }
-                const int ocol = (EPI == EPI_SWIGLU) ? (tn * (GN / 2) + c * 32) : (tn * GN + c * 32);
-                const int n_out = (EPI == EPI_SWIGLU) ? p.N / 2 : p.N;
+                const int ocol = ocol_base + c * 32;
                 if (row_ok && ocol < n_out) {
                     if (p.residual) {
-                        const __nv_bfloat16* rr = p.residual + (int64_t)row * p.ldr + ocol;
-                        if (ocol + 32 <= n_out && ((reinterpret_cast<uintptr_t>(rr) & 15) == 0)) {
-                            uint4 rv[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) rv[j] = *(reinterpret_cast<const uint4*>(rr) + j);
+                        if (res_vec && ocol + 32 <= n_out) {
                             const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(rv);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(rh[j]);
                         } else {
+                            const __nv_bfloat16* rr = p.residual + (int64_t)row * p.ldr + ocol;
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (ocol + j < n_out) v[j] += __bfloat162float(rr[j]);
@@ -231,6 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             if (ocol + j < n_out) op[j] = __float2bfloat16(v[j]);
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rv[j] = rn[j];
             }
         }
     }
