@@ -32,6 +32,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -60,9 +63,9 @@ __global__ void __launch_bounds__(128)
 attn_bidir_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const int32_t* __restrict__ cu, int n_heads,
                   int n_kv_heads, float scale_log2, __nv_bfloat16* __restrict__ out, int64_t ldo) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t kTile = 64 * HD * 2;
     const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
-    const uint32_t sK = sQ + 64 * HD * 2;
-    const uint32_t sV = sK + 64 * HD * 2;
+    const uint32_t sK0 = sQ + kTile;            // K/V tiles are double buffered: [K0 V0 K1 V1]
     const int qb = blockIdx.x, b = blockIdx.y, h = blockIdx.z;
     const int lo = cu[b];
     const int len = cu[b + 1] - lo;
@@ -75,6 +78,8 @@ attn_bidir_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const int32
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     load_tile<HD>(sQ, q_ptr, ld, q0, len);
+    load_tile<HD>(sK0, k_ptr, ld, 0, len);
+    load_tile<HD>(sK0 + kTile, v_ptr, ld, 0, len);
     cp_async_wait_all();
     __syncthreads();
     uint32_t qf[HD / 16][4];
@@ -91,11 +96,14 @@ attn_bidir_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const int32
     const int n_kt = (len + 63) / 64;
 
     for (int kt = 0; kt < n_kt; ++kt) {
-        __syncthreads();                                     // previous tile fully consumed
-        load_tile<HD>(sK, k_ptr, ld, kt * 64, len);
-        load_tile<HD>(sV, v_ptr, ld, kt * 64, len);
-        cp_async_wait_all();
-        __syncthreads();
+        const uint32_t sK = sK0 + (uint32_t)(kt & 1) * 2 * kTile;
+        const uint32_t sV = sK + kTile;
+        if (kt + 1 < n_kt) {                                 // prefetch the next K/V tile into the other buffer
+            const uint32_t nK = sK0 + (uint32_t)((kt + 1) & 1) * 2 * kTile;
+            load_tile<HD>(nK, k_ptr, ld, (kt + 1) * 64, len);
+            load_tile<HD>(nK + kTile, v_ptr, ld, (kt + 1) * 64, len);
+            cp_async_commit();
+        }
 
         float s[8][4];
 #pragma unroll
@@ -165,6 +173,10 @@ attn_bidir_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const int32
                 mma_bf16(o[2 * jn + 1], pa, bv[2], bv[3]);
             }
         }
+        if (kt + 1 < n_kt) {
+            cp_async_wait<0>();                              // next tile has landed (it had the whole tile to do so)
+            __syncthreads();                                 // and everyone is done reading the current one
+        }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -198,11 +210,11 @@ extern "C" int ezr_attn_bidir(const void* qkv, int64_t ld, const int32_t* cu_seq
     cudaStream_t st = (cudaStream_t)stream;
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
     dim3 grid((max_len + 63) / 64, n_seq, n_heads);
-    const size_t smem = (size_t)3 * 64 * head_dim * 2;
+    const size_t smem = (size_t)5 * 64 * head_dim * 2;      // Q + double-buffered K/V
     ProfScope prof(EZR_PROF_ENC_ATTN, st);
     if (head_dim == 64) {
         attn_bidir_kernel<64><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld, cu_seqlens, n_heads, n_kv_heads,
-                                                       scale_log2, (__nv_bfloat16*)out, ldo);
+                                                       scale_log2, (__nv_bfloat16*)out, ldo);   // 40 KB: no opt-in needed
     } else {
         static bool attr_done = false;
         if (!attr_done) {
