@@ -162,7 +162,14 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
         return EZR_ERR_UNSUPPORTED;
     }
     if (tc_ok && g_force_kernel != 1) {
-        const int variant = g_force_kernel == 3 ? 1 : (g_force_kernel == 2 ? 0 : g_default_variant);
+        int variant = g_force_kernel == 3 ? 1 : (g_force_kernel == 2 ? 0 : g_default_variant);
+        if (dim > 768) {
+            if (g_force_kernel == 2) {
+                set_error("dense_topk: the SS tcgen05 kernel supports dim <= 768 (got %d)", dim);
+                return EZR_ERR_UNSUPPORTED;
+            }
+            variant = 1;
+        }
         g_last_kernel = variant == 1 ? "tcgen05-ts" : "tcgen05";
         return dense_tc_topk(c, n_rows, dim, ld_corpus, q, n_queries, ld_queries, k, doc_group, q_group, id_base,
                              out_scores, out_ids, out_counts, workspace, workspace_bytes, st, variant);

@@ -23,7 +23,9 @@ namespace ezr {
 constexpr int TC_M = 128;       // queries per CTA = UMMA M
 constexpr int TC_N = 64;        // corpus rows per tile = UMMA N
 constexpr int TC_KC = 64;       // bf16 per k-chunk = one 128-byte swizzle row
-constexpr int TC_MAXD = 768;
+constexpr int TC_MAXD = 768;       // SS variant: whole query block in shared memory
+constexpr int TS_MAXD = 1024;      // TS variant: 768 columns in TMEM + up to 256 in shared memory
+constexpr int TS_TMEM_KC = 12;     // k-chunks of the query block held in tensor memory (12 x 32 = 384 columns)
 constexpr int TC_ACC = 4;       // TMEM accumulator stages (TC_N fp32 columns each)
 constexpr int TC_MAX_STAGES = 26;
 constexpr int TC_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
@@ -57,6 +59,8 @@ struct TcParams {
 
 struct TcBarriers {
     uint64_t a_full;
+    uint64_t ahi_full;     // TS variant, dim > 768: the shared-memory tail of the query block has landed (TMA)
+    uint64_t ahi_empty;    // ... and every MMA of the previous unit that read it has retired (tcgen05.commit)
     uint64_t b_full[TC_MAX_STAGES];
     uint64_t b_empty[TC_MAX_STAGES];
     uint64_t acc_full[TC_ACC];
@@ -250,7 +254,10 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char* smem_b = smem;
+    const int kc_tm = min(p.kchunks, TS_TMEM_KC);          // k-chunks of A in tensor memory
+    const int kc_sm = p.kchunks - kc_tm;                   // k-chunks of A in shared memory (dim > 768)
+    unsigned char* smem_ahi = smem;
+    unsigned char* smem_b = smem + (size_t)kc_sm * TC_A_CHUNK_BYTES;
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_b + (size_t)p.n_stages * p.kps * TC_B_STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5;
@@ -259,7 +266,10 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_c);
+        ptx::prefetch_tensormap(&map_q);
         ptx::mbar_init(&bars->a_full, 4);
+        ptx::mbar_init(&bars->ahi_full, 1);
+        ptx::mbar_init(&bars->ahi_empty, 1);
         for (int i = 0; i < p.n_stages; ++i) {
             ptx::mbar_init(&bars->b_full[i], 1);
             ptx::mbar_init(&bars->b_empty[i], 1);
@@ -281,11 +291,21 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             // ---------------- TMA producer: corpus tiles of every unit of this CTA, back to back ----------------
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int ui = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
                 const int slice = u / p.n_qblocks;
                 const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
                 const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
                 const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+                if (kc_sm > 0) {
+                    // tail of the query block (columns >= 768) -> shared memory, once the previous unit's MMAs are done
+                    const int q0 = (u % p.n_qblocks) * TC_M;
+                    ptx::mbar_wait(&bars->ahi_empty, ((uint32_t)ui & 1u) ^ 1u);
+                    ptx::mbar_expect_tx(&bars->ahi_full, (uint32_t)kc_sm * TC_A_CHUNK_BYTES);
+                    for (int j = 0; j < kc_sm; ++j)
+                        ptx::tma_load_2d(smem_ahi + (size_t)j * TC_A_CHUNK_BYTES, &map_q, &bars->ahi_full,
+                                         (kc_tm + j) * TC_KC, q0);
+                }
                 for (int t = 0; t < n_tiles; ++t) {
                     const int row0 = (int)(row_begin + (int64_t)t * TC_N);
                     for (int kc = 0; kc < p.kchunks; kc += p.kps) {
@@ -306,16 +326,18 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // datapath); only the tcgen05 instructions themselves are issued by one elected lane.
         constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_M, TC_N);
         const uint64_t b_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_b));
+        const uint64_t ahi_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_ahi));
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;           // tiles issued by this CTA so far (accumulator stage / phase)
-        int ui = 0;           // units started (phase of a_full)
+        int ui = 0;           // units started (phase of a_full / ahi_full)
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
             const int slice = u / p.n_qblocks;
             const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
             const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
             const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
             ptx::mbar_wait(&bars->a_full, (uint32_t)ui & 1u);      // this unit's query block is in TMEM
+            if (kc_sm > 0) ptx::mbar_wait(&bars->ahi_full, (uint32_t)ui & 1u);   // ... and its tail in shared memory
             ptx::tc_fence_after();
             for (int t = 0; t < n_tiles; ++t, ++it) {
                 const int as = it % TS_ACC;
@@ -330,14 +352,25 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     const uint64_t b_desc = b_desc0 + (uint64_t)(stage * p.kps * (TC_B_STAGE_BYTES >> 4));
                     if (ptx::elect_one()) {
                         for (int j = 0; j < p.kps; ++j) {
+                            if (kc + j < kc_tm) {
 #pragma unroll
-                            for (int k4 = 0; k4 < TC_KC / 16; ++k4)
-                                ptx::umma_f16_ts(d_tmem, a_tmem + j * (TC_KC / 2) + k4 * 8,
-                                                 b_desc + (uint64_t)(j * (TC_B_STAGE_BYTES >> 4) + k4 * 2), idesc,
-                                                 (uint32_t)((kc | j | k4) != 0));
+                                for (int k4 = 0; k4 < TC_KC / 16; ++k4)
+                                    ptx::umma_f16_ts(d_tmem, a_tmem + j * (TC_KC / 2) + k4 * 8,
+                                                     b_desc + (uint64_t)(j * (TC_B_STAGE_BYTES >> 4) + k4 * 2), idesc,
+                                                     (uint32_t)((kc | j | k4) != 0));
+                            } else {
+                                const uint64_t a_desc = ahi_desc0 + (uint64_t)((kc + j - kc_tm) * (TC_A_CHUNK_BYTES >> 4));
+#pragma unroll
+                                for (int k4 = 0; k4 < TC_KC / 16; ++k4)
+                                    ptx::umma_f16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2),
+                                                     b_desc + (uint64_t)(j * (TC_B_STAGE_BYTES >> 4) + k4 * 2), idesc, 1u);
+                            }
                         }
                         ptx::umma_commit(&bars->b_empty[stage]);
-                        if (kc + p.kps >= p.kchunks) ptx::umma_commit(&bars->acc_full[as]);
+                        if (kc + p.kps >= p.kchunks) {
+                            ptx::umma_commit(&bars->acc_full[as]);
+                            if (kc_sm > 0 && t == n_tiles - 1) ptx::umma_commit(&bars->ahi_empty);   // unit done with A_hi
+                        }
                     }
                     __syncwarp();
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -368,7 +401,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             // columns may be overwritten: 64 bf16 (= 32 packed 32-bit columns) per tcgen05.st.
             if (half == 0) {
                 const uint4* src = reinterpret_cast<const uint4*>(p.queries + (int64_t)(active ? qg : 0) * p.ldq);
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                for (int kc = 0; kc < kc_tm; ++kc) {
                     uint32_t r[32];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -539,7 +572,7 @@ static int ts_choose_splits(int qblocks, int64_t n_rows, int dim, int sms) {
 
 bool dense_tc_supported(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t ldc, const __nv_bfloat16* queries,
                         int n_queries, int64_t ldq, int k) {
-    if (dim % TC_KC != 0 || dim > TC_MAXD || dim <= 0) return false;
+    if (dim % TC_KC != 0 || dim > TS_MAXD || dim <= 0) return false;
     if (k < 1 || k > TC_KMAX) return false;
     if (ldc % 8 != 0 || ldq % 8 != 0) return false;
     if ((reinterpret_cast<uintptr_t>(corpus) & 15) || (reinterpret_cast<uintptr_t>(queries) & 15)) return false;
@@ -548,7 +581,7 @@ bool dense_tc_supported(const __nv_bfloat16* corpus, int64_t n_rows, int dim, in
 }
 
 size_t dense_tc_workspace(int64_t n_rows, int dim, int n_queries, int k) {
-    if (dim % TC_KC != 0 || dim > TC_MAXD || k > TC_KMAX || n_rows < 1) return 0;
+    if (dim % TC_KC != 0 || dim > TS_MAXD || k > TC_KMAX || n_rows < 1) return 0;
     const int slices = tc_slices(n_rows);
     const size_t n = (size_t)n_queries * slices * k * 2;      // TS variant: two lists per (query, split)
     return align_up(n * 4, 256) * 2;
@@ -579,7 +612,12 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     p.id_base = id_base;
     p.doc_group = doc_group;
     p.q_group = q_group;
-    const size_t a_bytes = variant == 1 ? 0 : (size_t)p.kchunks * TC_A_CHUNK_BYTES;
+    if (variant != 1 && dim > TC_MAXD) {
+        set_error("dense_topk(tcgen05 SS): dim=%d > %d; use the TS variant", dim, TC_MAXD);
+        return EZR_ERR_UNSUPPORTED;
+    }
+    const int kc_sm = p.kchunks > TS_TMEM_KC ? p.kchunks - TS_TMEM_KC : 0;
+    const size_t a_bytes = variant == 1 ? (size_t)kc_sm * TC_A_CHUNK_BYTES : (size_t)p.kchunks * TC_A_CHUNK_BYTES;
     const size_t fixed = 1024 /*alignment slack*/ + sizeof(TcBarriers) + 64;
     p.kps = 1;
     if (variant == 1) p.kps = (p.kchunks % 4 == 0) ? 4 : ((p.kchunks % 2 == 0) ? 2 : 1);

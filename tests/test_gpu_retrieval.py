@@ -270,6 +270,22 @@ def test_dense_exact_integer_inputs(kernel, n, d, q, k):
     _check_dense(res, c, qv, k, exact=True)
 
 
+@pytest.mark.parametrize("n,d,q,k", [(3000, 1024, 130, 10), (2500, 832, 5, 8), (70_000, 1024, 300, 10)])
+def test_dense_wide_dims_use_hybrid_tmem_smem_queries(n, d, q, k):
+    # BGE-large is 1024-d (BASELINE config 5): 768 columns of the query block sit in TMEM, the rest in shared memory
+    c, qv = _dense_case(n, d, q, 200 + n, integer=True)
+    res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), k)
+    assert _lib.lib().ezr_dense_last_kernel() == b"tcgen05-ts"
+    _check_dense(res, c, qv, k, exact=True)
+    L = _lib.lib()
+    _lib.check(L.ezr_dense_set_kernel(2))
+    try:
+        with pytest.raises(_lib.EzrError):
+            batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), k)      # SS variant stops at 768
+    finally:
+        L.ezr_dense_set_kernel(0)
+
+
 @pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_dense_unit_vectors_within_tolerance(kernel):
     c, qv = _dense_case(30_000, 768, 200, 7)
