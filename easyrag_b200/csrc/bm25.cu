@@ -103,19 +103,6 @@ template <> struct KeyOf<float> {
     static __device__ __forceinline__ int load(const float* acc, int i) { return reinterpret_cast<const int*>(acc)[i]; }
 };
 
-// 128-bit view of the accumulators: kDocsPerVec documents per access and the key of the e-th one.
-template <typename S> struct VecKeys;
-template <> struct VecKeys<double> {
-    static constexpr int kDocs = 2;
-    static __device__ __forceinline__ int key(const uint4& v, int e) { return (int)(e == 0 ? v.y : v.w); }
-};
-template <> struct VecKeys<float> {
-    static constexpr int kDocs = 4;
-    static __device__ __forceinline__ int key(const uint4& v, int e) {
-        return (int)(e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)));
-    }
-};
-
 // MODE 0: fused top-k (k<=32) -> per-(query,range) partial lists.  MODE 1: write the score row.
 // A CTA owns one query and kBmRpc consecutive document ranges.  Range i+1's first postings are issued right after
 // range i's accumulation, so their latency hides behind range i's selection phases; term ids / indptr / range
@@ -151,24 +138,19 @@ bm25_score_kernel(const Bm25Params p) {
     __shared__ int s_gthr;
     if (MODE == 0 && tid == kBmThreads - 1) s_gthr = *reinterpret_cast<const volatile int32_t*>(p.thr_key + q);
 
-    int longest = 0;
     if (tid < m0) {
         const int t = p.q_terms[qs + tid];
         if (t >= 0 && t < p.vocab) {
             const int base = (int)p.indptr[t];                  // n_postings < 2^31 (checked on the host)
             const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r0;
 #pragma unroll
-            for (int i = 0; i <= kBmRpc; ++i) {
-                s_off[i][tid] = base + (int)ro[min(i, n_r)];
-                if (i > 0) longest = max(longest, s_off[i][tid] - s_off[i - 1][tid]);
-            }
+            for (int i = 0; i <= kBmRpc; ++i) s_off[i][tid] = base + (int)ro[min(i, n_r)];
         } else {
 #pragma unroll
             for (int i = 0; i <= kBmRpc; ++i) s_off[i][tid] = 0;
         }
     }
-    // barrier + vote: is some (term, range) segment longer than the CTA?  (then the residual loops must run)
-    const bool any_long = __syncthreads_or(longest > kBmThreads) != 0;
+    __syncthreads();
 
     const int shared_thr = (MODE == 0) ? s_gthr : 0;
     int d[kBmMaxT];
@@ -200,12 +182,10 @@ bm25_score_kernel(const Bm25Params p) {
         for (int j = 0; j < kBmMaxT; ++j) {
             if (j < m0) {   // block-uniform
                 if (d[j] >= 0) acc[d[j] - rbase] += w[j];
-                if (any_long) {                                  // rare: a segment longer than the CTA
-                    const int beg = s_off[ri][j];
-                    const int len = s_off[ri + 1][j] - beg;
-                    for (int o = tid + kBmThreads; o < len; o += kBmThreads)
-                        acc[__ldg(post_doc + beg + o) - rbase] += __ldg(post_w + beg + o);
-                }
+                const int beg = s_off[ri][j];
+                const int len = s_off[ri + 1][j] - beg;
+                for (int o = tid + kBmThreads; o < len; o += kBmThreads)           // segments longer than the CTA
+                    acc[__ldg(post_doc + beg + o) - rbase] += __ldg(post_w + beg + o);
                 __syncthreads();
             }
         }
@@ -264,16 +244,15 @@ bm25_score_kernel(const Bm25Params p) {
                 if (tid == 0) s_thr = shared_thr;               // single pass: the shared bound replaces phase 1
             } else {
                 tmax = 0;
-                const uint4* a4 = reinterpret_cast<const uint4*>(acc);
+                if (want == -1) {
 #pragma unroll
-                for (int i = 0; i < kPer / VecKeys<S>::kDocs; ++i) {
-                    const int vi = tid + i * kBmThreads;
-                    const uint4 v = a4[vi];
-#pragma unroll
-                    for (int e = 0; e < VecKeys<S>::kDocs; ++e) {
-                        const int key = VecKeys<S>::key(v, e);
-                        if (want == -1) tmax = max(tmax, key);
-                        else if (key > tmax && p.doc_group[rbase + vi * VecKeys<S>::kDocs + e] == want) tmax = key;
+                    for (int i = 0; i < kPer; ++i) tmax = max(tmax, KeyOf<S>::load(acc, tid + i * kBmThreads));
+                } else {
+#pragma unroll 4
+                    for (int i = 0; i < kPer; ++i) {
+                        const int doc = tid + i * kBmThreads;
+                        const int key = KeyOf<S>::load(acc, doc);
+                        if (key > tmax && p.doc_group[rbase + doc] == want) tmax = key;
                     }
                 }
                 int gmax = tmax;
@@ -297,20 +276,14 @@ bm25_score_kernel(const Bm25Params p) {
             constexpr int kCand = kBmThreads;                   // candidate capacity (s_ws / s_wi are reused)
             __syncthreads();                                    // s_thr / s_wi read by everyone: reuse them
             if (tmax >= thr) {                                  // only threads owning a qualifying document re-scan
-                const uint4* a4 = reinterpret_cast<const uint4*>(acc);
 #pragma unroll 4
-                for (int i = 0; i < kPer / VecKeys<S>::kDocs; ++i) {
-                    const int vi = tid + i * kBmThreads;
-                    const uint4 v = a4[vi];
-#pragma unroll
-                    for (int e = 0; e < VecKeys<S>::kDocs; ++e) {
-                        if (VecKeys<S>::key(v, e) >= thr) {
-                            const int doc = vi * VecKeys<S>::kDocs + e;
-                            const S s = acc[doc];
-                            if (s > (S)0 && (want == -1 || p.doc_group[rbase + doc] == want)) {
-                                const int idx = atomicAdd(&s_cnt, 1);
-                                if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + doc; }
-                            }
+                for (int i = 0; i < kPer; ++i) {
+                    const int doc = tid + i * kBmThreads;
+                    if (KeyOf<S>::load(acc, doc) >= thr) {
+                        const S s = acc[doc];
+                        if (s > (S)0 && (want == -1 || p.doc_group[rbase + doc] == want)) {
+                            const int idx = atomicAdd(&s_cnt, 1);
+                            if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + doc; }
                         }
                     }
                 }
