@@ -27,6 +27,8 @@ class Bm25IndexStruct(C.Structure):
         ("post_w", C.c_void_p),
         ("range_off", C.c_void_p),
         ("doc_group", C.c_void_p),
+        ("monotone", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

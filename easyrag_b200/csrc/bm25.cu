@@ -90,6 +90,7 @@ struct Bm25Params {
     int32_t id_base;
     void* out_scores;   // fused: partial [Q][n_ranges][k]; rows: [Q][n_docs]
     int32_t* out_ids;   // fused: partial ids
+    int32_t monotone;   // every posting weight is >= 0 (no negative idf): partial sums only grow
     int32_t* thr_key;   // fused: [Q] running lower bound (integer key) of each query's k-th best score, zeroed per call
 };
 
@@ -102,6 +103,10 @@ template <> struct KeyOf<double> {
 template <> struct KeyOf<float> {
     static __device__ __forceinline__ int load(const float* acc, int i) { return reinterpret_cast<const int*>(acc)[i]; }
 };
+
+template <typename S> __device__ __forceinline__ int score_key(S v);
+template <> __device__ __forceinline__ int score_key<double>(double v) { return __double2hiint(v); }
+template <> __device__ __forceinline__ int score_key<float>(float v) { return __float_as_int(v); }
 
 // MODE 0: fused top-k (k<=32) -> per-(query,range) partial lists.  MODE 1: write the score row.
 // A CTA owns one query and kBmRpc consecutive document ranges.  Range i+1's first postings are issued right after
@@ -136,7 +141,10 @@ bm25_score_kernel(const Bm25Params p) {
     // they finished long ago).  Anything below it cannot reach the final top-k, so it may be dropped here already.
     // ONE thread reads it (other CTAs raise it concurrently; the branch below must be block-uniform).
     __shared__ int s_gthr;
-    if (MODE == 0 && tid == kBmThreads - 1) s_gthr = *reinterpret_cast<const volatile int32_t*>(p.thr_key + q);
+    if (MODE == 0 && tid == kBmThreads - 1) {
+        s_gthr = *reinterpret_cast<const volatile int32_t*>(p.thr_key + q);
+        s_cnt = 0;
+    }
 
     if (tid < m0) {
         const int t = p.q_terms[qs + tid];
@@ -153,6 +161,22 @@ bm25_score_kernel(const Bm25Params p) {
     __syncthreads();
 
     const int shared_thr = (MODE == 0) ? s_gthr : 0;
+    // With a bound from earlier ranges and non-negative weights, a document qualifies exactly once: when its
+    // partial sum crosses the bound.  It is appended to the candidate list right there, and the selection scan over
+    // all 8192 accumulators is not needed at all for this (query, range).
+    const bool track = (MODE == 0) && shared_thr > 0 && p.monotone != 0;
+    auto rmw = [&](int doc, S wv, int rbase_) {
+        S* a = acc + (doc - rbase_);
+        const S old = *a;
+        const S nw = old + wv;
+        *a = nw;
+        if (track && score_key<S>(nw) >= shared_thr && score_key<S>(old) < shared_thr) {
+            if (want == -1 || p.doc_group[doc] == want) {
+                const int idx = atomicAdd(&s_cnt, 1);
+                if (idx < kBmThreads) s_wi[idx] = doc;
+            }
+        }
+    };
     int d[kBmMaxT];
     S w[kBmMaxT];
     // first posting of every (first-chunk) term of range 0: all loads in flight together
@@ -181,11 +205,11 @@ bm25_score_kernel(const Bm25Params p) {
 #pragma unroll
         for (int j = 0; j < kBmMaxT; ++j) {
             if (j < m0) {   // block-uniform
-                if (d[j] >= 0) acc[d[j] - rbase] += w[j];
+                if (d[j] >= 0) rmw(d[j], w[j], rbase);
                 const int beg = s_off[ri][j];
                 const int len = s_off[ri + 1][j] - beg;
                 for (int o = tid + kBmThreads; o < len; o += kBmThreads)           // segments longer than the CTA
-                    acc[__ldg(post_doc + beg + o) - rbase] += __ldg(post_w + beg + o);
+                    rmw(__ldg(post_doc + beg + o), __ldg(post_w + beg + o), rbase);
                 __syncthreads();
             }
         }
@@ -207,7 +231,7 @@ bm25_score_kernel(const Bm25Params p) {
             for (int j = 0; j < mt; ++j) {
                 const int beg = s_lo[j], len = s_len2[j];
                 for (int o = tid; o < len; o += kBmThreads)
-                    acc[__ldg(post_doc + beg + o) - rbase] += __ldg(post_w + beg + o);
+                    rmw(__ldg(post_doc + beg + o), __ldg(post_w + beg + o), rbase);
                 __syncthreads();
             }
         }
@@ -238,52 +262,58 @@ bm25_score_kernel(const Bm25Params p) {
             //    itself to that output slot.  No sort, no serial insertion chain.
             // Exact ties at the bound (or fewer than k non-empty groups) can overflow the list; then the robust
             // warp-shuffle selection takes over.  Rows >= rn of the last range hold zeros and never qualify.
-            int tmax = 0x7fffffff;                              // "this thread must re-scan" when phase 1 is skipped
-            if (tid == 0) s_cnt = 0;
-            if (shared_thr > 0) {
-                if (tid == 0) s_thr = shared_thr;               // single pass: the shared bound replaces phase 1
+            constexpr int kCand = kBmThreads;                   // candidate capacity (s_ws / s_wi are reused)
+            if (track) {
+                // candidates were collected while accumulating (the last term's barrier made them visible): fetch
+                // their final scores
+                const int nc = min(s_cnt, kCand);
+                if (tid < nc) s_ws[tid] = acc[s_wi[tid] - rbase];
             } else {
-                tmax = 0;
-                if (want == -1) {
-#pragma unroll
-                    for (int i = 0; i < kPer; ++i) tmax = max(tmax, KeyOf<S>::load(acc, tid + i * kBmThreads));
+                int tmax = 0x7fffffff;                              // "this thread must re-scan" when phase 1 is skipped
+                if (shared_thr > 0) {
+                    if (tid == 0) s_thr = shared_thr;               // single pass: the shared bound replaces phase 1
                 } else {
+                    tmax = 0;
+                    if (want == -1) {
+#pragma unroll
+                        for (int i = 0; i < kPer; ++i) tmax = max(tmax, KeyOf<S>::load(acc, tid + i * kBmThreads));
+                    } else {
+#pragma unroll 4
+                        for (int i = 0; i < kPer; ++i) {
+                            const int doc = tid + i * kBmThreads;
+                            const int key = KeyOf<S>::load(acc, doc);
+                            if (key > tmax && p.doc_group[rbase + doc] == want) tmax = key;
+                        }
+                    }
+                    int gmax = tmax;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+                    if ((lane & 15) == 0) s_wi[tid >> 4] = gmax;    // 32 group maxima (0: no positive score in the group)
+                    __syncthreads();
+                    if (warp == 0) {
+                        const int mine = s_wi[lane];
+                        int rank = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int o = s_wi[j];
+                            rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
+                        }
+                        if (rank == p.k - 1) s_thr = mine;          // ranks are a permutation: exactly one lane writes
+                    }
+                }
+                __syncthreads();
+                const int thr = s_thr;                              // 0 when fewer than k groups saw a positive score
+                __syncthreads();                                    // s_thr / s_wi read by everyone: reuse them
+                if (tmax >= thr) {                                  // only threads owning a qualifying document re-scan
 #pragma unroll 4
                     for (int i = 0; i < kPer; ++i) {
                         const int doc = tid + i * kBmThreads;
-                        const int key = KeyOf<S>::load(acc, doc);
-                        if (key > tmax && p.doc_group[rbase + doc] == want) tmax = key;
-                    }
-                }
-                int gmax = tmax;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-                if ((lane & 15) == 0) s_wi[tid >> 4] = gmax;    // 32 group maxima (0: no positive score in the group)
-                __syncthreads();
-                if (warp == 0) {
-                    const int mine = s_wi[lane];
-                    int rank = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int o = s_wi[j];
-                        rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
-                    }
-                    if (rank == p.k - 1) s_thr = mine;          // ranks are a permutation: exactly one lane writes
-                }
-            }
-            __syncthreads();
-            const int thr = s_thr;                              // 0 when fewer than k groups saw a positive score
-            constexpr int kCand = kBmThreads;                   // candidate capacity (s_ws / s_wi are reused)
-            __syncthreads();                                    // s_thr / s_wi read by everyone: reuse them
-            if (tmax >= thr) {                                  // only threads owning a qualifying document re-scan
-#pragma unroll 4
-                for (int i = 0; i < kPer; ++i) {
-                    const int doc = tid + i * kBmThreads;
-                    if (KeyOf<S>::load(acc, doc) >= thr) {
-                        const S s = acc[doc];
-                        if (s > (S)0 && (want == -1 || p.doc_group[rbase + doc] == want)) {
-                            const int idx = atomicAdd(&s_cnt, 1);
-                            if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + doc; }
+                        if (KeyOf<S>::load(acc, doc) >= thr) {
+                            const S s = acc[doc];
+                            if (s > (S)0 && (want == -1 || p.doc_group[rbase + doc] == want)) {
+                                const int idx = atomicAdd(&s_cnt, 1);
+                                if (idx < kCand) { s_ws[idx] = s; s_wi[idx] = rbase + doc; }
+                            }
                         }
                     }
                 }
@@ -342,6 +372,7 @@ bm25_score_kernel(const Bm25Params p) {
         }
         if (more) {
             __syncthreads();                                    // everyone is done with acc / s_ws / s_wi of this range
+            if (tid == 0) s_cnt = 0;
             uint4* a4 = reinterpret_cast<uint4*>(acc);
 #pragma unroll
             for (int i = 0; i < kBmRange / kVec / kBmThreads; ++i) a4[tid + i * kBmThreads] = make_uint4(0u, 0u, 0u, 0u);
@@ -506,7 +537,7 @@ static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int
     p.indptr = ix->indptr; p.post_doc = ix->post_doc; p.post_w = ix->post_w; p.range_off = ix->range_off;
     p.doc_group = ix->doc_group; p.q_ptr = q_ptr; p.q_terms = q_terms; p.q_group = q_group;
     p.n_docs = ix->n_docs; p.vocab = ix->vocab; p.n_ranges = ix->n_ranges; p.k = k; p.id_base = id_base;
-    p.out_scores = out_scores; p.out_ids = out_ids; p.thr_key = thr_key;
+    p.out_scores = out_scores; p.out_ids = out_ids; p.thr_key = thr_key; p.monotone = ix->monotone;
     const size_t smem = (size_t)kBmRange * sizeof(S);
     static bool attr_done[4] = {false, false, false, false};
     const int which = (sizeof(S) == 8 ? 0 : 2) + mode;

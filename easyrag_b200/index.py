@@ -176,6 +176,8 @@ class Bm25Index:
             self.doc_group = None
             if doc_group is not None:
                 self.doc_group = doc_group[doc_lo:doc_hi].to(device=device, dtype=torch.int32).contiguous()
+            # rank_bm25 replaces negative idf by epsilon * average_idf, which is negative only when the mean idf is
+            self.monotone = bool((stats.idf >= 0).all())
             torch.cuda.current_stream().synchronize()
         self._struct = None
         self.refresh_struct()
@@ -189,6 +191,7 @@ class Bm25Index:
         s.post_w = self.post_w.data_ptr()
         s.range_off = self.range_off.data_ptr()
         s.doc_group = self.doc_group.data_ptr() if self.doc_group is not None else None
+        s.monotone = int(self.monotone)
         self._struct = s
 
     def set_doc_group(self, doc_group: Optional[torch.Tensor]):
@@ -212,7 +215,7 @@ class Bm25Index:
             arrays["doc_group"] = self.doc_group
         _save_arrays(path, dict(kind="bm25", n_docs=self.n_docs, vocab=self.vocab, score_type=self.score_type,
                                 doc_lo=self.doc_lo, doc_hi=self.doc_hi, n_ranges=self.n_ranges,
-                                range_size=_lib.BM25_RANGE), arrays)
+                                range_size=_lib.BM25_RANGE, monotone=bool(self.monotone)), arrays)
 
     @classmethod
     def load(cls, path: str, device=None) -> "Bm25Index":
@@ -232,6 +235,7 @@ class Bm25Index:
         self.post_w = get("post_w").to(device)
         self.range_off = get("range_off").to(device)
         self.n_postings = int(self.post_doc.numel())
+        self.monotone = bool(meta.get("monotone", False))
         self.doc_group = get("doc_group").to(device) if os.path.exists(os.path.join(path, "doc_group.npy")) else None
         self._struct = None
         self.refresh_struct()

@@ -71,6 +71,8 @@ typedef struct ezr_bm25_index {
     const void* post_w;        /* [n_postings] double or float */
     const uint32_t* range_off; /* [vocab*(n_ranges+1)] */
     const int32_t* doc_group;  /* [n_docs] metadata class of each document, or NULL */
+    int32_t monotone;          /* 1 if every post_w >= 0 (no negative idf): enables crossing-based selection */
+    int32_t reserved;
 } ezr_bm25_index;
 
 /* K_d[i] = k1 * (one_minus_b + (b*doc_len[i]) / avgdl)   -- rank_bm25 get_scores denominator term */
