@@ -43,6 +43,7 @@ SIGNATURES = {
     "ezr_version": (C.c_int, []),
     "ezr_last_error": (C.c_char_p, []),
     "ezr_device_check": (C.c_int, []),
+    "ezr_bm25_range_size": (C.c_int, []),
     "ezr_bm25_doc_norm": (C.c_int, [_p, _i64, _dbl, _dbl, _dbl, _dbl, _p, _p]),
     "ezr_bm25_weights": (C.c_int, [_p, _p, _p, _i32, _i64, _p, _p, _dbl, _i32, _p, _p]),
     "ezr_bm25_range_index": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
@@ -99,6 +100,8 @@ def lib() -> C.CDLL:
         handle = C.CDLL(str(LIB_PATH))
         _bind(handle, SIGNATURES)
         _lib = handle
+        global BM25_RANGE
+        BM25_RANGE = int(handle.ezr_bm25_range_size())
     return _lib
 
 

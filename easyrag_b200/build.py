@@ -49,6 +49,9 @@ def nvcc() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     OUT_DIR.mkdir(exist_ok=True)
+    extra = os.environ.get("EZR_NVCC_DEFS", "").split()       # e.g. "-DEZR_BM25_RANGE=4096" for tuning experiments
+    if extra:
+        return _build_variant(extra, verbose)
     digest = _digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
@@ -80,6 +83,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("link failed")
     STAMP.write_text(digest)
     return LIB
+
+
+def _build_variant(extra, verbose):
+    """Tuning builds: compile with extra -D flags into _lib/variant_<tag>/ (select with EASYRAG_B200_LIB)."""
+    tag = hashlib.sha256(" ".join(extra).encode()).hexdigest()[:8]
+    vdir = OUT_DIR / f"variant_{tag}"
+    vdir.mkdir(exist_ok=True)
+    lib = vdir / "libeasyrag_b200.so"
+    cmd = [nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *extra, "-shared", "-o", str(lib),
+           *[str(x) for x in _sources()]]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("variant build failed")
+    return lib
 
 
 if __name__ == "__main__":

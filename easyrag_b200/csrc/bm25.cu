@@ -69,8 +69,19 @@ __global__ void bm25_range_index_kernel(const int64_t* __restrict__ indptr, cons
 }
 
 // ---------------------------------------------------------------- scoring --
-constexpr int kBmRange = 8192;   // documents per CTA: 64 KB of float64 accumulators
-constexpr int kBmThreads = 512;
+#ifndef EZR_BM25_RANGE
+#define EZR_BM25_RANGE 8192
+#endif
+#ifndef EZR_BM25_THREADS
+#define EZR_BM25_THREADS 512
+#endif
+#ifndef EZR_BM25_MINB
+#define EZR_BM25_MINB 3
+#endif
+constexpr int kBmRange = EZR_BM25_RANGE;     // documents per CTA (8192 -> 64 KB of float64 accumulators)
+constexpr int kBmThreads = EZR_BM25_THREADS;
+constexpr int kBmGroup = kBmThreads / 32;    // lanes per group: 32 group maxima bound the k-th score (k <= 32)
+static_assert(kBmGroup == 8 || kBmGroup == 16 || kBmGroup == 32, "BM25 CTA must have 256, 512 or 1024 threads");
 constexpr int kBmMaxT = 12;      // query terms preloaded per round (queries are 4-12 terms; longer ones loop)
 constexpr int kBmRpc = 1;        // document ranges per CTA (1: measured faster than 4 on B200)
 
@@ -113,7 +124,7 @@ template <> __device__ __forceinline__ int score_key<float>(float v) { return __
 // range i's accumulation, so their latency hides behind range i's selection phases; term ids / indptr / range
 // offsets are fetched once per CTA.
 template <typename S, int MODE>
-__global__ void __launch_bounds__(kBmThreads, 3)
+__global__ void __launch_bounds__(kBmThreads, EZR_BM25_MINB)
 bm25_score_kernel(const Bm25Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S* acc = reinterpret_cast<S*>(smem_raw);
@@ -146,19 +157,24 @@ bm25_score_kernel(const Bm25Params p) {
         s_cnt = 0;
     }
 
+    int longest = 0;
     if (tid < m0) {
         const int t = p.q_terms[qs + tid];
         if (t >= 0 && t < p.vocab) {
             const int base = (int)p.indptr[t];                  // n_postings < 2^31 (checked on the host)
             const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r0;
 #pragma unroll
-            for (int i = 0; i <= kBmRpc; ++i) s_off[i][tid] = base + (int)ro[min(i, n_r)];
+            for (int i = 0; i <= kBmRpc; ++i) {
+                s_off[i][tid] = base + (int)ro[min(i, n_r)];
+                if (i > 0) longest = max(longest, s_off[i][tid] - s_off[i - 1][tid]);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i <= kBmRpc; ++i) s_off[i][tid] = 0;
         }
     }
-    __syncthreads();
+    // barrier + vote: is some (term, range) segment longer than the CTA?  Only then do the residual loops run.
+    const bool any_long = __syncthreads_or(longest > kBmThreads) != 0;
 
     const int shared_thr = (MODE == 0) ? s_gthr : 0;
     // With a bound from earlier ranges and non-negative weights, a document qualifies exactly once: when its
@@ -206,10 +222,12 @@ bm25_score_kernel(const Bm25Params p) {
         for (int j = 0; j < kBmMaxT; ++j) {
             if (j < m0) {   // block-uniform
                 if (d[j] >= 0) rmw(d[j], w[j], rbase);
-                const int beg = s_off[ri][j];
-                const int len = s_off[ri + 1][j] - beg;
-                for (int o = tid + kBmThreads; o < len; o += kBmThreads)           // segments longer than the CTA
-                    rmw(__ldg(post_doc + beg + o), __ldg(post_w + beg + o), rbase);
+                if (any_long) {                                  // rare: a segment longer than the CTA
+                    const int beg = s_off[ri][j];
+                    const int len = s_off[ri + 1][j] - beg;
+                    for (int o = tid + kBmThreads; o < len; o += kBmThreads)
+                        rmw(__ldg(post_doc + beg + o), __ldg(post_w + beg + o), rbase);
+                }
                 __syncthreads();
             }
         }
@@ -287,8 +305,8 @@ bm25_score_kernel(const Bm25Params p) {
                     }
                     int gmax = tmax;
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-                    if ((lane & 15) == 0) s_wi[tid >> 4] = gmax;    // 32 group maxima (0: no positive score in the group)
+                    for (int o = kBmGroup / 2; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+                    if ((lane & (kBmGroup - 1)) == 0) s_wi[tid / kBmGroup] = gmax;   // 32 group maxima (0: none positive)
                     __syncthreads();
                     if (warp == 0) {
                         const int mine = s_wi[lane];
@@ -570,6 +588,8 @@ static int check_index(const ezr_bm25_index* ix) {
 using namespace ezr;
 
 extern "C" {
+
+int ezr_bm25_range_size(void) { return kBmRange; }
 
 int ezr_bm25_doc_norm(const int32_t* doc_len, int64_t n_docs, double k1, double b, double one_minus_b,
                       double avgdl, double* out_kd, void* stream) {

@@ -75,6 +75,9 @@ typedef struct ezr_bm25_index {
     int32_t reserved;
 } ezr_bm25_index;
 
+/* documents per range the library was built for (the `range_size` an index must use) */
+int ezr_bm25_range_size(void);
+
 /* K_d[i] = k1 * (one_minus_b + (b*doc_len[i]) / avgdl)   -- rank_bm25 get_scores denominator term */
 int ezr_bm25_doc_norm(const int32_t* doc_len, int64_t n_docs, double k1, double b, double one_minus_b,
                       double avgdl, double* out_kd, void* stream);

@@ -199,3 +199,72 @@ def test_bert_encoder_vs_transformers(pooling):
     _, ef = model.embed_packed(PackedBatch.from_lists(seqs, DEV))
     assert (_cos_rows(ef.cpu(), ref) > 1 - 1e-3).all()
     assert (ef.cpu() - ref).abs().max() < 2e-2
+
+
+# ------------------------------------------------------------ drop-in embedding classes
+class _FakeHFTokenizer:
+    """Minimal stand-in for a HF tokenizer (no tokenizer files offline): whitespace words -> ids by hash.
+
+    Same call shape GTEEmbedding / HuggingFaceEmbedding use: tokenizer(texts, max_length=, padding=True,
+    truncation=True, return_tensors='pt') -> {"input_ids", "attention_mask"}; pads LEFT like Qwen2Tokenizer
+    (tokenization_qwen.py:218) or RIGHT like BERT tokenizers.
+    """
+
+    def __init__(self, vocab, side="left", eos=2):
+        self.vocab, self.side, self.eos = vocab, side, eos
+
+    def __call__(self, texts, max_length=512, padding=True, truncation=True, return_tensors="pt"):
+        seqs = []
+        for t in texts:
+            ids = [3 + (sum(map(ord, w)) * 7919) % (self.vocab - 3) for w in t.split()][: max_length - 1] + [self.eos]
+            seqs.append(ids)
+        return dict(zip(("input_ids", "attention_mask"), (oenc.pad_left if self.side == "left" else oenc.pad_right)(seqs)))
+
+
+def test_gte_embedding_dropin_surface():
+    from easyrag_b200.embeddings import GTEEmbedding
+    from easyrag_b200.schema import TextNode
+    z, cfg, state = _golden()
+    enc_model = Qwen2Encoder(cfg, state, device=DEV)
+    tok = _FakeHFTokenizer(cfg.vocab_size, "left")
+    emb = GTEEmbedding(model_name="gte-tiny", embed_batch_size=4, embed_type=1, encoder=enc_model, tokenizer=tok)
+    texts = ["alpha beta gamma", "delta", "epsilon zeta eta theta iota kappa"]
+    got = emb._get_text_embeddings(texts)
+    ids, mask = tok(texts)["input_ids"], tok(texts)["attention_mask"]
+    ref = oenc.gte_embed(state, cfg, ids, mask)
+    assert len(got) == 3 and len(got[0]) == cfg.hidden_size and isinstance(got[0][0], float)
+    assert (_cos_rows(torch.tensor(got), ref) > 1 - 1e-3).all()
+    # query path prepends the instruct string (gte_embeddings.py:52-53,80-82)
+    q = emb.get_query_embedding("what is alpha")
+    iq, mq = tok([emb.get_detailed_instruct("what is alpha")]).values()
+    assert _cos_rows(torch.tensor([q]), oenc.gte_embed(state, cfg, iq, mq)).item() > 1 - 1e-3
+    # TransformComponent behaviour: __call__(nodes) fills node.embedding from get_node_content(node, embed_type)
+    nodes = [TextNode(text="body one", metadata={"file_path": "a/b.txt"}), TextNode(text="body two")]
+    out = emb(nodes)
+    assert out is nodes and all(len(n.embedding) == cfg.hidden_size for n in nodes)
+    want = emb._get_text_embeddings(["###\na/b.txt\n\nbody one", "body two"])
+    assert np.allclose(nodes[0].embedding, want[0]) and np.allclose(nodes[1].embedding, want[1])
+
+
+def test_hf_embedding_dropin_surface():
+    from easyrag_b200.embeddings import HuggingFaceEmbedding
+    cfg = BertConfig(vocab_size=500, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                     num_attention_heads=2, max_position_embeddings=64)
+    state = random_state("bert", cfg, 31, std=0.05)
+    model = BertEncoder(cfg, state, device=DEV, pooling="cls")
+    tok = _FakeHFTokenizer(cfg.vocab_size, "right")
+    with pytest.raises(ValueError):
+        HuggingFaceEmbedding(model_name="x", pooling="mean", encoder=model, hf_tokenizer=tok)   # hf_embeddings.py:67-76
+    emb = HuggingFaceEmbedding(model_name="BAAI/bge-small-zh", embed_batch_size=2, encoder=model, hf_tokenizer=tok)
+    texts = ["one two three", "four", "five six"]
+    got = torch.tensor(emb._get_text_embeddings(texts))
+    seqs = [[int(t) for t, m in zip(r, mk) if m] for r, mk in zip(*tok(texts).values())]
+    ref = oenc.bert_embed(state, cfg, seqs, pooling="cls")
+    assert (_cos_rows(got, ref) > 1 - 1e-3).all()
+    assert np.allclose(got.norm(dim=1).numpy(), 1.0, atol=1e-4)
+    # a str gives one vector; the query prompt of BGE-zh models is prepended (llama_index get_query_instruct_for_model_name)
+    q = emb._get_query_embedding("seven eight")
+    assert isinstance(q, list) and len(q) == cfg.hidden_size
+    from easyrag_b200.embeddings.hf_embeddings import BGE_QUERY_ZH
+    seq = [[int(t) for t, m in zip(r, mk) if m] for r, mk in zip(*tok([BGE_QUERY_ZH + "seven eight"]).values())]
+    assert _cos_rows(torch.tensor([q]), oenc.bert_embed(state, cfg, seq, pooling="cls")).item() > 1 - 1e-3
