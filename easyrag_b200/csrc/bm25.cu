@@ -69,16 +69,19 @@ __global__ void bm25_range_index_kernel(const int64_t* __restrict__ indptr, cons
 }
 
 // ---------------------------------------------------------------- scoring --
+// Launch shape, swept on B200 (profiles/README.md): (range, threads, CTAs/SM) = (4096, 256, 6) 19.6 ms,
+// (8192, 512, 3) 21.3 ms, (8192, 512, 2) 25.0 ms, (16384, 1024, 1) 29.3 ms, (4096, 512, 3) 31.4 ms per 10k queries.
+// The kernel is latency/barrier bound, so many small CTAs per SM win.
 #ifndef EZR_BM25_RANGE
-#define EZR_BM25_RANGE 8192
+#define EZR_BM25_RANGE 4096
 #endif
 #ifndef EZR_BM25_THREADS
-#define EZR_BM25_THREADS 512
+#define EZR_BM25_THREADS 256
 #endif
 #ifndef EZR_BM25_MINB
-#define EZR_BM25_MINB 3
+#define EZR_BM25_MINB 6
 #endif
-constexpr int kBmRange = EZR_BM25_RANGE;     // documents per CTA (8192 -> 64 KB of float64 accumulators)
+constexpr int kBmRange = EZR_BM25_RANGE;     // documents per CTA (4096 -> 32 KB of float64 accumulators)
 constexpr int kBmThreads = EZR_BM25_THREADS;
 constexpr int kBmGroup = kBmThreads / 32;    // lanes per group: 32 group maxima bound the k-th score (k <= 32)
 static_assert(kBmGroup == 8 || kBmGroup == 16 || kBmGroup == 32, "BM25 CTA must have 256, 512 or 1024 threads");

@@ -64,7 +64,7 @@ typedef struct ezr_bm25_index {
     int64_t n_postings;
     int32_t vocab;
     int32_t score_type;        /* ezr_score_type of post_w */
-    int32_t range_size;        /* 8192 */
+    int32_t range_size;        /* ezr_bm25_range_size(): 4096 */
     int32_t n_ranges;          /* ceil(n_docs / range_size) */
     const int64_t* indptr;     /* [vocab+1] */
     const int32_t* post_doc;   /* [n_postings] ascending inside a term */
