@@ -190,9 +190,11 @@ def algorithmic_bytes(args, data, index, n_rows_local, n_slices_q):
     df = (index.indptr[1:] - index.indptr[:-1])
     postings = int(df[terms[valid]].sum())
     bm25 = postings * (4 + index.post_w.element_size()) + args.queries * args.k * 12
+    # two-phase path: the candidate pass reads one packed 4-byte word per posting (+ the candidate ids it emits)
+    bm25_cand = postings * 4 + args.queries * args.k * 4
     passes = -(-args.queries // 128)
     dense = passes * n_rows_local * args.dim * 2 + args.queries * args.dim * 2 + args.queries * args.k * 8
-    return {"bm25_score": bm25, "dense_tc": dense, "postings_per_step": postings, "dense_passes": passes}
+    return {"bm25_score": bm25, "bm25_cand": bm25_cand, "dense_tc": dense, "postings_per_step": postings, "dense_passes": passes}
 
 
 def run_ours(args):
@@ -276,7 +278,8 @@ def run_ours(args):
     _lib.check(L.ezr_profile_enable(1))
     ms = timed(step_device, args.steps)
     _lib.check(L.ezr_profile_enable(0))
-    prof = {name: _lib.profile_read(name) for name in ("bm25_score", "dense_tc", "dense_simt", "merge", "fuse")}
+    prof = {name: _lib.profile_read(name) for name in ("bm25_cand", "bm25_rescore", "bm25_score", "dense_tc",
+                                                       "dense_simt", "merge", "fuse")}
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
@@ -298,12 +301,15 @@ def run_ours(args):
               if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s")
     dense_flops = 2.0 * dense.n_rows * args.dim * args.queries          # per launch: every query x every local row
     kernels = {}
-    for name in ("bm25_score", "dense_tc"):
+    two_phase = prof["bm25_cand"][1] > 0
+    for name in ("bm25_cand", "bm25_score", "dense_tc"):
         tot, n = prof[name]
-        if n:
+        if n and not (name == "bm25_score" and two_phase):     # two-phase: bm25_score only sees overflowed queries
             avg_ms = tot / n
             kernels[name] = {"launches": n, "avg_ms": avg_ms, "alg_bytes_per_launch": alg[name],
                              "GBps": alg[name] / (avg_ms * 1e-3) / 1e9}
+    others = {name: {"launches": prof[name][1], "avg_ms": prof[name][0] / prof[name][1]}
+              for name in ("bm25_rescore", "bm25_score", "merge", "fuse") if prof[name][1] and name not in kernels}
     if "dense_tc" in kernels:
         # The persistent kernel shares each corpus pass between all resident query blocks through L2, so HBM is not
         # its bound (ncu: DRAM traffic ~ a few corpus passes per launch); it is a [Q x D] . [D x N] contraction on the
@@ -324,8 +330,12 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom]["GBps"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "kernels": kernels,
-                    "note": "algorithmic bytes = postings touched (12 B each) + outputs; ncu shows most of them are "
-                            "served from L2 (range-major grid), DRAM traffic per launch is in `traffic`"}
+                    "note": ("algorithmic bytes = postings touched (4 B packed word each) + candidate ids"
+                             if dom == "bm25_cand" else "algorithmic bytes = postings touched (12 B each) + outputs")
+                            + "; ncu shows most of them are served from L2 (range-major grid), DRAM traffic per "
+                              "launch is in `traffic`"}
+    if roofline:
+        roofline["other_kernels"] = others
     launches_per_step = sum(prof[n_][1] for n_ in prof) // max(args.steps, 1)
     value = args.steps * args.queries / (ms * 1e-3)
     e2e_v = args.steps * args.queries / (ms_e2e * 1e-3)

@@ -28,7 +28,8 @@ class Bm25IndexStruct(C.Structure):
         ("range_off", C.c_void_p),
         ("doc_group", C.c_void_p),
         ("monotone", C.c_int32),
-        ("reserved", C.c_int32),
+        ("pk_scale_log2", C.c_int32),
+        ("post_pk", C.c_void_p),
     ]
 
 
@@ -47,6 +48,8 @@ SIGNATURES = {
     "ezr_bm25_doc_norm": (C.c_int, [_p, _i64, _dbl, _dbl, _dbl, _dbl, _p, _p]),
     "ezr_bm25_weights": (C.c_int, [_p, _p, _p, _i32, _i64, _p, _p, _dbl, _i32, _p, _p]),
     "ezr_bm25_range_index": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
+    "ezr_bm25_pack": (C.c_int, [_p, _p, _i64, _i32, _p, C.POINTER(C.c_int32), _p, _p]),
+    "ezr_bm25_cand_capacity": (C.c_int, []),
     "ezr_bm25_topk_workspace": (_sz, [_IX, _i32, _i32]),
     "ezr_bm25_topk": (C.c_int, [_IX, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p, _sz, _p]),
     "ezr_bm25_scores": (C.c_int, [_IX, _p, _p, _i32, _p, _p]),
@@ -132,7 +135,8 @@ def require_cuda() -> None:
     check(lib().ezr_device_check(), "ezr_device_check")
 
 
-PROF_SLOTS = {"bm25_score": 0, "dense_tc": 1, "dense_simt": 2, "merge": 3, "fuse": 4,
+PROF_SLOTS = {"bm25_cand": 8, "bm25_rescore": 9,
+              "bm25_score": 0, "dense_tc": 1, "dense_simt": 2, "merge": 3, "fuse": 4,
               "enc_gemm": 5, "enc_attn": 6, "enc_other": 7}
 
 

@@ -106,6 +106,8 @@ struct Bm25Params {
     int32_t* out_ids;   // fused: partial ids
     int32_t monotone;   // every posting weight is >= 0 (no negative idf): partial sums only grow
     int32_t* thr_key;   // fused: [Q] running lower bound (integer key) of each query's k-th best score, zeroed per call
+    const int32_t* q_list;   // optional indirection: CTA column i works on query q_list[i] ...
+    const int32_t* q_count;  // ... for i < *q_count (the two-phase path hands its overflowed queries over this way)
 };
 
 // Integer sort key of a non-negative score: IEEE-754 ordering of non-negative floats equals the ordering of their
@@ -127,8 +129,7 @@ template <> __device__ __forceinline__ int score_key<float>(float v) { return __
 // range i's accumulation, so their latency hides behind range i's selection phases; term ids / indptr / range
 // offsets are fetched once per CTA.
 template <typename S, int MODE>
-__global__ void __launch_bounds__(kBmThreads, EZR_BM25_MINB)
-bm25_score_kernel(const Bm25Params p) {
+__device__ __forceinline__ void bm25_score_body(const Bm25Params& p, const int q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S* acc = reinterpret_cast<S*>(smem_raw);
     __shared__ int s_off[kBmRpc + 1][kBmMaxT];      // first-chunk terms: absolute posting offset at each range boundary
@@ -138,7 +139,6 @@ bm25_score_kernel(const Bm25Params p) {
     __shared__ int s_thr;
     __shared__ int s_cnt;
 
-    const int q = blockIdx.x;
     const int r0 = blockIdx.y * kBmRpc;
     const int n_r = min(kBmRpc, p.n_ranges - r0);
     const int tid = threadIdx.x;
@@ -402,14 +402,38 @@ bm25_score_kernel(const Bm25Params p) {
     }
 }
 
+template <typename S, int MODE>
+__global__ void __launch_bounds__(kBmThreads, EZR_BM25_MINB)
+bm25_score_kernel(const Bm25Params p) {
+    if (p.q_list == nullptr) {
+        bm25_score_body<S, MODE>(p, blockIdx.x);
+        return;
+    }
+    const int nq = *p.q_count;
+    for (int qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+        bm25_score_body<S, MODE>(p, p.q_list[qi]);
+        __syncthreads();                                        // shared state is re-initialised per query
+    }
+}
+
+}  // namespace ezr
+#include "bm25_pk.cuh"
+namespace ezr {
+
 // One warp per row: merge n_cand candidates (id<0 = empty) into the final top-k (k<=32).
+// row_list / row_count (optional): warp i handles row row_list[i] for i < *row_count.
 template <typename S>
 __global__ void merge_warp_kernel(const S* __restrict__ cs, const int32_t* __restrict__ cid, int n_rows, int n_cand,
                                   int64_t stride, int k, int id_add, S* __restrict__ out_s,
-                                  int32_t* __restrict__ out_id, int32_t* __restrict__ out_cnt) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                  int32_t* __restrict__ out_id, int32_t* __restrict__ out_cnt,
+                                  const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
+    if (row_list) {
+        if (row >= *row_count) return;
+        row = row_list[row];
+    }
     WarpTopK<S> tk;
     tk.init(k);
     const S* rs = cs + (int64_t)row * stride;
@@ -536,13 +560,14 @@ static int select_rows_impl(const S* scores, int n_rows, int64_t n_cols, int64_t
 
 template <typename S>
 static int merge_impl(const S* cs, const int32_t* cid, int n_rows, int n_cand, int64_t stride, int k, int id_add,
-                      S* out_s, int32_t* out_id, int32_t* out_cnt, cudaStream_t st) {
+                      S* out_s, int32_t* out_id, int32_t* out_cnt, cudaStream_t st,
+                      const int32_t* row_list = nullptr, const int32_t* row_count = nullptr) {
     if (n_rows == 0) return EZR_OK;
     if (k <= 32) {
         const int wpb = 8;
         ProfScope prof(EZR_PROF_MERGE, st);
         merge_warp_kernel<S><<<ceil_div(n_rows, wpb), wpb * 32, 0, st>>>(cs, cid, n_rows, n_cand, stride, k, id_add,
-                                                                        out_s, out_id, out_cnt);
+                                                                        out_s, out_id, out_cnt, row_list, row_count);
         EZR_LAUNCH_CHECK();
         return EZR_OK;
     }
@@ -553,8 +578,10 @@ static int merge_impl(const S* cs, const int32_t* cid, int n_rows, int n_cand, i
 template <typename S>
 static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t* q_terms, int n_queries,
                        int k, const int32_t* q_group, int id_base, int mode, void* out_scores, int32_t* out_ids,
-                       int32_t* thr_key, cudaStream_t st) {
+                       int32_t* thr_key, cudaStream_t st, const int32_t* q_list = nullptr,
+                       const int32_t* q_count = nullptr) {
     Bm25Params p;
+    p.q_list = q_list; p.q_count = q_count;
     p.indptr = ix->indptr; p.post_doc = ix->post_doc; p.post_w = ix->post_w; p.range_off = ix->range_off;
     p.doc_group = ix->doc_group; p.q_ptr = q_ptr; p.q_terms = q_terms; p.q_group = q_group;
     p.n_docs = ix->n_docs; p.vocab = ix->vocab; p.n_ranges = ix->n_ranges; p.k = k; p.id_base = id_base;
@@ -567,10 +594,88 @@ static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int
         EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[which] = true;
     }
-    dim3 grid(n_queries, (ix->n_ranges + kBmRpc - 1) / kBmRpc);
+    // with a query list the CTA columns loop over it (it is normally empty: keep the grid small)
+    dim3 grid(q_list ? (n_queries < 16 ? n_queries : 16) : n_queries, (ix->n_ranges + kBmRpc - 1) / kBmRpc);
     ProfScope prof(EZR_PROF_BM25_SCORE, st);
     kern<<<grid, kBmThreads, smem, st>>>(p);
     EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+
+// ---- two-phase path (bm25_pk.cuh) ----
+static bool pk_usable(const ezr_bm25_index* ix, int k) {
+    return kPkEnabled && ix->post_pk != nullptr && ix->monotone && ix->score_type == EZR_F64 && k <= 32;
+}
+
+struct PkWorkspace {
+    int32_t *thr_key, *thr_q, *cand_cnt, *ovf, *ovf_n, *ovf_list, *cand_ids, *cand_q;
+    size_t zero_bytes, total;
+};
+
+static PkWorkspace pk_carve(void* base, int n_queries) {
+    PkWorkspace w;
+    const size_t q = (size_t)n_queries;
+    char* b = reinterpret_cast<char*>(base);
+    w.thr_key = reinterpret_cast<int32_t*>(b);
+    w.thr_q = w.thr_key + q;
+    w.cand_cnt = w.thr_q + q;
+    w.ovf = w.cand_cnt + q;
+    w.ovf_n = w.ovf + q;
+    w.zero_bytes = (4 * q + 1) * 4;                     // everything up to here is zeroed per call
+    size_t off = align_up(w.zero_bytes, 256);
+    w.ovf_list = reinterpret_cast<int32_t*>(b + off);
+    off += align_up(q * 4, 256);
+    w.cand_ids = reinterpret_cast<int32_t*>(b + off);
+    off += align_up(q * kPkListCap * 4, 256);
+    w.cand_q = reinterpret_cast<int32_t*>(b + off);
+    off += align_up(q * kPkListCap * 4, 256);
+    w.total = off;
+    return w;
+}
+
+static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t* q_terms, int n_queries, int k,
+                     const int32_t* q_group, int id_base, const PkWorkspace& w, double* out_scores,
+                     int32_t* out_ids, int32_t* out_counts, cudaStream_t st) {
+    Bm25Params p;
+    p.indptr = ix->indptr; p.post_doc = ix->post_doc; p.post_w = ix->post_w; p.range_off = ix->range_off;
+    p.doc_group = ix->doc_group; p.q_ptr = q_ptr; p.q_terms = q_terms; p.q_group = q_group;
+    p.n_docs = ix->n_docs; p.vocab = ix->vocab; p.n_ranges = ix->n_ranges; p.k = k; p.id_base = id_base;
+    p.out_scores = nullptr; p.out_ids = nullptr; p.thr_key = nullptr; p.monotone = ix->monotone;
+    p.q_list = nullptr; p.q_count = nullptr;
+    PkParams c;
+    c.post_pk = ix->post_pk; c.thr_q = w.thr_q; c.cand_cnt = w.cand_cnt; c.cand_ids = w.cand_ids; c.cand_q = w.cand_q; c.ovf = w.ovf;
+    c.ovf_n = w.ovf_n; c.ovf_list = w.ovf_list;
+    const size_t smem = (size_t)kBmRange * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        EZR_CUDA(cudaFuncSetAttribute(bm25_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    // Document ranges go in chunks of doubling size (4, 4, 8, 16, ...); between chunks every query's bound is
+    // raised to the k-th best of all candidates so far, so the expected number of candidates a chunk adds stays
+    // around k however many ranges it spans.
+    {
+        ProfScope prof(EZR_PROF_BM25_CAND, st);
+        int r0 = 0, span = 4;
+        while (r0 < ix->n_ranges) {
+            int len = ix->n_ranges - r0 < span ? ix->n_ranges - r0 : span;
+            if (ix->n_ranges - (r0 + len) < span / 2) len = ix->n_ranges - r0;      // no tiny last chunk
+            bm25_cand_kernel<<<dim3(n_queries, len), kBmThreads, smem, st>>>(p, c, r0);
+            EZR_LAUNCH_CHECK();
+            r0 += len;
+            if (r0 < ix->n_ranges) {
+                bm25_bound_kernel<<<n_queries, kBdThreads, 0, st>>>(p, c);
+                EZR_LAUNCH_CHECK();
+            }
+            if (r0 > 4) span *= 2;
+        }
+    }
+    {
+        ProfScope prof(EZR_PROF_BM25_RESCORE, st);
+        bm25_rescore_kernel<<<n_queries, kRsThreads, 0, st>>>(p, c, out_scores, out_ids, out_counts);
+        EZR_LAUNCH_CHECK();
+    }
     return EZR_OK;
 }
 
@@ -632,12 +737,51 @@ int ezr_bm25_range_index(const int64_t* indptr, const int32_t* post_doc, int32_t
     return EZR_OK;
 }
 
+int ezr_bm25_pack(const int32_t* post_doc, const double* post_w, int64_t n_postings, int32_t range_size,
+                  uint32_t* out_pk, int32_t* out_scale_log2, void* scratch16, void* stream) {
+    EZR_CHECK_ARG(kPkEnabled, "bm25_pack: this build's range size %d is not a power of two", kBmRange);
+    EZR_CHECK_ARG(range_size == kBmRange, "bm25_pack: range_size must be %d (got %d)", kBmRange, range_size);
+    EZR_CHECK_ARG(out_scale_log2 != nullptr && scratch16 != nullptr, "bm25_pack: NULL argument");
+    EZR_CHECK_ARG(n_postings >= 0 && n_postings < ((int64_t)1 << 31), "bm25_pack: n_postings out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    *out_scale_log2 = 0;
+    if (n_postings == 0) return EZR_OK;
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(scratch16);
+    EZR_CUDA(cudaMemsetAsync(d, 0, 16, st));
+    bm25_wmax_kernel<<<sm_count() * 8, 256, 0, st>>>(post_w, n_postings, d);
+    EZR_LAUNCH_CHECK();
+    unsigned long long h[2];
+    EZR_CUDA(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, st));
+    EZR_CUDA(cudaStreamSynchronize(st));
+    if (h[1] != 0ull) {
+        set_error("bm25_pack: negative or non-finite contribution; the two-phase path needs non-negative weights");
+        return EZR_ERR_INVALID;
+    }
+    double wmax;
+    memcpy(&wmax, &h[0], 8);
+    int e = 0;
+    if (wmax > 0.0) {
+        int ex;
+        frexp(wmax, &ex);                       // wmax < 2^ex
+        e = kPkWBits - 1 - ex;                  // wmax * 2^e < 2^(WBits-1): ceil() fits, sums of 2^(31-WBits) terms too
+    }
+    const double scale = ldexp(1.0, e);
+    bm25_pack_kernel<<<(unsigned)((n_postings + 255) / 256), 256, 0, st>>>(post_doc, post_w, n_postings, scale, out_pk);
+    EZR_LAUNCH_CHECK();
+    *out_scale_log2 = e;
+    return EZR_OK;
+}
+
+int ezr_bm25_cand_capacity(void) { return kPkEnabled ? kPkListCap : 0; }
+
 size_t ezr_bm25_topk_workspace(const ezr_bm25_index* ix, int32_t n_queries, int32_t k) {
     if (!ix || n_queries <= 0 || k <= 0) return 0;
     const size_t ss = ix->score_type == EZR_F64 ? 8 : 4;
     if (k <= 32) {
         const size_t n = (size_t)n_queries * ix->n_ranges * k;
-        return align_up(n * ss, 256) + align_up(n * 4, 256) + align_up((size_t)n_queries * 4, 256);
+        const size_t lists = align_up(n * ss, 256) + align_up(n * 4, 256);
+        if (pk_usable(ix, k)) return lists + pk_carve(nullptr, n_queries).total;
+        return lists + align_up((size_t)n_queries * 4, 256);
     }
     // score rows, one query block at a time is the caller's job: here all rows at once
     size_t rows = align_up((size_t)n_queries * ix->n_docs * ss, 256);
@@ -672,6 +816,21 @@ int ezr_bm25_topk(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32_t*
         void* ps = workspace;
         int32_t* pi = reinterpret_cast<int32_t*>((char*)workspace + align_up(n * ss, 256));
         int32_t* thr = reinterpret_cast<int32_t*>((char*)workspace + align_up(n * ss, 256) + align_up(n * 4, 256));
+        if (pk_usable(ix, k)) {
+            // candidates from packed postings -> exact rescoring; overflowed queries (normally none) go through
+            // the ordered kernel below, restricted to ovf_list
+            const PkWorkspace w = pk_carve(thr, n_queries);
+            EZR_CUDA(cudaMemsetAsync(thr, 0, w.zero_bytes, st));
+            rc = pk_launch(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, w, (double*)out_scores, out_ids,
+                           out_counts, st);
+            if (rc) return rc;
+            rc = bm25_launch<double>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, w.thr_key, st,
+                                     w.ovf_list, w.ovf_n);
+            if (rc) return rc;
+            const int n_cand = ix->n_ranges * k;
+            return merge_impl<double>((const double*)ps, pi, n_queries, n_cand, n_cand, k, id_base,
+                                      (double*)out_scores, out_ids, out_counts, st, w.ovf_list, w.ovf_n);
+        }
         EZR_CUDA(cudaMemsetAsync(thr, 0, (size_t)n_queries * 4, st));
         rc = f64 ? bm25_launch<double>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, thr, st)
                  : bm25_launch<float>(ix, q_ptr, q_terms, n_queries, k, q_group, id_base, 0, ps, pi, thr, st);

@@ -1,0 +1,392 @@
+// Two-phase BM25 top-k (float64 Okapi indices with non-negative weights): included by bm25.cu.
+//
+// The ordered float64 accumulation of bm25_score_kernel pays one block barrier per query term to reproduce the
+// reference's sum order (retrievers.py:128-151 -> rank_bm25 get_scores adds term by term) for EVERY document,
+// although only the few documents near the top-k boundary need their exact score.  Here:
+//
+//   phase 1  bm25_cand_kernel      integer upper-bound scores from 4-byte packed postings
+//                                  (doc-in-range | ceil(w * 2^e)), shared-memory integer atomics, NO ordering and
+//                                  no per-term barrier; documents that may reach the top-k are appended to a
+//                                  per-query candidate list.
+//   phase 2  bm25_rescore_kernel   every candidate's exact float64 score, terms added strictly in token order
+//                                  (binary search of the candidate in each term's posting segment), then the
+//                                  canonical top-k of the candidates.
+//
+// Why the candidate set is a superset of the exact top-k.  For a document d and a query of m tokens let
+//   s(d)  = the reference's float64 score (sequentially rounded sum of the stored contributions w_j),
+//   Q(d)  = sum_j ceil(w_j * S) (S = 2^e, the multiplication is exact), the integer phase 1 accumulates.
+// The real sum R = sum w_j satisfies S*R <= Q <= S*R + m, and |s - R| <= m * 2^-53 * R, far below 1/S.  Hence
+//   Q(d) - m - 1  <=  S*s(d)  <=  Q(d) + 1.
+// If k distinct documents have Q >= G then the final k-th best score s* has S*s* >= B := G - m - 1, and a
+// document with Q(d) + 1 < B cannot reach the top-k.  Phase 1 keeps every document with Q(d) >= B - 1 where B is
+// the running bound of the query (raised with atomicMax as document ranges complete), phase 2 decides exactly.
+// Queries whose candidate list overflows (mass ties) are handed to bm25_score_kernel, so results never depend on
+// the capacity constants.
+#pragma once
+
+namespace ezr {
+
+constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
+constexpr bool kPkEnabled = (kBmRange & (kBmRange - 1)) == 0;
+constexpr int kPkDocBits = ilog2_c(kBmRange);
+constexpr int kPkWBits = 32 - kPkDocBits;                 // 20 bits of weight for 4096-document ranges
+constexpr uint32_t kPkWMask = (1u << kPkWBits) - 1u;
+constexpr int kPkMaxTerms = 1 << (31 - kPkWBits);         // packed weights are < 2^(WBits-1): sums stay below 2^30
+constexpr int kPkLocalCap = 512;                          // candidates one (query, range) CTA can hold
+#ifndef EZR_BM25_CAND_CAP
+#define EZR_BM25_CAND_CAP 1024
+#endif
+constexpr int kPkListCap = EZR_BM25_CAND_CAP;             // candidates per query (per shard)
+#ifndef EZR_BM25_PK_MINB
+#define EZR_BM25_PK_MINB 8
+#endif
+
+struct PkParams {
+    const uint32_t* post_pk;   // [n_postings]
+    int32_t* thr_q;            // [Q] running bound B (integer domain), zeroed per call
+    int32_t* cand_cnt;         // [Q] zeroed per call
+    int32_t* cand_ids;         // [Q][kPkListCap] shard-local document ids
+    int32_t* cand_q;           // [Q][kPkListCap] their integer scores Q(d)
+    int32_t* ovf;              // [Q] zeroed per call: 1 = hand the query to the ordered kernel
+    int32_t* ovf_n;            // [1] zeroed per call
+    int32_t* ovf_list;         // [Q]
+};
+
+// ---- index build: largest weight (as bits; non-negative doubles order like their bit patterns) + validity ----
+__global__ void bm25_wmax_kernel(const double* __restrict__ w, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long mx = 0ull;
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = w[i];
+        if (!(v >= 0.0) || isinf(v)) bad = 1;
+        else mx = max(mx, (unsigned long long)__double_as_longlong(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, mx);
+        if (bad) atomicMax(out + 1, 1ull);
+    }
+}
+
+__global__ void bm25_pack_kernel(const int32_t* __restrict__ post_doc, const double* __restrict__ w, int64_t n,
+                                 double scale, uint32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = ceil(__dmul_rn(w[i], scale));       // exact product (power of two), exact ceil
+    out[i] = ((uint32_t)(post_doc[i] & (kBmRange - 1)) << kPkWBits) | (uint32_t)x;
+}
+
+// ---- phase 1 ----
+// One CTA per (query, document range).  Work is dealt to warps in 32-posting chunks over ALL terms of the query
+// (a warp's lanes each hold one term's segment; ballot + shuffles map a chunk number to its term), so a warp only
+// executes code for chunks that exist: no per-term pass over empty segments, no ordering, one barrier before the
+// atomics and one after.
+constexpr int kPkWarps = kBmThreads / 32;
+constexpr int kPkUnroll = 4;                             // chunks a warp keeps in flight
+
+__global__ void __launch_bounds__(kBmThreads, EZR_BM25_PK_MINB)
+bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
+    extern __shared__ __align__(16) unsigned char pk_smem_raw[];
+    uint32_t* acc = reinterpret_cast<uint32_t*>(pk_smem_raw);   // [kBmRange] integer upper-bound scores
+    __shared__ int s_wi[kPkLocalCap];
+    __shared__ int s_cnt, s_b, s_thr;
+
+    const int q = blockIdx.x, r = r_begin + blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qs = p.q_ptr[q];
+    const int m = p.q_ptr[q + 1] - qs;
+    if (m > kPkMaxTerms) {                               // block-uniform: the integer sums could wrap
+        if (tid == 0) c.ovf[q] = 1;
+        return;
+    }
+    const int rbase = r * kBmRange;
+    const uint32_t* __restrict__ pk = c.post_pk;
+    const int want = p.q_group ? p.q_group[q] : -1;
+    if (tid == kBmThreads - 1) {
+        s_b = *reinterpret_cast<const volatile int32_t*>(c.thr_q + q);
+        s_cnt = 0;
+    }
+    // lane j of every warp: posting segment of token tb + j in this range
+    auto load_seg = [&](int tb, int& beg, int& len) {
+        beg = 0; len = 0;
+        if (tb + lane < m) {
+            const int t = p.q_terms[qs + tb + lane];
+            if (t >= 0 && t < p.vocab) {
+                const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
+                const uint32_t o0 = __ldg(ro), o1 = __ldg(ro + 1);
+                beg = (int)__ldg(p.indptr + t) + (int)o0;
+                len = (int)(o1 - o0);
+            }
+        }
+    };
+    int beg, len;
+    load_seg(0, beg, len);
+    {
+        uint4* a4 = reinterpret_cast<uint4*>(acc);
+#pragma unroll
+        for (int i = 0; i < kBmRange / 4 / kBmThreads; ++i) a4[tid + i * kBmThreads] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+
+    const int bound = s_b;                               // B: lower bound of S * (k-th best exact score), 0 = none yet
+    const bool track = bound > 0;
+    const uint32_t tq = (uint32_t)max(bound - 1, 1);
+    auto apply = [&](uint32_t x) {
+        if (x == 0u) return;                             // no posting (or a zero contribution)
+        const uint32_t dl = x >> kPkWBits, wq = x & kPkWMask;
+        const uint32_t old = atomicAdd(&acc[dl], wq);
+        if (track && old < tq && old + wq >= tq) {       // weights are non-negative: a document crosses once
+            if (want == -1 || p.doc_group[rbase + (int)dl] == want) {
+                const int idx = atomicAdd(&s_cnt, 1);
+                if (idx < kPkLocalCap) s_wi[idx] = (int)dl;
+            }
+        }
+    };
+    for (int tb = 0; tb < m; tb += 32) {
+        if (tb > 0) load_seg(tb, beg, len);
+        // exclusive prefix of chunk counts over the 32 tokens of this batch
+        const int nch = (len + 31) >> 5;
+        int inc = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int pre = inc - nch;
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        for (int g0 = warp; g0 < total; g0 += kPkWarps * kPkUnroll) {
+            uint32_t x[kPkUnroll];
+#pragma unroll
+            for (int u = 0; u < kPkUnroll; ++u) {
+                const int g = g0 + u * kPkWarps;
+                x[u] = 0u;
+                if (g < total) {                         // warp-uniform
+                    // token whose chunk range contains g: the last lane with pre <= g (empty tokens share a prefix
+                    // with their successor and are skipped by taking the last one)
+                    const unsigned mask = __ballot_sync(0xffffffffu, pre <= g);
+                    const int j = 31 - __clz(mask);
+                    const int jb = __shfl_sync(0xffffffffu, beg, j);
+                    const int jl = __shfl_sync(0xffffffffu, len, j);
+                    const int jp = __shfl_sync(0xffffffffu, pre, j);
+                    const int o = ((g - jp) << 5) + lane;
+                    if (o < jl) x[u] = __ldg(pk + jb + o);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kPkUnroll; ++u) apply(x[u]);
+        }
+    }
+    __syncthreads();                                     // every contribution of this (query, range) is in acc
+
+    const int slack = m + 1;
+    if (!track) {
+        // No bound yet (first ranges of a query): k-th largest of 32 disjoint group maxima = G, then compact.
+        constexpr int kPer = kBmRange / kBmThreads;
+        uint32_t tmax = 0u;
+        if (want == -1) {
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) tmax = max(tmax, acc[tid + i * kBmThreads]);
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < kPer; ++i) {
+                const int doc = tid + i * kBmThreads;
+                const uint32_t v = acc[doc];
+                if (v > tmax && p.doc_group[rbase + doc] == want) tmax = v;
+            }
+        }
+        uint32_t gmax = tmax;
+#pragma unroll
+        for (int o = kBmGroup / 2; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        if ((lane & (kBmGroup - 1)) == 0) s_wi[tid / kBmGroup] = (int)gmax;
+        if (tid == 0) s_thr = 0;
+        __syncthreads();
+        if (warp == 0) {
+            const int mine = s_wi[lane];
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int o = s_wi[j];
+                rank += (o > mine || (o == mine && j < lane)) ? 1 : 0;
+            }
+            if (rank == p.k - 1) s_thr = mine;           // 0 when fewer than k groups hold a positive score
+        }
+        __syncthreads();
+        const int g = s_thr;
+        const int bl = g > 0 ? g - slack : 0;            // B from this range alone
+        const uint32_t tl = (uint32_t)max(bl - 1, 1);
+        __syncthreads();                                 // s_wi is reused as the candidate list
+        if (tmax >= tl) {
+#pragma unroll 4
+            for (int i = 0; i < kPer; ++i) {
+                const int doc = tid + i * kBmThreads;
+                if (acc[doc] >= tl && (want == -1 || p.doc_group[rbase + doc] == want)) {
+                    const int idx = atomicAdd(&s_cnt, 1);
+                    if (idx < kPkLocalCap) s_wi[idx] = doc;
+                }
+            }
+        }
+        if (tid == 0 && bl > 0) atomicMax(c.thr_q + q, bl);
+        __syncthreads();
+    }
+    const int n = s_cnt;
+    if (n == 0) return;
+    if (n > kPkLocalCap) {
+        if (tid == 0) c.ovf[q] = 1;
+        return;
+    }
+    for (int i = tid; i < n; i += kBmThreads) {
+        const int dl = s_wi[i];
+        const uint32_t mine = acc[dl];
+        const int slot = atomicAdd(c.cand_cnt + q, 1);
+        if (slot < kPkListCap) {
+            c.cand_ids[(int64_t)q * kPkListCap + slot] = rbase + dl;
+            c.cand_q[(int64_t)q * kPkListCap + slot] = (int)mine;
+        } else {
+            c.ovf[q] = 1;
+        }
+        if (track && n >= p.k) {                         // this range alone holds k documents above the bound
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const uint32_t o = acc[s_wi[j]];
+                rank += (o > mine || (o == mine && j < i)) ? 1 : 0;
+            }
+            if (rank == p.k - 1 && (int)mine - slack > bound) atomicMax(c.thr_q + q, (int)mine - slack);
+        }
+    }
+}
+
+// ---- between range chunks: raise every query's bound to the k-th best of ALL candidates so far, drop the rest ----
+// (a single range only knows its own k-th best; the bound that keeps later ranges quiet is the running global one)
+constexpr int kBdThreads = 128;
+
+__global__ void __launch_bounds__(kBdThreads)
+bm25_bound_kernel(const Bm25Params p, const PkParams c) {
+    __shared__ int s_q[kPkListCap];
+    __shared__ int s_id[kPkListCap];
+    __shared__ int s_kth, s_n2;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int n = c.cand_cnt[q];
+    if (c.ovf[q] != 0 || n < p.k) return;                // block-uniform
+    if (n > kPkListCap) {
+        if (tid == 0) c.ovf[q] = 1;
+        return;
+    }
+    for (int i = tid; i < n; i += kBdThreads) {
+        s_q[i] = c.cand_q[(int64_t)q * kPkListCap + i];
+        s_id[i] = c.cand_ids[(int64_t)q * kPkListCap + i];
+    }
+    if (tid == 0) s_n2 = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kBdThreads) {
+        const int mine = s_q[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const int o = s_q[j];
+            rank += (o > mine || (o == mine && j < i)) ? 1 : 0;
+        }
+        if (rank == p.k - 1) s_kth = mine;               // ranks are a permutation: exactly one writer
+    }
+    __syncthreads();
+    const int m = p.q_ptr[q + 1] - p.q_ptr[q];
+    const int b = max(s_kth - (m + 1), c.thr_q[q]);
+    for (int i = tid; i < n; i += kBdThreads) {
+        if (s_q[i] >= b - 1) {
+            const int pos = atomicAdd(&s_n2, 1);
+            c.cand_q[(int64_t)q * kPkListCap + pos] = s_q[i];
+            c.cand_ids[(int64_t)q * kPkListCap + pos] = s_id[i];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        c.thr_q[q] = b;
+        c.cand_cnt[q] = s_n2;
+    }
+}
+
+// ---- phase 2: exact scores of the candidates in token order, canonical top-k ----
+constexpr int kRsThreads = 128;
+constexpr int kRsTok = 64;     // tokens whose (term, base) are staged in shared memory
+
+__global__ void __launch_bounds__(kRsThreads)
+bm25_rescore_kernel(const Bm25Params p, const PkParams c, double* __restrict__ out_scores,
+                    int32_t* __restrict__ out_ids, int32_t* __restrict__ out_counts) {
+    __shared__ double s_sc[kPkListCap];
+    __shared__ int s_id[kPkListCap];
+    __shared__ int s_t[kRsTok];
+    __shared__ int s_base[kRsTok];
+    __shared__ int s_pos;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = c.cand_cnt[q];
+    if (c.ovf[q] != 0 || n > kPkListCap) {               // block-uniform
+        if (tid == 0) c.ovf_list[atomicAdd(c.ovf_n, 1)] = q;
+        return;
+    }
+    const int qs = p.q_ptr[q];
+    const int m = p.q_ptr[q + 1] - qs;
+    if (tid == 0) s_pos = 0;
+    for (int j = tid; j < min(m, kRsTok); j += kRsThreads) {
+        const int t = p.q_terms[qs + j];
+        const bool ok = t >= 0 && t < p.vocab;
+        s_t[j] = ok ? t : -1;
+        s_base[j] = ok ? (int)p.indptr[t] : 0;
+    }
+    __syncthreads();
+    const double* __restrict__ post_w = reinterpret_cast<const double*>(p.post_w);
+    for (int ci = warp; ci < n; ci += kRsThreads / 32) {
+        const int doc = c.cand_ids[(int64_t)q * kPkListCap + ci];
+        const int r = doc / kBmRange;
+        double s = 0.0;
+        for (int c0 = 0; c0 < m; c0 += 32) {
+            const int j = c0 + lane;
+            double wv = 0.0;
+            if (j < m) {
+                int t, base;
+                if (j < kRsTok) { t = s_t[j]; base = s_base[j]; }
+                else {
+                    t = p.q_terms[qs + j];
+                    if (t < 0 || t >= p.vocab) t = -1;
+                    base = t >= 0 ? (int)p.indptr[t] : 0;
+                }
+                if (t >= 0) {
+                    const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
+                    int lo = base + (int)ro[0], hi = base + (int)ro[1];
+                    while (lo < hi) {                    // lower_bound of doc in the term's postings of range r
+                        const int mid = (lo + hi) >> 1;
+                        if (__ldg(p.post_doc + mid) < doc) lo = mid + 1; else hi = mid;
+                    }
+                    if (lo < base + (int)ro[1] && __ldg(p.post_doc + lo) == doc) wv = __ldg(post_w + lo);
+                }
+            }
+            const int cnt = min(32, m - c0);
+            for (int jj = 0; jj < cnt; ++jj) s = __dadd_rn(s, __shfl_sync(0xffffffffu, wv, jj));   // token order
+        }
+        if (lane == 0) { s_sc[ci] = s; s_id[ci] = doc; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kRsThreads) {
+        const double ms = s_sc[i];
+        const int mi = s_id[i];
+        if (ms > 0.0) {                                  // retrievers.py:195-196: only positive scores qualify
+            atomicAdd(&s_pos, 1);
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += better<double>(s_sc[j], s_id[j], ms, mi) ? 1 : 0;
+            if (rank < p.k) {
+                out_scores[(int64_t)q * p.k + rank] = ms;
+                out_ids[(int64_t)q * p.k + rank] = mi + p.id_base;
+            }
+        }
+    }
+    __syncthreads();
+    const int have = min(s_pos, p.k);
+    for (int i = have + tid; i < p.k; i += kRsThreads) {
+        out_scores[(int64_t)q * p.k + i] = ScoreTraits<double>::lowest();
+        out_ids[(int64_t)q * p.k + i] = -1;
+    }
+    if (tid == 0) out_counts[q] = have;
+}
+
+}  // namespace ezr

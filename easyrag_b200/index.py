@@ -129,8 +129,10 @@ class Bm25Index:
     """
 
     def __init__(self, stats: Bm25Stats, device=None, doc_lo: int = 0, doc_hi: Optional[int] = None,
-                 doc_group: Optional[torch.Tensor] = None, k1: float = K1, b: float = B):
+                 doc_group: Optional[torch.Tensor] = None, k1: float = K1, b: float = B,
+                 packed: Optional[bool] = None):
         _lib.require_cuda()
+        self._packed_opt = packed
         L = _lib.lib()
         device = torch.device(device if device is not None else "cuda")
         doc_hi = stats.n_docs if doc_hi is None else doc_hi
@@ -178,9 +180,32 @@ class Bm25Index:
                 self.doc_group = doc_group[doc_lo:doc_hi].to(device=device, dtype=torch.int32).contiguous()
             # rank_bm25 replaces negative idf by epsilon * average_idf, which is negative only when the mean idf is
             self.monotone = bool((stats.idf >= 0).all())
+            self._build_packed()
             torch.cuda.current_stream().synchronize()
         self._struct = None
         self.refresh_struct()
+
+    def _build_packed(self):
+        """4-byte packed postings for the candidate pass of ``ezr_bm25_topk`` (derived data, never stored on disk).
+
+        Only float64 indices with non-negative contributions qualify; ``EASYRAG_B200_BM25_PACKED=0`` keeps the
+        ordered single-pass kernel (A/B measurements)."""
+        self.post_pk, self.pk_scale_log2 = None, 0
+        want = getattr(self, "_packed_opt", None)
+        if want is None:
+            want = os.environ.get("EASYRAG_B200_BM25_PACKED", "1") != "0"
+        if (not want or self.score_type != _lib.F64 or not self.monotone or self.n_postings == 0
+                or _lib.lib().ezr_bm25_cand_capacity() == 0):
+            return
+        import ctypes
+        with torch.cuda.device(self.device):
+            pk = torch.empty(self.n_postings, dtype=torch.int32, device=self.device)
+            scratch = torch.empty(2, dtype=torch.int64, device=self.device)
+            e = ctypes.c_int32(0)
+            _lib.check(_lib.lib().ezr_bm25_pack(_lib.ptr(self.post_doc), _lib.ptr(self.post_w), self.n_postings,
+                                                _lib.BM25_RANGE, _lib.ptr(pk), ctypes.byref(e), _lib.ptr(scratch),
+                                                _lib.stream_ptr()), "ezr_bm25_pack")
+        self.post_pk, self.pk_scale_log2 = pk, int(e.value)
 
     def refresh_struct(self):
         s = _lib.Bm25IndexStruct()
@@ -192,6 +217,8 @@ class Bm25Index:
         s.range_off = self.range_off.data_ptr()
         s.doc_group = self.doc_group.data_ptr() if self.doc_group is not None else None
         s.monotone = int(self.monotone)
+        s.pk_scale_log2 = int(self.pk_scale_log2)
+        s.post_pk = self.post_pk.data_ptr() if self.post_pk is not None else None
         self._struct = s
 
     def set_doc_group(self, doc_group: Optional[torch.Tensor]):
@@ -205,7 +232,8 @@ class Bm25Index:
 
     def index_bytes(self) -> int:
         return (self.post_doc.numel() * 4 + self.post_w.numel() * self.post_w.element_size()
-                + self.range_off.numel() * 4 + self.indptr.numel() * 8)
+                + self.range_off.numel() * 4 + self.indptr.numel() * 8
+                + (self.post_pk.numel() * 4 if self.post_pk is not None else 0))
 
     # ---- on-disk format (the reference rebuilds the BM25 index in RAM on every start,
     # retrievers.py:98-118).  A directory of .npy arrays + meta.json; loading needs no tokenisation and no log().
@@ -218,12 +246,13 @@ class Bm25Index:
                                 range_size=_lib.BM25_RANGE, monotone=bool(self.monotone)), arrays)
 
     @classmethod
-    def load(cls, path: str, device=None) -> "Bm25Index":
+    def load(cls, path: str, device=None, packed: Optional[bool] = None) -> "Bm25Index":
         _lib.require_cuda()
         meta, get = _load_arrays(path)
         if meta["kind"] != "bm25" or meta["range_size"] != _lib.BM25_RANGE:
             raise ValueError(f"{path}: not a BM25 index of this build")
         self = cls.__new__(cls)
+        self._packed_opt = packed
         device = torch.device(device if device is not None else "cuda")
         self.stats = None
         self.device = device
@@ -237,6 +266,7 @@ class Bm25Index:
         self.n_postings = int(self.post_doc.numel())
         self.monotone = bool(meta.get("monotone", False))
         self.doc_group = get("doc_group").to(device) if os.path.exists(os.path.join(path, "doc_group.npy")) else None
+        self._build_packed()
         self._struct = None
         self.refresh_struct()
         return self

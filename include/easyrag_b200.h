@@ -72,7 +72,9 @@ typedef struct ezr_bm25_index {
     const uint32_t* range_off; /* [vocab*(n_ranges+1)] */
     const int32_t* doc_group;  /* [n_docs] metadata class of each document, or NULL */
     int32_t monotone;          /* 1 if every post_w >= 0 (no negative idf): enables crossing-based selection */
-    int32_t reserved;
+    int32_t pk_scale_log2;     /* e of ezr_bm25_pack (informational) */
+    const uint32_t* post_pk;   /* [n_postings] packed postings from ezr_bm25_pack, or NULL: enables the two-phase
+                                  top-k (integer candidate pass + exact float64 rescoring) for F64 / monotone / k<=32 */
 } ezr_bm25_index;
 
 /* documents per range the library was built for (the `range_size` an index must use) */
@@ -89,6 +91,18 @@ int ezr_bm25_weights(const int64_t* indptr, const int32_t* post_doc, const int32
 
 int ezr_bm25_range_index(const int64_t* indptr, const int32_t* post_doc, int32_t vocab, int32_t range_size,
                          int32_t n_ranges, uint32_t* out_range_off, void* stream);
+
+/* Packed postings for the candidate pass of ezr_bm25_topk: out_pk[p] = (post_doc[p] mod range_size) << W |
+ * ceil(post_w[p] * 2^e), W = 32 - log2(range_size), e chosen from the largest weight so that every field fits
+ * (returned in *out_scale_log2).  Rounding up makes the integer sums upper bounds of the float64 scores; the
+ * exact scores of the surviving candidates are recomputed from post_w in token order, so results stay
+ * bit-identical to rank_bm25 (retrievers.py:128-151).  Needs non-negative finite weights (else EZR_ERR_INVALID).
+ * scratch16: 16 bytes of device memory.  Synchronises the stream (index-build time). */
+int ezr_bm25_pack(const int32_t* post_doc, const double* post_w, int64_t n_postings, int32_t range_size,
+                  uint32_t* out_pk, int32_t* out_scale_log2, void* scratch16, void* stream);
+
+/* candidates per query the two-phase path can hold before it hands a query to the ordered kernel (0: not built) */
+int ezr_bm25_cand_capacity(void);
 
 /* BM25Retriever.get_scores + .filter for a batch of queries (retrievers.py:128-151,191-210):
  * query i has terms q_terms[q_ptr[i] .. q_ptr[i+1]) in token order (duplicates repeat, <0 or >=vocab = unknown).
@@ -206,7 +220,9 @@ typedef enum ezr_prof_slot {
     EZR_PROF_ENC_GEMM = 5,   /* encoder GEMMs */
     EZR_PROF_ENC_ATTN = 6,   /* encoder attention */
     EZR_PROF_ENC_OTHER = 7,  /* encoder norms / elementwise */
-    EZR_PROF_COUNT = 8
+    EZR_PROF_BM25_CAND = 8,  /* bm25_cand_kernel (integer candidate pass over packed postings) */
+    EZR_PROF_BM25_RESCORE = 9, /* bm25_rescore_kernel (exact float64 rescoring + top-k of the candidates) */
+    EZR_PROF_COUNT = 10
 } ezr_prof_slot;
 int ezr_profile_enable(int32_t on);
 int ezr_profile_reset(void);

@@ -166,6 +166,90 @@ def test_bm25_massive_ties_take_overflow_path():
         _check_bm25_topk(batched.bm25_topk(ix, qp, qt, k), rows, k)
 
 
+
+# ---- two-phase path (packed postings -> integer candidates -> exact rescoring) vs the ordered kernel ----
+def test_bm25_pack_matches_definition(c1):
+    ix = c1["index"]
+    assert ix.post_pk is not None, "float64 Okapi index with non-negative idf must carry packed postings"
+    R = _lib.BM25_RANGE
+    wbits = 32 - int(np.log2(R))
+    w = ix.post_w.cpu().numpy()
+    d = ix.post_doc.cpu().numpy()
+    pk = ix.post_pk.cpu().numpy().view(np.uint32)
+    e = ix.pk_scale_log2
+    wq = np.ceil(np.ldexp(w, e)).astype(np.uint64)
+    assert wq.max() < (1 << (wbits - 1))
+    assert (wq[w > 0] >= 1).all()
+    assert np.array_equal(pk >> wbits, (d % R).astype(np.uint32))
+    assert np.array_equal(pk & ((1 << wbits) - 1), wq.astype(np.uint32))
+
+
+def _topk_bytes(res):
+    return res.ids.cpu().numpy().tobytes(), res.scores.cpu().numpy().tobytes(), res.counts.cpu().numpy().tobytes()
+
+
+def test_bm25_two_phase_equals_ordered_kernel_and_oracle():
+    corpus = synth.make_sparse_corpus(30_000, 4000, 4242, mean_len=50, min_len=0, max_len=200)
+    stats = Bm25Stats.from_tokens(corpus.tokens, corpus.doc_ptr, corpus.vocab, bm25_type=0)
+    groups = synth.make_groups(corpus.n_docs, 5, 9)
+    a = Bm25Index(stats, device=DEV, doc_group=groups, packed=True)
+    b = Bm25Index(stats, device=DEV, doc_group=groups, packed=False)
+    assert a.post_pk is not None and b.post_pk is None
+    o = obm.OkapiCSR(corpus.doc_lists(), corpus.vocab)
+    qs = synth.make_queries(corpus, 200, 4243)
+    lists = [[int(t) for t in terms] for terms in qs.term_lists()]
+    present = np.nonzero(o.df)[0]
+    rng = np.random.default_rng(5)
+    lists += [[int(t) for t in rng.choice(present, 40)],          # > kBmMaxT tokens: chunked accumulation
+              [int(t) for t in rng.choice(present, 100)],         # > 64 tokens: rescoring reads tokens from global
+              [int(present[0])] * 7 + [int(present[1])],          # duplicated tokens
+              [], [-1, corpus.vocab + 3]]
+    ptr = torch.tensor(np.cumsum([0] + [len(l) for l in lists]), dtype=torch.int32)
+    terms = torch.tensor([t for l in lists for t in l], dtype=torch.int32)
+    rows = [o.get_scores(l) for l in lists]
+    _lib.lib().ezr_profile_enable(1)
+    for k in (1, 10, 32):
+        _lib.lib().ezr_profile_reset()
+        ra = batched.bm25_topk(a, ptr, terms, k, id_base=1000)
+        torch.cuda.synchronize()
+        assert _lib.profile_read("bm25_cand")[1] == 1 and _lib.profile_read("bm25_rescore")[1] == 1
+        rb = batched.bm25_topk(b, ptr, terms, k, id_base=1000)
+        assert _topk_bytes(ra) == _topk_bytes(rb)
+        _check_bm25_topk(ra, rows, k, id_base=1000)
+    _lib.lib().ezr_profile_enable(0)
+    g = groups.numpy()
+    want = np.array([i % 7 - 1 for i in range(len(lists))], dtype=np.int32)      # 5 = no such class
+    allowed = [None if w == -1 else (g == w) for w in want]
+    ra = batched.bm25_topk(a, ptr, terms, 10, q_group=torch.from_numpy(want))
+    rb = batched.bm25_topk(b, ptr, terms, 10, q_group=torch.from_numpy(want))
+    assert _topk_bytes(ra) == _topk_bytes(rb)
+    _check_bm25_topk(ra, rows, 10, allowed=allowed)
+
+
+def test_bm25_two_phase_hands_overflow_and_huge_queries_to_ordered_kernel():
+    # half of the corpus is one repeated document (mass ties overflow the candidate list), the rest is random;
+    # a batch mixes tie queries, ordinary queries and a query of > 2048 tokens (integer sums could wrap)
+    base = synth.make_sparse_corpus(10_000, 500, 31, mean_len=20, min_len=1, max_len=60)
+    rnd = base.doc_lists()
+    same = np.array([490, 491, 492, 493, 490], dtype=np.int32)
+    docs = [same if i % 2 else rnd[i // 2] for i in range(20_000)]
+    tokens = torch.from_numpy(np.concatenate(docs)).to(torch.int32)
+    ptr = torch.tensor(np.cumsum([0] + [len(d) for d in docs]), dtype=torch.int64)
+    o = obm.OkapiCSR(docs, 500)
+    stats = Bm25Stats.from_tokens(tokens, ptr, 500)
+    a = Bm25Index(stats, device=DEV, packed=True)
+    assert a.post_pk is not None
+    present = np.nonzero(o.df)[0]
+    rng = np.random.default_rng(6)
+    lists = [[490, 491], [int(t) for t in rng.choice(present, 6)], [493], [int(t) for t in rng.choice(present, 9)],
+             [int(t) for t in rng.choice(present, 2100)], [int(t) for t in rng.choice(present, 4)] + [492]]
+    qp = torch.tensor(np.cumsum([0] + [len(l) for l in lists]), dtype=torch.int32)
+    qt = torch.tensor([t for l in lists for t in l], dtype=torch.int32)
+    rows = [o.get_scores(l) for l in lists]
+    for k in (1, 10, 32):
+        _check_bm25_topk(batched.bm25_topk(a, qp, qt, k), rows, k)
+
+
 def test_bm25s_float32_bit_exact():
     corpus = synth.make_sparse_corpus(9000, 3000, 5, mean_len=60, min_len=1, max_len=200)
     qs = synth.make_queries(corpus, 40, 6)
