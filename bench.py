@@ -44,7 +44,7 @@ METRIC = "queries/sec dense+BM25+RRF top-10 over 1M x 768 chunks"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000)
@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=32, help="bounded sample for the CPU baseline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--dense-kernel", type=int, default=0, help="0 auto, 1 simt, 2 tcgen05 SS, 3 tcgen05 TS")
+    ap.add_argument("--overlap", type=int, default=0, help="1: dense and BM25 routes on two streams")
+    ap.add_argument("--dense-probe", type=int, default=0, help="measurement probe of the dense kernel (results invalid)")
+    ap.add_argument("--dense-stages", type=int, default=0, help="cap of the dense kernel's TMA ring (0 = all smem)")
     return ap.parse_args()
 
 
@@ -83,13 +86,20 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index = index
-        self.lines = []
+        self.lines = []          # (arrival time, csv line)
+        self.windows = []        # [t_begin, t_end] of the timed regions
         self.proc = None
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -97,7 +107,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -106,7 +116,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # nvidia-smi is started before the warm-up (its start-up takes longer than a short timed region); only
+        # samples that arrived while a timed region was running count (a line arrives a few ms after its sample)
+        inside = [ln for t, ln in self.lines if any(a <= t <= (b or t) + 0.03 for a, b in self.windows)]
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -216,6 +229,8 @@ def run_ours(args):
     _lib.require_cuda()
     L = _lib.lib()
     _lib.check(L.ezr_dense_set_kernel(args.dense_kernel))
+    _lib.check(L.ezr_dense_set_stage_cap(args.dense_stages))
+    _lib.check(L.ezr_dense_set_probe(args.dense_probe))
 
     data = make_data(args, dev)
     lo, hi = ezdist.shard_bounds(args.rows, world, rank, align=8192)
@@ -224,7 +239,7 @@ def run_ours(args):
     dense = DenseIndex(data["vec"][lo:hi], device=dev, row_lo=lo)
     torch.cuda.synchronize()
     build_s = time.time() - t0
-    ranker = batched.CoarseRanker(dense, sparse, canon=None, overlap=False)
+    ranker = batched.CoarseRanker(dense, sparse, canon=None, overlap=bool(args.overlap))
     sharded = ezdist.ShardedCoarseRanker(ranker) if world > 1 else None
     k = args.k
     q = data["queries"]
@@ -268,22 +283,26 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
     _lib.check(L.ezr_profile_reset())
     _lib.check(L.ezr_profile_enable(1))
+    sampler.begin()
     ms = timed(step_device, args.steps)
+    sampler.end()
     _lib.check(L.ezr_profile_enable(0))
     prof = {name: _lib.profile_read(name) for name in ("bm25_cand", "bm25_rescore", "bm25_score", "dense_tc",
                                                        "dense_simt", "merge", "fuse")}
-    clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
+    sampler.begin()
     ms_e2e = timed(step_e2e, args.steps)
+    sampler.end()
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:

@@ -61,6 +61,8 @@ SIGNATURES = {
     "ezr_dense_topk": (C.c_int, [_p, _i64, _i32, _i64, _p, _i32, _i64, _i32, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
     "ezr_dense_set_kernel": (C.c_int, [_i32]),
     "ezr_dense_last_kernel": (C.c_char_p, []),
+    "ezr_dense_set_stage_cap": (C.c_int, [_i32]),
+    "ezr_dense_set_probe": (C.c_int, [_i32]),
     "ezr_rrf_fuse": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "ezr_gemm_bf16": (C.c_int, [_p, _i32, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _i64, _i32, _p]),
     "ezr_attn_bidir": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _i32, C.c_float, _p, _i64, _p]),

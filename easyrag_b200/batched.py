@@ -228,11 +228,13 @@ class CoarseRanker:
         if self.overlap:
             self.s_dense.wait_stream(cur)
             self.s_sparse.wait_stream(cur)
+            # dense first: its persistent CTAs (one per SM) must be resident before the BM25 grid starts filling
+            # whatever shared memory / registers / issue slots they leave free
+            with torch.cuda.stream(self.s_dense):
+                dense_topk(self.dense, queries, k, q_group=q_group, ws=self.ws_dense, stream=self.s_dense, out=d_out)
             with torch.cuda.stream(self.s_sparse):
                 bm25_topk(self.sparse, q_ptr, q_terms, k, q_group=q_group, ws=self.ws_sparse, stream=self.s_sparse,
                           out=s_out)
-            with torch.cuda.stream(self.s_dense):
-                dense_topk(self.dense, queries, k, q_group=q_group, ws=self.ws_dense, stream=self.s_dense, out=d_out)
             cur.wait_stream(self.s_sparse)
             cur.wait_stream(self.s_dense)
         else:

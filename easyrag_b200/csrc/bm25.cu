@@ -69,19 +69,20 @@ __global__ void bm25_range_index_kernel(const int64_t* __restrict__ indptr, cons
 }
 
 // ---------------------------------------------------------------- scoring --
-// Launch shape, swept on B200 (profiles/README.md): (range, threads, CTAs/SM) = (4096, 256, 6) 19.6 ms,
-// (8192, 512, 3) 21.3 ms, (8192, 512, 2) 25.0 ms, (16384, 1024, 1) 29.3 ms, (4096, 512, 3) 31.4 ms per 10k queries.
-// The kernel is latency/barrier bound, so many small CTAs per SM win.
+// Launch shapes, swept on B200 (profiles/README.md).  The ordered kernel alone preferred (range, threads, CTAs/SM) =
+// (4096, 256, 6) at 19.6 ms per 10k queries over (8192, 512, 3) at 21.3 ms; since the two-phase path
+// (bm25_pk.cuh) took over the fused top-k, the range is chosen for ITS candidate pass, which is issue bound and
+// wants fewer, larger CTAs: (8192 docs, 256 threads, 6 CTAs/SM, 8 loads in flight) 6.9 ms vs (4096, 256, 8, 4) 7.9 ms.
 #ifndef EZR_BM25_RANGE
-#define EZR_BM25_RANGE 4096
+#define EZR_BM25_RANGE 8192
 #endif
 #ifndef EZR_BM25_THREADS
-#define EZR_BM25_THREADS 256
+#define EZR_BM25_THREADS 512
 #endif
 #ifndef EZR_BM25_MINB
-#define EZR_BM25_MINB 6
+#define EZR_BM25_MINB 3
 #endif
-constexpr int kBmRange = EZR_BM25_RANGE;     // documents per CTA (4096 -> 32 KB of float64 accumulators)
+constexpr int kBmRange = EZR_BM25_RANGE;     // documents per CTA (8192 -> 64 KB of float64 accumulators)
 constexpr int kBmThreads = EZR_BM25_THREADS;
 constexpr int kBmGroup = kBmThreads / 32;    // lanes per group: 32 group maxima bound the k-th score (k <= 32)
 static_assert(kBmGroup == 8 || kBmGroup == 16 || kBmGroup == 32, "BM25 CTA must have 256, 512 or 1024 threads");
@@ -646,10 +647,12 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
     PkParams c;
     c.post_pk = ix->post_pk; c.thr_q = w.thr_q; c.cand_cnt = w.cand_cnt; c.cand_ids = w.cand_ids; c.cand_q = w.cand_q; c.ovf = w.ovf;
     c.ovf_n = w.ovf_n; c.ovf_list = w.ovf_list;
-    const size_t smem = (size_t)kBmRange * 4;
+    const size_t smem = (size_t)(kBmRange + 32) * 4;
     static bool attr_done = false;
     if (!attr_done) {
         EZR_CUDA(cudaFuncSetAttribute(bm25_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EZR_CUDA(cudaFuncSetAttribute(bm25_cand_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     // Document ranges go in chunks of doubling size (4, 4, 8, 16, ...); between chunks every query's bound is
@@ -661,7 +664,7 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
         while (r0 < ix->n_ranges) {
             int len = ix->n_ranges - r0 < span ? ix->n_ranges - r0 : span;
             if (ix->n_ranges - (r0 + len) < span / 2) len = ix->n_ranges - r0;      // no tiny last chunk
-            bm25_cand_kernel<<<dim3(n_queries, len), kBmThreads, smem, st>>>(p, c, r0);
+            bm25_cand_kernel<<<dim3(n_queries, len), kPkThreads, smem, st>>>(p, c, r0);
             EZR_LAUNCH_CHECK();
             r0 += len;
             if (r0 < ix->n_ranges) {

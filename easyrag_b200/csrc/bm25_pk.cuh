@@ -29,7 +29,7 @@ namespace ezr {
 constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
 constexpr bool kPkEnabled = (kBmRange & (kBmRange - 1)) == 0;
 constexpr int kPkDocBits = ilog2_c(kBmRange);
-constexpr int kPkWBits = 32 - kPkDocBits;                 // 20 bits of weight for 4096-document ranges
+constexpr int kPkWBits = 32 - kPkDocBits;                 // 19 bits of weight for 8192-document ranges
 constexpr uint32_t kPkWMask = (1u << kPkWBits) - 1u;
 constexpr int kPkMaxTerms = 1 << (31 - kPkWBits);         // packed weights are < 2^(WBits-1): sums stay below 2^30
 constexpr int kPkLocalCap = 512;                          // candidates one (query, range) CTA can hold
@@ -38,8 +38,18 @@ constexpr int kPkLocalCap = 512;                          // candidates one (que
 #endif
 constexpr int kPkListCap = EZR_BM25_CAND_CAP;             // candidates per query (per shard)
 #ifndef EZR_BM25_PK_MINB
-#define EZR_BM25_PK_MINB 8
+#define EZR_BM25_PK_MINB 6
 #endif
+#ifndef EZR_BM25_PK_THREADS
+#define EZR_BM25_PK_THREADS 256
+#endif
+#ifndef EZR_BM25_PK_UNROLL
+#define EZR_BM25_PK_UNROLL 8
+#endif
+constexpr int kPkThreads = EZR_BM25_PK_THREADS;           // candidate-pass CTA (independent of the ordered kernel's)
+constexpr int kPkGroup = kPkThreads / 32;                 // lanes per group: 32 disjoint group maxima
+static_assert(kPkThreads % 32 == 0 && kPkThreads >= 64 && (kPkGroup & (kPkGroup - 1)) == 0, "bad EZR_BM25_PK_THREADS");
+static_assert(kBmRange % (4 * kPkThreads) == 0, "range must be a multiple of 4 * EZR_BM25_PK_THREADS");
 
 struct PkParams {
     const uint32_t* post_pk;   // [n_postings]
@@ -81,17 +91,18 @@ __global__ void bm25_pack_kernel(const int32_t* __restrict__ post_doc, const dou
 }
 
 // ---- phase 1 ----
-// One CTA per (query, document range).  Work is dealt to warps in 32-posting chunks over ALL terms of the query
-// (a warp's lanes each hold one term's segment; ballot + shuffles map a chunk number to its term), so a warp only
-// executes code for chunks that exist: no per-term pass over empty segments, no ordering, one barrier before the
+// One CTA per (query, document range).  Work is dealt to warps in 128-posting pieces over ALL terms of the query
+// (a warp's lanes each hold one term's segment; ballot + shuffles map a piece number to its term), so a warp only
+// executes code for pieces that exist: no per-term pass over empty segments, no ordering, one barrier before the
 // atomics and one after.
-constexpr int kPkWarps = kBmThreads / 32;
-constexpr int kPkUnroll = 4;                             // chunks a warp keeps in flight
+constexpr int kPkWarps = kPkThreads / 32;
+constexpr int kPkUnroll = EZR_BM25_PK_UNROLL;                             // loads a lane keeps in flight
+constexpr int kPkPiece = 32 * kPkUnroll;                 // postings per work item
 
-__global__ void __launch_bounds__(kBmThreads, EZR_BM25_PK_MINB)
+__global__ void __launch_bounds__(kPkThreads, EZR_BM25_PK_MINB)
 bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     extern __shared__ __align__(16) unsigned char pk_smem_raw[];
-    uint32_t* acc = reinterpret_cast<uint32_t*>(pk_smem_raw);   // [kBmRange] integer upper-bound scores
+    uint32_t* acc = reinterpret_cast<uint32_t*>(pk_smem_raw);   // [kBmRange + 32] integer upper-bound scores + spare
     __shared__ int s_wi[kPkLocalCap];
     __shared__ int s_cnt, s_b, s_thr;
 
@@ -106,7 +117,7 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     const int rbase = r * kBmRange;
     const uint32_t* __restrict__ pk = c.post_pk;
     const int want = p.q_group ? p.q_group[q] : -1;
-    if (tid == kBmThreads - 1) {
+    if (tid == kPkThreads - 1) {
         s_b = *reinterpret_cast<const volatile int32_t*>(c.thr_q + q);
         s_cnt = 0;
     }
@@ -128,28 +139,37 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     {
         uint4* a4 = reinterpret_cast<uint4*>(acc);
 #pragma unroll
-        for (int i = 0; i < kBmRange / 4 / kBmThreads; ++i) a4[tid + i * kBmThreads] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < kBmRange / 4 / kPkThreads; ++i) a4[tid + i * kPkThreads] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < 32) acc[kBmRange + tid] = 0u;         // spare slots of apply()
     }
     __syncthreads();
 
     const int bound = s_b;                               // B: lower bound of S * (k-th best exact score), 0 = none yet
     const bool track = bound > 0;
-    const uint32_t tq = (uint32_t)max(bound - 1, 1);
-    auto apply = [&](uint32_t x) {
-        if (x == 0u) return;                             // no posting (or a zero contribution)
-        const uint32_t dl = x >> kPkWBits, wq = x & kPkWMask;
+    // crossing test in one unsigned compare: old < tq <= old + wq  <=>  tq - 1 - old < wq  (wraps to a huge value
+    // when old >= tq; without a bound tq1 = 2^32-1: ~old is never below a packed weight)
+    const uint32_t tq1 = track ? (uint32_t)max(bound - 1, 1) - 1u : 0xffffffffu;
+    // Lanes without a posting add 0 to a private spare slot behind the accumulators (no branch around the atomic,
+    // no same-address serialisation); crossings are rare: the caller votes and only then takes the push path.
+    const uint32_t spare = (uint32_t)(kBmRange + lane);
+    auto apply = [&](uint32_t x) -> bool {
+        const uint32_t wq = x & kPkWMask;
+        const uint32_t dl = x != 0u ? (x >> kPkWBits) : spare;
         const uint32_t old = atomicAdd(&acc[dl], wq);
-        if (track && old < tq && old + wq >= tq) {       // weights are non-negative: a document crosses once
-            if (want == -1 || p.doc_group[rbase + (int)dl] == want) {
-                const int idx = atomicAdd(&s_cnt, 1);
-                if (idx < kPkLocalCap) s_wi[idx] = (int)dl;
-            }
+        return tq1 - old < wq;                           // weights are non-negative: a document crosses once
+    };
+    auto push = [&](uint32_t x) {
+        const uint32_t dl = x >> kPkWBits;
+        if (want == -1 || p.doc_group[rbase + (int)dl] == want) {
+            const int idx = atomicAdd(&s_cnt, 1);
+            if (idx < kPkLocalCap) s_wi[idx] = (int)dl;
         }
     };
     for (int tb = 0; tb < m; tb += 32) {
         if (tb > 0) load_seg(tb, beg, len);
-        // exclusive prefix of chunk counts over the 32 tokens of this batch
-        const int nch = (len + 31) >> 5;
+        // exclusive prefix of piece counts over the 32 tokens of this batch (a piece = kPkPiece postings of one
+        // token: kPkUnroll loads per lane in flight, the piece -> token mapping is paid once per piece)
+        const int nch = (len + kPkPiece - 1) / kPkPiece;
         int inc = nch;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -158,26 +178,26 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
         }
         const int pre = inc - nch;
         const int total = __shfl_sync(0xffffffffu, inc, 31);
-        for (int g0 = warp; g0 < total; g0 += kPkWarps * kPkUnroll) {
+        for (int g = warp; g < total; g += kPkWarps) {
+            // token whose piece range contains g: the last lane with pre <= g (empty tokens share a prefix with
+            // their successor and are skipped by taking the last one)
+            const unsigned mask = __ballot_sync(0xffffffffu, pre <= g);
+            const int j = 31 - __clz(mask);
+            const int jb = __shfl_sync(0xffffffffu, beg, j);
+            const int jl = __shfl_sync(0xffffffffu, len, j);
+            const int jp = __shfl_sync(0xffffffffu, pre, j);
+            const int o0 = (g - jp) * kPkPiece + lane;
+            const uint32_t* src = pk + jb + o0;
             uint32_t x[kPkUnroll];
 #pragma unroll
+            for (int u = 0; u < kPkUnroll; ++u) x[u] = (o0 + u * 32 < jl) ? __ldg(src + u * 32) : 0u;
+#pragma unroll
             for (int u = 0; u < kPkUnroll; ++u) {
-                const int g = g0 + u * kPkWarps;
-                x[u] = 0u;
-                if (g < total) {                         // warp-uniform
-                    // token whose chunk range contains g: the last lane with pre <= g (empty tokens share a prefix
-                    // with their successor and are skipped by taking the last one)
-                    const unsigned mask = __ballot_sync(0xffffffffu, pre <= g);
-                    const int j = 31 - __clz(mask);
-                    const int jb = __shfl_sync(0xffffffffu, beg, j);
-                    const int jl = __shfl_sync(0xffffffffu, len, j);
-                    const int jp = __shfl_sync(0xffffffffu, pre, j);
-                    const int o = ((g - jp) << 5) + lane;
-                    if (o < jl) x[u] = __ldg(pk + jb + o);
+                const bool crossed = apply(x[u]);
+                if (__any_sync(0xffffffffu, crossed)) {  // warp-uniform branch; almost never taken
+                    if (crossed) push(x[u]);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kPkUnroll; ++u) apply(x[u]);
         }
     }
     __syncthreads();                                     // every contribution of this (query, range) is in acc
@@ -185,23 +205,23 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     const int slack = m + 1;
     if (!track) {
         // No bound yet (first ranges of a query): k-th largest of 32 disjoint group maxima = G, then compact.
-        constexpr int kPer = kBmRange / kBmThreads;
+        constexpr int kPer = kBmRange / kPkThreads;
         uint32_t tmax = 0u;
         if (want == -1) {
 #pragma unroll
-            for (int i = 0; i < kPer; ++i) tmax = max(tmax, acc[tid + i * kBmThreads]);
+            for (int i = 0; i < kPer; ++i) tmax = max(tmax, acc[tid + i * kPkThreads]);
         } else {
 #pragma unroll 4
             for (int i = 0; i < kPer; ++i) {
-                const int doc = tid + i * kBmThreads;
+                const int doc = tid + i * kPkThreads;
                 const uint32_t v = acc[doc];
                 if (v > tmax && p.doc_group[rbase + doc] == want) tmax = v;
             }
         }
         uint32_t gmax = tmax;
 #pragma unroll
-        for (int o = kBmGroup / 2; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-        if ((lane & (kBmGroup - 1)) == 0) s_wi[tid / kBmGroup] = (int)gmax;
+        for (int o = kPkGroup / 2; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        if ((lane & (kPkGroup - 1)) == 0) s_wi[tid / kPkGroup] = (int)gmax;
         if (tid == 0) s_thr = 0;
         __syncthreads();
         if (warp == 0) {
@@ -222,7 +242,7 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
         if (tmax >= tl) {
 #pragma unroll 4
             for (int i = 0; i < kPer; ++i) {
-                const int doc = tid + i * kBmThreads;
+                const int doc = tid + i * kPkThreads;
                 if (acc[doc] >= tl && (want == -1 || p.doc_group[rbase + doc] == want)) {
                     const int idx = atomicAdd(&s_cnt, 1);
                     if (idx < kPkLocalCap) s_wi[idx] = doc;
@@ -238,7 +258,7 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
         if (tid == 0) c.ovf[q] = 1;
         return;
     }
-    for (int i = tid; i < n; i += kBmThreads) {
+    for (int i = tid; i < n; i += kPkThreads) {
         const int dl = s_wi[i];
         const uint32_t mine = acc[dl];
         const int slot = atomicAdd(c.cand_cnt + q, 1);

@@ -113,7 +113,7 @@ static int simt_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64
 }
 
 static thread_local int g_force_kernel = 0;
-static const int g_default_variant = 1;   // auto: persistent TS kernel (queries in TMEM); 2 forces the SS kernel
+static const int g_default_variant = 2;   // auto: persistent TS kernel (queries in TMEM), 128-row corpus tiles
 static thread_local const char* g_last_kernel = "none";
 
 }  // namespace ezr
@@ -123,12 +123,25 @@ using namespace ezr;
 extern "C" {
 
 int ezr_dense_set_kernel(int32_t which) {
-    EZR_CHECK_ARG(which >= 0 && which <= 3, "dense_set_kernel: 0 auto, 1 simt, 2 tcgen05 (SS), 3 tcgen05 (TS)");
+    EZR_CHECK_ARG(which >= 0 && which <= 4,
+                  "dense_set_kernel: 0 auto, 1 simt, 2 tcgen05 (SS), 3 tcgen05 (TS, N=64), 4 tcgen05 (TS, N=128)");
     g_force_kernel = which;
     return EZR_OK;
 }
 
 const char* ezr_dense_last_kernel(void) { return g_last_kernel; }
+
+int ezr_dense_set_probe(int32_t probe) {
+    EZR_CHECK_ARG(probe >= 0 && probe <= 7, "dense_set_probe: bit mask 0..7");
+    g_dense_probe = probe;
+    return EZR_OK;
+}
+
+int ezr_dense_set_stage_cap(int32_t stages) {
+    EZR_CHECK_ARG(stages == 0 || stages >= 2, "dense_set_stage_cap: 0 (no cap) or >= 2 TMA stages");
+    g_dense_stage_cap = stages;
+    return EZR_OK;
+}
 
 size_t ezr_dense_topk_workspace(int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k) {
     if (n_rows <= 0 || n_queries <= 0 || k <= 0) return 0;
@@ -162,15 +175,12 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
         return EZR_ERR_UNSUPPORTED;
     }
     if (tc_ok && g_force_kernel != 1) {
-        int variant = g_force_kernel == 3 ? 1 : (g_force_kernel == 2 ? 0 : g_default_variant);
-        if (dim > 768) {
-            if (g_force_kernel == 2) {
-                set_error("dense_topk: the SS tcgen05 kernel supports dim <= 768 (got %d)", dim);
-                return EZR_ERR_UNSUPPORTED;
-            }
-            variant = 1;
+        int variant = g_force_kernel == 4 ? 2 : g_force_kernel == 3 ? 1 : (g_force_kernel == 2 ? 0 : g_default_variant);
+        if (dim > 768 && variant == 0) {
+            set_error("dense_topk: the SS tcgen05 kernel supports dim <= 768 (got %d)", dim);
+            return EZR_ERR_UNSUPPORTED;
         }
-        g_last_kernel = variant == 1 ? "tcgen05-ts" : "tcgen05";
+        g_last_kernel = variant == 2 ? "tcgen05-ts128" : variant == 1 ? "tcgen05-ts" : "tcgen05";
         return dense_tc_topk(c, n_rows, dim, ld_corpus, q, n_queries, ld_queries, k, doc_group, q_group, id_base,
                              out_scores, out_ids, out_counts, workspace, workspace_bytes, st, variant);
     }

@@ -20,6 +20,9 @@
 
 namespace ezr {
 
+int g_dense_probe = 0;       // ezr_dense_set_probe
+int g_dense_stage_cap = 0;   // 0: use all shared memory for the TMA ring (ezr_dense_set_stage_cap)
+
 constexpr int TC_M = 128;       // queries per CTA = UMMA M
 constexpr int TC_N = 64;        // corpus rows per tile = UMMA N
 constexpr int TC_KC = 64;       // bf16 per k-chunk = one 128-byte swizzle row
@@ -55,6 +58,7 @@ struct TcParams {
     int n_slices;
     int n_qblocks;        // TS variant: units = n_slices x n_qblocks, walked by persistent CTAs
     int kps;              // TS variant: k-chunks (TMA boxes) per pipeline stage: 1, 2 or 4
+    int probe;            // measurement probes (ezr_dense_set_probe): 1 = no TMA loads, 2 = no MMAs, 3 = no epilogue scan; results are garbage
 };
 
 struct TcBarriers {
@@ -247,18 +251,27 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // for a LONG run of corpus rows (n_rows / n_splits), so the per-thread top-k lists warm up once per unit and
 // almost nothing passes the threshold afterwards, and the query blocks that are resident at the same time stream
 // the SAME corpus split, so every corpus tile is fetched from HBM once and served to the other CTAs from L2.
-// TMEM: A at columns [0, 384), two 64-column accumulator stages at [384, 512).
-template <bool FILTER, int KT>
+// TMEM (TN = 64):  A at columns [0, 384), two 64-column accumulator stages at [384, 512).
+// TMEM (TN = 128): A at columns [0, 256) (k-chunks 0..7; the rest of the query block sits in shared memory and
+// those k-steps use the SS form), two 128-column accumulator stages at [256, 512).  The TS form reads its A
+// operand from tensor memory at 64 B/clk (4 KB per 128x16 slab = 64 cycles per MMA, measured: a pipeline run
+// with the TMA loads removed still takes 64 cycles per N=64 MMA, twice its 32-cycle floor), so only N >= 128
+// keeps the tensor pipe busy: one MMA then covers 128 corpus rows in the same 64 cycles.
+template <bool FILTER, int KT, int TN>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                 const TcParams p) {
+    constexpr int TMEM_KC = TN == 64 ? 12 : 8;             // k-chunks of A held in tensor memory
+    constexpr int ACC_COL0 = TMEM_KC * (TC_KC / 2);        // first accumulator column
+    constexpr int B_CHUNK_BYTES = TN * TC_KC * 2;          // one k-chunk of a corpus tile
+    static_assert(ACC_COL0 + TS_ACC * TN <= 512, "tensor memory layout");
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    const int kc_tm = min(p.kchunks, TS_TMEM_KC);          // k-chunks of A in tensor memory
+    const int kc_tm = min(p.kchunks, TMEM_KC);             // k-chunks of A in tensor memory
     const int kc_sm = p.kchunks - kc_tm;                   // k-chunks of A in shared memory (dim > 768)
     unsigned char* smem_ahi = smem;
     unsigned char* smem_b = smem + (size_t)kc_sm * TC_A_CHUNK_BYTES;
-    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_b + (size_t)p.n_stages * p.kps * TC_B_STAGE_BYTES);
+    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_b + (size_t)p.n_stages * p.kps * B_CHUNK_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -296,7 +309,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const int slice = u / p.n_qblocks;
                 const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
                 const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
-                const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+                const int n_tiles = (int)((row_end - row_begin + TN - 1) / TN);
                 if (kc_sm > 0) {
                     // tail of the query block (columns >= 768) -> shared memory, once the previous unit's MMAs are done
                     const int q0 = (u % p.n_qblocks) * TC_M;
@@ -307,13 +320,18 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                          (kc_tm + j) * TC_KC, q0);
                 }
                 for (int t = 0; t < n_tiles; ++t) {
-                    const int row0 = (int)(row_begin + (int64_t)t * TC_N);
+                    const int row0 = (int)(row_begin + (int64_t)t * TN);
                     for (int kc = 0; kc < p.kchunks; kc += p.kps) {
                         ptx::mbar_wait(&bars->b_empty[stage], phase ^ 1);
-                        ptx::mbar_expect_tx(&bars->b_full[stage], (uint32_t)(p.kps * TC_B_STAGE_BYTES));
-                        unsigned char* dst = smem_b + (size_t)stage * (size_t)(p.kps * TC_B_STAGE_BYTES);
+                        if ((p.probe & 1)) {                       // probe: pipeline without the loads
+                            ptx::mbar_arrive(&bars->b_full[stage]);
+                            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
+                        ptx::mbar_expect_tx(&bars->b_full[stage], (uint32_t)(p.kps * B_CHUNK_BYTES));
+                        unsigned char* dst = smem_b + (size_t)stage * (size_t)(p.kps * B_CHUNK_BYTES);
                         for (int j = 0; j < p.kps; ++j)
-                            ptx::tma_load_2d(dst + (size_t)j * TC_B_STAGE_BYTES, &map_c, &bars->b_full[stage],
+                            ptx::tma_load_2d(dst + (size_t)j * B_CHUNK_BYTES, &map_c, &bars->b_full[stage],
                                              (kc + j) * TC_KC, row0);
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
@@ -324,7 +342,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // ---------------- MMA issuer ----------------
         // The whole warp walks the loop (warp-uniform control flow, so descriptor arithmetic stays on the uniform
         // datapath); only the tcgen05 instructions themselves are issued by one elected lane.
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_M, TC_N);
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_M, TN);
         const uint64_t b_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_b));
         const uint64_t ahi_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_ahi));
         int stage = 0;
@@ -335,7 +353,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const int slice = u / p.n_qblocks;
             const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
             const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
-            const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+            const int n_tiles = (int)((row_end - row_begin + TN - 1) / TN);
             ptx::mbar_wait(&bars->a_full, (uint32_t)ui & 1u);      // this unit's query block is in TMEM
             if (kc_sm > 0) ptx::mbar_wait(&bars->ahi_full, (uint32_t)ui & 1u);   // ... and its tail in shared memory
             ptx::tc_fence_after();
@@ -344,26 +362,26 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const uint32_t aph = (uint32_t)(it / TS_ACC) & 1u;
                 ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(TS_ACC_COL0 + as * TC_N);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ACC_COL0 + as * TN);
                 for (int kc = 0; kc < p.kchunks; kc += p.kps) {
                     ptx::mbar_wait(&bars->b_full[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t a_tmem = tmem_base + (uint32_t)(kc * (TC_KC / 2));
-                    const uint64_t b_desc = b_desc0 + (uint64_t)(stage * p.kps * (TC_B_STAGE_BYTES >> 4));
+                    const uint64_t b_desc = b_desc0 + (uint64_t)(stage * p.kps * (B_CHUNK_BYTES >> 4));
                     if (ptx::elect_one()) {
-                        for (int j = 0; j < p.kps; ++j) {
+                        for (int j = 0; j < ((p.probe & 2) ? (kc == 0 ? 1 : 0) : p.kps); ++j) {   // probe 2: one k-chunk per tile
                             if (kc + j < kc_tm) {
 #pragma unroll
                                 for (int k4 = 0; k4 < TC_KC / 16; ++k4)
                                     ptx::umma_f16_ts(d_tmem, a_tmem + j * (TC_KC / 2) + k4 * 8,
-                                                     b_desc + (uint64_t)(j * (TC_B_STAGE_BYTES >> 4) + k4 * 2), idesc,
+                                                     b_desc + (uint64_t)(j * (B_CHUNK_BYTES >> 4) + k4 * 2), idesc,
                                                      (uint32_t)((kc | j | k4) != 0));
                             } else {
                                 const uint64_t a_desc = ahi_desc0 + (uint64_t)((kc + j - kc_tm) * (TC_A_CHUNK_BYTES >> 4));
 #pragma unroll
                                 for (int k4 = 0; k4 < TC_KC / 16; ++k4)
                                     ptx::umma_f16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2),
-                                                     b_desc + (uint64_t)(j * (TC_B_STAGE_BYTES >> 4) + k4 * 2), idesc, 1u);
+                                                     b_desc + (uint64_t)(j * (B_CHUNK_BYTES >> 4) + k4 * 2), idesc, 1u);
                             }
                         }
                         ptx::umma_commit(&bars->b_empty[stage]);
@@ -392,7 +410,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const int q0 = (u % p.n_qblocks) * TC_M;
             const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
             const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
-            const int n_tiles = (int)((row_end - row_begin + TC_N - 1) / TC_N);
+            const int n_tiles = (int)((row_end - row_begin + TN - 1) / TN);
             const int qg = q0 + m;
             const bool active = qg < p.n_queries;
             int want = -1;
@@ -427,19 +445,25 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const uint32_t aph = (uint32_t)(it / TS_ACC) & 1u;
                 ptx::mbar_wait(&bars->acc_full[as], aph);
                 ptx::tc_fence_after();
-                const int64_t doc0 = row_begin + (int64_t)t * TC_N + half * 32;
+                constexpr int SUBS = TN / 64;            // 32-column batches per epilogue warp and tile
+#pragma unroll 1
+                for (int sub = 0; sub < SUBS; ++sub) {
+                const int64_t doc0 = row_begin + (int64_t)t * TN + half * (TN / 2) + sub * 32;
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                       (uint32_t)(TS_ACC_COL0 + as * TC_N + half * 32), r);
+                                       (uint32_t)(ACC_COL0 + as * TN + half * (TN / 2) + sub * 32), r);
                 ptx::tmem_ld_wait();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);   // scores are in registers: stage is free
+                if (sub == SUBS - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);   // scores are in registers: stage is free
+                }
                 // Fast path (straight-line, static register indices): the maximum of the 32 scores.  After the
                 // lists have warmed up most batches of 32 end here.
                 float mx = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                if (p.probe & 4) mx = -INFINITY;
                 if (active && mx >= thr) {
                     // Slow path: which of the 32 reach the threshold (bit mask, static indices), then ONE copy of the
                     // insertion code over the set bits, in increasing document order (a fully unrolled version is
@@ -482,6 +506,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         }
                     }
                 }
+                }   // sub
             }
             if (active) {
                 const int64_t o = (((int64_t)qg * p.n_slices + slice) * 2 + half) * k;
@@ -544,16 +569,16 @@ static int tc_slices(int64_t n_rows) {
     return (int)(tiles < sms ? tiles : sms);
 }
 
-static int tc_rows_per_slice(int64_t n_rows, int slices) {
-    const int64_t tiles = (n_rows + TC_N - 1) / TC_N;
-    return (int)((tiles + slices - 1) / slices) * TC_N;
+static int tc_rows_per_slice(int64_t n_rows, int slices, int tn = TC_N) {
+    const int64_t tiles = (n_rows + tn - 1) / tn;
+    return (int)((tiles + slices - 1) / slices) * tn;
 }
 
 // TS variant: number of corpus splits.  Units = splits x query blocks are walked by `sms` persistent CTAs.
 // Cost model: makespan = waves x (unit length + re-warm time of the per-thread top-k lists), in units of the time
 // one CTA needs to stream the whole corpus (~45 GB/s per SM); re-warming costs ~20 us per unit.
-static int ts_choose_splits(int qblocks, int64_t n_rows, int dim, int sms) {
-    const int64_t tiles = (n_rows + TC_N - 1) / TC_N;
+static int ts_choose_splits(int qblocks, int64_t n_rows, int dim, int sms, int tn) {
+    const int64_t tiles = (n_rows + tn - 1) / tn;
     int64_t max_s = tiles / 4;                 // at least 4 tiles per unit
     if (max_s > sms) max_s = sms;
     if (max_s < 1) max_s = 1;
@@ -602,8 +627,11 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     p.dim = dim;
     p.n_rows = n_rows;
     p.n_qblocks = (n_queries + TC_M - 1) / TC_M;
-    p.n_slices = variant == 1 ? ts_choose_splits(p.n_qblocks, n_rows, dim, sm_count()) : tc_slices(n_rows);
-    p.rows_per_slice = tc_rows_per_slice(n_rows, p.n_slices);
+    const bool ts = variant >= 1;
+    const int tn = variant == 2 ? 128 : TC_N;                   // corpus rows per tile (UMMA N)
+    const int tmem_kc = variant == 2 ? 8 : TS_TMEM_KC;          // k-chunks of the query block in tensor memory
+    p.n_slices = ts ? ts_choose_splits(p.n_qblocks, n_rows, dim, sm_count(), tn) : tc_slices(n_rows);
+    p.rows_per_slice = tc_rows_per_slice(n_rows, p.n_slices, tn);
     // with the rounded-up slice size the last slices may be empty: shrink to the non-empty ones
     p.n_slices = (int)((n_rows + p.rows_per_slice - 1) / p.rows_per_slice);
     p.n_queries = n_queries;
@@ -612,24 +640,29 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     p.id_base = id_base;
     p.doc_group = doc_group;
     p.q_group = q_group;
-    if (variant != 1 && dim > TC_MAXD) {
+    if (!ts && dim > TC_MAXD) {
         set_error("dense_topk(tcgen05 SS): dim=%d > %d; use the TS variant", dim, TC_MAXD);
         return EZR_ERR_UNSUPPORTED;
     }
-    const int kc_sm = p.kchunks > TS_TMEM_KC ? p.kchunks - TS_TMEM_KC : 0;
-    const size_t a_bytes = variant == 1 ? (size_t)kc_sm * TC_A_CHUNK_BYTES : (size_t)p.kchunks * TC_A_CHUNK_BYTES;
+    const int kc_sm = p.kchunks > tmem_kc ? p.kchunks - tmem_kc : 0;
+    const size_t a_bytes = ts ? (size_t)kc_sm * TC_A_CHUNK_BYTES : (size_t)p.kchunks * TC_A_CHUNK_BYTES;
+    const size_t chunk_bytes = (size_t)tn * TC_KC * 2;          // one k-chunk of a corpus tile
     const size_t fixed = 1024 /*alignment slack*/ + sizeof(TcBarriers) + 64;
+    p.probe = g_dense_probe;
     p.kps = 1;
     if (variant == 1) p.kps = (p.kchunks % 4 == 0) ? 4 : ((p.kchunks % 2 == 0) ? 2 : 1);
-    int stages = (int)((TC_SMEM_LIMIT - fixed - a_bytes) / ((size_t)p.kps * TC_B_STAGE_BYTES));
+    if (variant == 2) p.kps = (p.kchunks % 2 == 0) ? 2 : 1;     // 32 KB per stage either way
+    int stages = (int)((TC_SMEM_LIMIT - fixed - a_bytes) / ((size_t)p.kps * chunk_bytes));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    // leave shared memory to kernels of another stream (the BM25 route) when the caller overlaps the two routes
+    if (g_dense_stage_cap > 0 && stages > g_dense_stage_cap) stages = g_dense_stage_cap;
     if (stages < 2) {
         set_error("dense_topk(tcgen05): dim=%d leaves no room for a TMA ring", dim);
         return EZR_ERR_UNSUPPORTED;
     }
     p.n_stages = stages;
-    const size_t smem = fixed + a_bytes + (size_t)stages * p.kps * TC_B_STAGE_BYTES;
-    const int lists = variant == 1 ? 2 : 1;
+    const size_t smem = fixed + a_bytes + (size_t)stages * p.kps * chunk_bytes;
+    const int lists = ts ? 2 : 1;
     const size_t n_part = (size_t)n_queries * p.n_slices * k * lists;
     p.part_s = reinterpret_cast<float*>(ws);
     p.part_id = reinterpret_cast<int32_t*>((char*)ws + align_up(n_part * 4, 256));
@@ -637,32 +670,41 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     CUtensorMap map_q, map_c;
     int rc = encode_tmap_2d_bf16(&map_q, queries, (uint64_t)dim, (uint64_t)n_queries, (uint64_t)ldq, TC_KC, TC_M);
     if (rc) return rc;
-    rc = encode_tmap_2d_bf16(&map_c, corpus, (uint64_t)dim, (uint64_t)n_rows, (uint64_t)ldc, TC_KC, TC_N);
+    rc = encode_tmap_2d_bf16(&map_c, corpus, (uint64_t)dim, (uint64_t)n_rows, (uint64_t)ldc, TC_KC, (uint32_t)tn);
     if (rc) return rc;
 
     const bool filter = (q_group != nullptr);
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const TcParams);
-    static const kern_t table[2][2][4] = {
+    static const kern_t table[3][2][4] = {
         {{dense_tc_kernel<false, 4>, dense_tc_kernel<false, 8>, dense_tc_kernel<false, 12>, dense_tc_kernel<false, 16>},
          {dense_tc_kernel<true, 4>, dense_tc_kernel<true, 8>, dense_tc_kernel<true, 12>, dense_tc_kernel<true, 16>}},
-        {{dense_ts_kernel<false, 4>, dense_ts_kernel<false, 8>, dense_ts_kernel<false, 12>, dense_ts_kernel<false, 16>},
-         {dense_ts_kernel<true, 4>, dense_ts_kernel<true, 8>, dense_ts_kernel<true, 12>, dense_ts_kernel<true, 16>}}};
+        {{dense_ts_kernel<false, 4, 64>, dense_ts_kernel<false, 8, 64>, dense_ts_kernel<false, 12, 64>,
+          dense_ts_kernel<false, 16, 64>},
+         {dense_ts_kernel<true, 4, 64>, dense_ts_kernel<true, 8, 64>, dense_ts_kernel<true, 12, 64>,
+          dense_ts_kernel<true, 16, 64>}},
+        {{dense_ts_kernel<false, 4, 128>, dense_ts_kernel<false, 8, 128>, dense_ts_kernel<false, 12, 128>,
+          dense_ts_kernel<false, 16, 128>},
+         {dense_ts_kernel<true, 4, 128>, dense_ts_kernel<true, 8, 128>, dense_ts_kernel<true, 12, 128>,
+          dense_ts_kernel<true, 16, 128>}}};
     const int kt = (k + 3) / 4 - 1;
-    const int vi = variant == 1 ? 1 : 0;
+    const int vi = variant;
     kern_t kern = table[vi][filter ? 1 : 0][kt];
-    static bool attr_done[2][2][4] = {};
+    static bool attr_done[3][2][4] = {};
     if (!attr_done[vi][filter ? 1 : 0][kt]) {
         EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        // always configure the SM for the largest shared-memory carveout: with a capped ring the rest of the
+        // shared memory is then available to co-resident CTAs of other streams
+        EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done[vi][filter ? 1 : 0][kt] = true;
     }
     dim3 grid(p.n_slices, p.n_qblocks);
-    if (variant == 1) {
+    if (ts) {
         const int units = p.n_slices * p.n_qblocks;
         grid = dim3(units < sm_count() ? units : sm_count(), 1);
     }
     {
         ProfScope prof(EZR_PROF_DENSE_TC, st);
-        kern<<<grid, variant == 1 ? TS_THREADS : TC_THREADS, smem, st>>>(map_q, map_c, p);
+        kern<<<grid, ts ? TS_THREADS : TC_THREADS, smem, st>>>(map_q, map_c, p);
     }
     EZR_LAUNCH_CHECK();
     const int n_cand = p.n_slices * k * lists;

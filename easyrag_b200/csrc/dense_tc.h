@@ -15,4 +15,7 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
                   float* out_scores, int32_t* out_ids, int32_t* out_counts, void* ws, size_t ws_bytes,
                   cudaStream_t st, int variant);   // variant 0: queries in shared memory (SS), 1: in TMEM (TS)
 
+extern int g_dense_probe;       // see ezr_dense_set_probe
+extern int g_dense_stage_cap;   // see ezr_dense_set_stage_cap
+
 }  // namespace ezr

@@ -147,10 +147,22 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
                    int32_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes,
                    void* stream);
 /* 0 = pick automatically, 1 = force the generic SIMT kernel, 2 = force tcgen05 with the query block in shared
- * memory (SS), 3 = force tcgen05 with the query block in tensor memory (TS); 2/3 error if the shape is unsupported */
+ * memory (SS), 3 = force tcgen05 with the query block in tensor memory (TS) and 64-row corpus tiles, 4 = TS with
+ * 128-row corpus tiles (the automatic choice); 2/3/4 error if the shape is unsupported */
 int ezr_dense_set_kernel(int32_t which);
-/* name of the kernel the last ezr_dense_topk call on this thread launched ("tcgen05" / "tcgen05-ts" / "simt") */
+/* name of the kernel the last ezr_dense_topk call on this thread launched
+ * ("tcgen05" / "tcgen05-ts" / "tcgen05-ts128" / "simt") */
 const char* ezr_dense_last_kernel(void);
+
+/* Cap the TMA ring of the tcgen05 kernels at `stages` stages (0 = use all shared memory, the default).  A capped
+ * ring leaves shared memory on every SM for kernels of another stream: CoarseRanker(overlap=True) uses it to let
+ * BM25 CTAs co-reside with the persistent dense CTA (tensor pipe vs. integer/issue bound work). */
+int ezr_dense_set_stage_cap(int32_t stages);
+
+/* Measurement probes for the tcgen05 TS kernel (results become garbage; never use outside bench experiments):
+ * bit mask: 1 = pipeline without TMA loads, 2 = one k-chunk of MMAs per tile, 4 = epilogue without the
+ * insertion path. */
+int ezr_dense_set_probe(int32_t probe);
 
 /* ------------------------------------------------------------- fusion ---
  * HybridRetriever.reciprocal_rank_fusion (retrievers.py:256-274): list a first, then list b

@@ -39,5 +39,5 @@ def test_cpu_reference_arm_matches_oracle():
 def test_bench_defaults_finish_fast_and_name_the_metric():
     sys.argv = ["bench.py"]
     a = bench.parse()
-    assert a.gpus == 1 and a.steps <= 20 and a.warmup >= 3 and a.rows == 1_000_000 and a.dim == 768 and a.k == 10
+    assert a.gpus == 1 and a.steps <= 50 and a.warmup >= 3 and a.rows == 1_000_000 and a.dim == 768 and a.k == 10
     assert "queries/sec" in bench.METRIC and "1M" in bench.METRIC

@@ -189,7 +189,8 @@ def _topk_bytes(res):
 
 
 def test_bm25_two_phase_equals_ordered_kernel_and_oracle():
-    corpus = synth.make_sparse_corpus(30_000, 4000, 4242, mean_len=50, min_len=0, max_len=200)
+    # 140k documents = 18 ranges of 8192: three range chunks (4, 4, 10) with two bound updates in between
+    corpus = synth.make_sparse_corpus(140_000, 4000, 4242, mean_len=30, min_len=0, max_len=120)
     stats = Bm25Stats.from_tokens(corpus.tokens, corpus.doc_ptr, corpus.vocab, bm25_type=0)
     groups = synth.make_groups(corpus.n_docs, 5, 9)
     a = Bm25Index(stats, device=DEV, doc_group=groups, packed=True)
@@ -339,7 +340,8 @@ def _check_dense(res, c, qv, k, allowed=None, exact=False, id_base=0):
             assert m[got].all()
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])       # 1 = generic SIMT, 2 = tcgen05 (queries in smem), 3 = tcgen05 (queries in TMEM)
+# 1 = generic SIMT, 2 = tcgen05 (queries in smem), 3 = tcgen05 (queries in TMEM, 64-row tiles), 4 = same, 128-row tiles
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 @pytest.mark.parametrize("n,d,q,k", [(5000, 128, 130, 10), (777, 768, 3, 5), (64, 64, 1, 16), (20_000, 768, 257, 10),
                                      (100, 256, 5, 12)])
 def test_dense_exact_integer_inputs(kernel, n, d, q, k):
@@ -348,7 +350,7 @@ def test_dense_exact_integer_inputs(kernel, n, d, q, k):
     _lib.check(L.ezr_dense_set_kernel(kernel))
     try:
         res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), k)
-        assert L.ezr_dense_last_kernel() == {1: b"simt", 2: b"tcgen05", 3: b"tcgen05-ts"}[kernel]
+        assert L.ezr_dense_last_kernel() == {1: b"simt", 2: b"tcgen05", 3: b"tcgen05-ts", 4: b"tcgen05-ts128"}[kernel]
     finally:
         L.ezr_dense_set_kernel(0)
     _check_dense(res, c, qv, k, exact=True)
@@ -356,12 +358,20 @@ def test_dense_exact_integer_inputs(kernel, n, d, q, k):
 
 @pytest.mark.parametrize("n,d,q,k", [(3000, 1024, 130, 10), (2500, 832, 5, 8), (70_000, 1024, 300, 10)])
 def test_dense_wide_dims_use_hybrid_tmem_smem_queries(n, d, q, k):
-    # BGE-large is 1024-d (BASELINE config 5): 768 columns of the query block sit in TMEM, the rest in shared memory
+    # BGE-large is 1024-d (BASELINE config 5): part of the query block sits in TMEM (512 columns of it with
+    # 128-row tiles, 768 with 64-row tiles), the rest in shared memory
     c, qv = _dense_case(n, d, q, 200 + n, integer=True)
     res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), k)
-    assert _lib.lib().ezr_dense_last_kernel() == b"tcgen05-ts"
+    assert _lib.lib().ezr_dense_last_kernel() == b"tcgen05-ts128"
     _check_dense(res, c, qv, k, exact=True)
     L = _lib.lib()
+    _lib.check(L.ezr_dense_set_kernel(3))
+    try:
+        res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), k)
+        assert L.ezr_dense_last_kernel() == b"tcgen05-ts"
+    finally:
+        L.ezr_dense_set_kernel(0)
+    _check_dense(res, c, qv, k, exact=True)
     _lib.check(L.ezr_dense_set_kernel(2))
     try:
         with pytest.raises(_lib.EzrError):
@@ -370,7 +380,7 @@ def test_dense_wide_dims_use_hybrid_tmem_smem_queries(n, d, q, k):
         L.ezr_dense_set_kernel(0)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 def test_dense_unit_vectors_within_tolerance(kernel):
     c, qv = _dense_case(30_000, 768, 200, 7)
     L = _lib.lib()
@@ -382,7 +392,7 @@ def test_dense_unit_vectors_within_tolerance(kernel):
     _check_dense(res, c, qv, 10)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 def test_dense_dir_filter_and_id_base(kernel):
     c, qv = _dense_case(9000, 256, 70, 11, integer=True)
     groups = synth.make_groups(9000, 4, 12)
