@@ -72,6 +72,7 @@ SIGNATURES = {
     "ezr_layernorm": (C.c_int, [_p, _i64, _p, _p, C.c_float, _i32, _i32, _p, _i64, _p]),
     "ezr_rope": (C.c_int, [_p, _i64, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "ezr_pool_normalize": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _p, C.c_float, _i32, _i32, _p, _p, _p]),
+    "ezr_launch_count": (C.c_longlong, []),
     "ezr_profile_enable": (C.c_int, [_i32]),
     "ezr_profile_reset": (C.c_int, []),
     "ezr_profile_read": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

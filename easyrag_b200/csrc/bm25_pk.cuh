@@ -43,6 +43,9 @@ constexpr int kPkListCap = EZR_BM25_CAND_CAP;             // candidates per quer
 #ifndef EZR_BM25_PK_THREADS
 #define EZR_BM25_PK_THREADS 256
 #endif
+#ifndef EZR_BM25_PK_BRANCHY
+#define EZR_BM25_PK_BRANCHY 0
+#endif
 #ifndef EZR_BM25_PK_UNROLL
 #define EZR_BM25_PK_UNROLL 8
 #endif
@@ -154,7 +157,12 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     const uint32_t spare = (uint32_t)(kBmRange + lane);
     auto apply = [&](uint32_t x) -> bool {
         const uint32_t wq = x & kPkWMask;
+#if EZR_BM25_PK_BRANCHY      // A/B switch: predicate the atomic instead (idle lanes issue nothing)
+        if (x == 0u) return false;
+        const uint32_t dl = x >> kPkWBits;
+#else
         const uint32_t dl = x != 0u ? (x >> kPkWBits) : spare;
+#endif
         const uint32_t old = atomicAdd(&acc[dl], wq);
         return tq1 - old < wq;                           // weights are non-negative: a document crosses once
     };

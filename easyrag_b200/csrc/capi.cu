@@ -36,6 +36,9 @@ struct ProfSlot {
     size_t used = 0;
 };
 static bool g_prof_on = false;
+unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 static ProfSlot g_prof[EZR_PROF_COUNT];
 
 bool prof_begin(int slot, cudaStream_t st) {
@@ -65,6 +68,8 @@ int ezr_profile_enable(int32_t on) {
     ezr::g_prof_on = on != 0;
     return EZR_OK;
 }
+
+long long ezr_launch_count(void) { return (long long)__atomic_load_n(&ezr::g_launches, __ATOMIC_RELAXED); }
 
 int ezr_profile_reset(void) {
     for (auto& s : ezr::g_prof) s.used = 0;

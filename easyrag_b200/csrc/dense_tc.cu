@@ -369,19 +369,25 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     const uint32_t a_tmem = tmem_base + (uint32_t)(kc * (TC_KC / 2));
                     const uint64_t b_desc = b_desc0 + (uint64_t)(stage * p.kps * (B_CHUNK_BYTES >> 4));
                     if (ptx::elect_one()) {
-                        for (int j = 0; j < ((p.probe & 2) ? (kc == 0 ? 1 : 0) : p.kps); ++j) {   // probe 2: one k-chunk per tile
-                            if (kc + j < kc_tm) {
+                        const int nj = (p.probe & 2) ? (kc == 0 ? 1 : 0) : p.kps;     // probe 2: one k-chunk per tile
 #pragma unroll
-                                for (int k4 = 0; k4 < TC_KC / 16; ++k4)
-                                    ptx::umma_f16_ts(d_tmem, a_tmem + j * (TC_KC / 2) + k4 * 8,
-                                                     b_desc + (uint64_t)(j * (B_CHUNK_BYTES >> 4) + k4 * 2), idesc,
-                                                     (uint32_t)((kc | j | k4) != 0));
-                            } else {
-                                const uint64_t a_desc = ahi_desc0 + (uint64_t)((kc + j - kc_tm) * (TC_A_CHUNK_BYTES >> 4));
+                        for (int j = 0; j < 4; ++j) {                                 // kps <= 4: static offsets
+                            if (j < nj) {
+                                if (kc + j < kc_tm) {
 #pragma unroll
-                                for (int k4 = 0; k4 < TC_KC / 16; ++k4)
-                                    ptx::umma_f16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2),
-                                                     b_desc + (uint64_t)(j * (B_CHUNK_BYTES >> 4) + k4 * 2), idesc, 1u);
+                                    for (int k4 = 0; k4 < TC_KC / 16; ++k4)
+                                        ptx::umma_f16_ts(d_tmem, a_tmem + j * (TC_KC / 2) + k4 * 8,
+                                                         b_desc + (uint64_t)(j * (B_CHUNK_BYTES >> 4) + k4 * 2), idesc,
+                                                         (uint32_t)((kc | j | k4) != 0));
+                                } else {
+                                    const uint64_t a_desc =
+                                        ahi_desc0 + (uint64_t)((kc + j - kc_tm) * (TC_A_CHUNK_BYTES >> 4));
+#pragma unroll
+                                    for (int k4 = 0; k4 < TC_KC / 16; ++k4)
+                                        ptx::umma_f16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2),
+                                                         b_desc + (uint64_t)(j * (B_CHUNK_BYTES >> 4) + k4 * 2), idesc,
+                                                         1u);
+                                }
                             }
                         }
                         ptx::umma_commit(&bars->b_empty[stage]);

@@ -33,7 +33,13 @@ const char* get_error();
         }                                                                                \
     } while (0)
 
-#define EZR_LAUNCH_CHECK() EZR_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here: the launch counter behind ezr_launch_count()
+void count_launch();
+#define EZR_LAUNCH_CHECK()              \
+    do {                                \
+        ::ezr::count_launch();          \
+        EZR_CUDA(cudaGetLastError());   \
+    } while (0)
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

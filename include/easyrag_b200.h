@@ -236,6 +236,8 @@ typedef enum ezr_prof_slot {
     EZR_PROF_BM25_RESCORE = 9, /* bm25_rescore_kernel (exact float64 rescoring + top-k of the candidates) */
     EZR_PROF_COUNT = 10
 } ezr_prof_slot;
+/* kernels launched by this library since it was loaded (every launch site counts itself) */
+long long ezr_launch_count(void);
 int ezr_profile_enable(int32_t on);
 int ezr_profile_reset(void);
 int ezr_profile_read(int32_t slot, double* total_ms, int32_t* launches);

@@ -229,7 +229,7 @@ def test_bm25_two_phase_equals_ordered_kernel_and_oracle():
 
 def test_bm25_two_phase_hands_overflow_and_huge_queries_to_ordered_kernel():
     # half of the corpus is one repeated document (mass ties overflow the candidate list), the rest is random;
-    # a batch mixes tie queries, ordinary queries and a query of > 2048 tokens (integer sums could wrap)
+    # a batch mixes tie queries, ordinary queries and a query of > 4096 tokens (integer sums could wrap)
     base = synth.make_sparse_corpus(10_000, 500, 31, mean_len=20, min_len=1, max_len=60)
     rnd = base.doc_lists()
     same = np.array([490, 491, 492, 493, 490], dtype=np.int32)
@@ -243,7 +243,7 @@ def test_bm25_two_phase_hands_overflow_and_huge_queries_to_ordered_kernel():
     present = np.nonzero(o.df)[0]
     rng = np.random.default_rng(6)
     lists = [[490, 491], [int(t) for t in rng.choice(present, 6)], [493], [int(t) for t in rng.choice(present, 9)],
-             [int(t) for t in rng.choice(present, 2100)], [int(t) for t in rng.choice(present, 4)] + [492]]
+             [int(t) for t in rng.choice(present, 4200)], [int(t) for t in rng.choice(present, 4)] + [492]]
     qp = torch.tensor(np.cumsum([0] + [len(l) for l in lists]), dtype=torch.int32)
     qt = torch.tensor([t for l in lists for t in l], dtype=torch.int32)
     rows = [o.get_scores(l) for l in lists]
