@@ -124,3 +124,23 @@ def test_get_node_content_views():
     assert get_node_content(n, 2) == "###\nkp\n\nbody"
     assert get_node_content(n, 4) == "fp" and get_node_content(n, 5) == "kp"
     assert get_node_content(schema.TextNode("b"), 5) == ""
+
+
+def test_rerank_handoff_slices_like_the_reference():
+    # rerankers.py:309-322: slices of embed_bs over the coarse list, pairs (query, get_node_content(node, embed_type))
+    import torch
+    from easyrag_b200 import handoff
+    from easyrag_b200.schema import TextNode, NodeWithScore
+    nodes = [NodeWithScore(node=TextNode(text=f"chunk {i}", metadata={"file_path": f"f{i}.txt"}), score=1.0 / (i + 1))
+             for i in range(70)]
+    got = list(handoff.rerank_batches(nodes, "问题", embed_type=1, batch_size=32))
+    assert [(b, e) for b, e, _ in got] == [(0, 32), (32, 64), (64, 70)]
+    for b, e, pairs in got:
+        assert pairs == [("问题", "###\nf%d.txt\n\nchunk %d" % (i, i)) for i in range(b, e)]
+    assert list(handoff.rerank_batches([], "q")) == []
+    ids = torch.tensor([[5, 3, 9, -1], [7, -1, -1, -1], [-1, -1, -1, -1]], dtype=torch.int32)
+    cnt = torch.tensor([3, 1, 0], dtype=torch.int32)
+    assert list(handoff.candidate_batches(ids, cnt, batch_size=2)) == [(0, 0, [5, 3]), (0, 2, [9]), (1, 0, [7])]
+    import pytest
+    with pytest.raises(ValueError):
+        list(handoff.rerank_batches(nodes, "q", batch_size=0))
