@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--dense-kernel", type=int, default=0, help="0 auto, 1 simt, 2 tcgen05 SS, 3 tcgen05 TS")
     ap.add_argument("--overlap", type=int, default=0, help="1: dense and BM25 routes on two streams")
+    ap.add_argument("--self-check", type=int, default=64,
+                    help="after timing: first N queries through both BM25 kernel paths at full size, compared bit for bit")
     ap.add_argument("--dense-probe", type=int, default=0, help="measurement probe of the dense kernel (results invalid)")
     ap.add_argument("--dense-stages", type=int, default=0, help="cap of the dense kernel's TMA ring (0 = all smem)")
     return ap.parse_args()
@@ -306,6 +308,22 @@ def run_ours(args):
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
 
+    # Full-size property check outside the timed regions: the two-phase path (integer candidates + exact
+    # rescoring) and the ordered float64 kernel are independent implementations; on this shard they must return
+    # the same ids, scores and counts bit for bit.
+    self_check = None
+    if args.self_check > 0 and sparse.post_pk is not None:
+        nq = min(args.self_check, args.queries)
+        qp = data["queries"].term_ptr[:nq + 1].to(dev)
+        qt = data["queries"].terms.to(dev)
+        a = batched.bm25_topk(sparse, qp, qt, k)
+        b = batched.bm25_topk(sparse.ordered_view(), qp, qt, k)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(a.ids, b.ids) and torch.equal(a.counts, b.counts)
+                    and torch.equal(a.scores.view(torch.int64), b.scores.view(torch.int64)))
+        self_check = {"bm25_two_phase_equals_ordered": same, "queries": nq, "postings_local": sparse.n_postings}
+        if not same:
+            raise SystemExit(f"bench.py self-check FAILED on rank {rank}: BM25 kernel paths disagree")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -385,7 +403,8 @@ def run_ours(args):
         "gpu_launches": int(launches_timed),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "setup": {"generate_s": round(data["gen_s"], 1), "index_build_s": round(build_s, 1),
-                  "index_bytes": sparse.index_bytes(), "dense_kernel": L.ezr_dense_last_kernel().decode()},
+                  "index_bytes": sparse.index_bytes(), "dense_kernel": L.ezr_dense_last_kernel().decode(),
+                  "self_check": self_check},
     }
     print(json.dumps(line))
     if world > 1:

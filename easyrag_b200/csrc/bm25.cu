@@ -40,7 +40,7 @@ __global__ void bm25_weights_kernel(const int64_t* __restrict__ indptr, const in
     // term of posting p: largest t with indptr[t] <= p
     int lo = 0, hi = vocab;   // invariant: indptr[lo] <= p < indptr[hi]
     while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
+        const int mid = lo + ((hi - lo) >> 1);
         if (indptr[mid] <= p) lo = mid; else hi = mid;
     }
     const double tf = (double)post_tf[p];

@@ -383,7 +383,7 @@ bm25_rescore_kernel(const Bm25Params p, const PkParams c, double* __restrict__ o
                     const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
                     int lo = base + (int)ro[0], hi = base + (int)ro[1];
                     while (lo < hi) {                    // lower_bound of doc in the term's postings of range r
-                        const int mid = (lo + hi) >> 1;
+                        const int mid = lo + ((hi - lo) >> 1);       // lo + hi can pass 2^31 on a 2^30+ posting shard
                         if (__ldg(p.post_doc + mid) < doc) lo = mid + 1; else hi = mid;
                     }
                     if (lo < base + (int)ro[1] && __ldg(p.post_doc + lo) == doc) wv = __ldg(post_w + lo);

@@ -221,6 +221,17 @@ class Bm25Index:
         s.post_pk = self.post_pk.data_ptr() if self.post_pk is not None else None
         self._struct = s
 
+    def ordered_view(self) -> "Bm25Index":
+        """The same device arrays without the packed postings: ``ezr_bm25_topk`` then runs the ordered float64
+        kernel.  Two independent kernel paths over one index = a full-size self-check (bench.py --self-check)."""
+        import copy
+        v = copy.copy(self)
+        v._packed_opt = False
+        v.post_pk, v.pk_scale_log2 = None, 0
+        v._struct = None
+        v.refresh_struct()
+        return v
+
     def set_doc_group(self, doc_group: Optional[torch.Tensor]):
         self.doc_group = None if doc_group is None else doc_group.to(device=self.device, dtype=torch.int32).contiguous()
         self.refresh_struct()

@@ -251,6 +251,40 @@ def test_bm25_two_phase_hands_overflow_and_huge_queries_to_ordered_kernel():
         _check_bm25_topk(batched.bm25_topk(a, qp, qt, k), rows, k)
 
 
+
+def test_bm25_negative_idf_index_uses_ordered_kernel():
+    # Five terms in ~90% of the documents and one in ~30%: the mean idf is negative, so rank_bm25's epsilon floor
+    # (eps * average_idf) is negative too and contributions can be negative.  Partial sums are then not monotone:
+    # no packed postings, no crossing-based selection - the ordered kernel must still match the oracle bit for bit.
+    rng = np.random.default_rng(17)
+    docs = []
+    for i in range(20_000):
+        d = [t for t in range(5) if rng.random() < 0.9] * int(rng.integers(1, 3))
+        if rng.random() < 0.3:
+            d += [5] * int(rng.integers(1, 4))
+        docs.append(np.array(d if d else [0], dtype=np.int32))
+    tokens = torch.from_numpy(np.concatenate(docs)).to(torch.int32)
+    ptr = torch.tensor(np.cumsum([0] + [len(d) for d in docs]), dtype=torch.int64)
+    o = obm.OkapiCSR(docs, 6)
+    assert (o.idf < 0).any() and (o.idf > 0).any()
+    ix = Bm25Index(Bm25Stats.from_tokens(tokens, ptr, 6), device=DEV)
+    assert not ix.monotone and ix.post_pk is None
+    w = ix.post_w.cpu().numpy()
+    for t in range(6):
+        assert w[o.indptr[t]:o.indptr[t + 1]].tobytes() == o.contributions(t).tobytes()
+    assert (w < 0).any() and (w > 0).any()
+    lists = [[5], [5, 0], [0, 1, 2], [5, 5, 3], [4, 5, 1, 0, 2, 3]]
+    qp = torch.tensor(np.cumsum([0] + [len(l) for l in lists]), dtype=torch.int32)
+    qt = torch.tensor([t for l in lists for t in l], dtype=torch.int32)
+    rows = [o.get_scores(l) for l in lists]
+    assert any((r > 0).any() for r in rows) and any((r < 0).any() for r in rows)
+    for k in (1, 10, 32):
+        _check_bm25_topk(batched.bm25_topk(ix, qp, qt, k), rows, k)
+    got = batched.bm25_scores(ix, qp, qt).cpu().numpy()
+    for i, row in enumerate(rows):
+        assert got[i].tobytes() == row.tobytes()
+
+
 def test_bm25s_float32_bit_exact():
     corpus = synth.make_sparse_corpus(9000, 3000, 5, mean_len=60, min_len=1, max_len=200)
     qs = synth.make_queries(corpus, 40, 6)
