@@ -312,7 +312,7 @@ def run_ours(args):
     # rescoring) and the ordered float64 kernel are independent implementations; on this shard they must return
     # the same ids, scores and counts bit for bit.
     self_check = None
-    if args.self_check > 0 and sparse.post_pk is not None:
+    if args.self_check > 0 and sparse.post_pk is not None and args.dense_probe == 0:
         nq = min(args.self_check, args.queries)
         qp = data["queries"].term_ptr[:nq + 1].to(dev)
         qt = data["queries"].terms.to(dev)
@@ -324,6 +324,23 @@ def run_ours(args):
         self_check = {"bm25_two_phase_equals_ordered": same, "queries": nq, "postings_local": sparse.n_postings}
         if not same:
             raise SystemExit(f"bench.py self-check FAILED on rank {rank}: BM25 kernel paths disagree")
+        # dense route: the tcgen05 kernel against the generic fp32 SIMT kernel + row selection over the full shard;
+        # different accumulation orders, so the bar is the north star's cosine tolerance on the sorted score lists
+        if k <= 16:
+            r_tc = batched.dense_topk(dense, d_qvec[:nq], k)
+            tc_name = L.ezr_dense_last_kernel().decode()
+            _lib.check(L.ezr_dense_set_kernel(1))
+            try:
+                r_simt = batched.dense_topk(dense, d_qvec[:nq], k)
+            finally:
+                _lib.check(L.ezr_dense_set_kernel(args.dense_kernel))
+            torch.cuda.synchronize()
+            diff = float((r_tc.scores - r_simt.scores).abs().max())
+            agree = float((r_tc.ids == r_simt.ids).float().mean())
+            self_check.update({"dense_kernel": tc_name, "dense_vs_simt_max_abs_score_diff": diff,
+                               "dense_vs_simt_id_agreement": agree, "dense_tol": 1e-3})
+            if not diff <= 1e-3:
+                raise SystemExit(f"bench.py self-check FAILED on rank {rank}: dense kernels differ by {diff}")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -34,7 +34,7 @@ class Bm25IndexStruct(C.Structure):
 
 
 F64, F32 = 0, 1
-BM25_RANGE = 4096          # overwritten from ezr_bm25_range_size() when the library loads
+BM25_RANGE = 8192          # overwritten from ezr_bm25_range_size() when the library loads
 
 _p, _i32, _i64, _sz, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_double
 _IX = C.POINTER(Bm25IndexStruct)

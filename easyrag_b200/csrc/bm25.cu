@@ -8,11 +8,18 @@
 // Design (DESIGN.md "BM25"): the per-posting contribution is query independent,
 // so it is computed once at index build with explicit round-to-nearest
 // intrinsics (no FMA contraction) and stored next to the doc id (12 B/posting).
-// At query time a CTA owns (query, range of 8192 documents): its float64
-// accumulators live in shared memory, query terms are applied strictly in
-// token order (one barrier per term keeps the float64 sum order of the
-// reference), and the top-k is taken from shared memory by warp-shuffle
-// insertion.  Score vectors never touch HBM.
+// Two query-time paths share this index:
+//  * bm25_score_kernel (this file, "ordered"): a CTA owns (query, range of 8192
+//    documents); float64 accumulators live in shared memory, query terms are
+//    applied strictly in token order (one barrier per term keeps the float64
+//    sum order of the reference), top-k by threshold -> compact -> rank.  Used
+//    for float32 / negative-idf indices, score rows (k > 32) and as the
+//    hand-over target of the path below.
+//  * bm25_cand_kernel + bm25_bound_kernel + bm25_rescore_kernel (bm25_pk.cuh,
+//    "two-phase", the default for the fused top-k): integer upper-bound scores
+//    from 4-byte packed postings with shared-memory atomics, then the exact
+//    ordered float64 score of the surviving candidates only.
+// Score vectors never touch HBM on the fused paths.
 #include "ezr_common.cuh"
 #include "select.cuh"
 #include "../../include/easyrag_b200.h"

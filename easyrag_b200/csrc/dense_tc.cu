@@ -28,14 +28,14 @@ constexpr int TC_N = 64;        // corpus rows per tile = UMMA N
 constexpr int TC_KC = 64;       // bf16 per k-chunk = one 128-byte swizzle row
 constexpr int TC_MAXD = 768;       // SS variant: whole query block in shared memory
 constexpr int TS_MAXD = 1024;      // TS variant: 768 columns in TMEM + up to 256 in shared memory
-constexpr int TS_TMEM_KC = 12;     // k-chunks of the query block held in tensor memory (12 x 32 = 384 columns)
+constexpr int TS_TMEM_KC = 12;     // 64-row-tile TS kernel: k-chunks of the query block in tensor memory (12 x 32 = 384 columns;
+                                   // the 128-row-tile kernel keeps 8, see dense_ts_kernel)
 constexpr int TC_ACC = 4;       // TMEM accumulator stages (TC_N fp32 columns each)
 constexpr int TC_MAX_STAGES = 26;
 constexpr int TC_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TC_KMAX = 16;
 constexpr int TS_ACC = 2;          // TS variant: accumulator stages
 constexpr int TS_THREADS = 320;    // TS variant: TMA warp, MMA warp, 8 epilogue warps
-constexpr int TS_ACC_COL0 = 384;   // TS variant: first accumulator column (A occupies [0, 384))
 constexpr int TC_A_CHUNK_BYTES = TC_M * TC_KC * 2;   // 16384
 constexpr int TC_B_STAGE_BYTES = TC_N * TC_KC * 2;   // 8192
 constexpr int TC_SMEM_LIMIT = 232448;                 // 227 KB opt-in maximum per CTA
