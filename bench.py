@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--overlap", type=int, default=0, help="1: dense and BM25 routes on two streams")
     ap.add_argument("--self-check", type=int, default=64,
                     help="after timing: first N queries through both BM25 kernel paths at full size, compared bit for bit")
+    ap.add_argument("--bm25-skip", type=int, default=0, help="1: candidate pass skips non-essential terms (A/B)")
     ap.add_argument("--dense-probe", type=int, default=0, help="measurement probe of the dense kernel (results invalid)")
     ap.add_argument("--dense-stages", type=int, default=0, help="cap of the dense kernel's TMA ring (0 = all smem)")
     return ap.parse_args()
@@ -233,6 +234,7 @@ def run_ours(args):
     _lib.check(L.ezr_dense_set_kernel(args.dense_kernel))
     _lib.check(L.ezr_dense_set_stage_cap(args.dense_stages))
     _lib.check(L.ezr_dense_set_probe(args.dense_probe))
+    _lib.check(L.ezr_bm25_set_skipping(args.bm25_skip))
 
     data = make_data(args, dev)
     lo, hi = ezdist.shard_bounds(args.rows, world, rank, align=8192)

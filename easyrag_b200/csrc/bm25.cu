@@ -612,12 +612,19 @@ static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int
 
 
 // ---- two-phase path (bm25_pk.cuh) ----
+// ezr_bm25_set_skipping.  OFF by default: measured on the 1M x 10k-query step the candidate pass drops from 7.7 to
+// 6.6 ms but the rescoring grows from 0.28 to 2.3 ms (profiles/r02i_*), because candidates then only carry partial
+// lower bounds and the running bound tightens more slowly.  Kept (and parity-tested) as the starting point for a
+// version that refines the bounds between chunks.
+static int g_bm25_skip = 0;
+
 static bool pk_usable(const ezr_bm25_index* ix, int k) {
     return kPkEnabled && ix->post_pk != nullptr && ix->monotone && ix->score_type == EZR_F64 && k <= 32;
 }
 
 struct PkWorkspace {
-    int32_t *thr_key, *thr_q, *cand_cnt, *ovf, *ovf_n, *ovf_list, *cand_ids, *cand_q;
+    int32_t *thr_key, *thr_q, *cand_cnt, *ovf, *ne_sum, *ovf_n, *ovf_list, *cand_ids, *cand_q, *cand_u;
+    uint32_t* ne_mask;
     size_t zero_bytes, total;
 };
 
@@ -629,14 +636,18 @@ static PkWorkspace pk_carve(void* base, int n_queries) {
     w.thr_q = w.thr_key + q;
     w.cand_cnt = w.thr_q + q;
     w.ovf = w.cand_cnt + q;
-    w.ovf_n = w.ovf + q;
-    w.zero_bytes = (4 * q + 1) * 4;                     // everything up to here is zeroed per call
+    w.ne_mask = reinterpret_cast<uint32_t*>(w.ovf + q);
+    w.ne_sum = w.ovf + 2 * q;
+    w.ovf_n = w.ovf + 3 * q;
+    w.zero_bytes = (6 * q + 1) * 4;                     // everything up to here is zeroed per call
     size_t off = align_up(w.zero_bytes, 256);
     w.ovf_list = reinterpret_cast<int32_t*>(b + off);
     off += align_up(q * 4, 256);
     w.cand_ids = reinterpret_cast<int32_t*>(b + off);
     off += align_up(q * kPkListCap * 4, 256);
     w.cand_q = reinterpret_cast<int32_t*>(b + off);
+    off += align_up(q * kPkListCap * 4, 256);
+    w.cand_u = reinterpret_cast<int32_t*>(b + off);
     off += align_up(q * kPkListCap * 4, 256);
     w.total = off;
     return w;
@@ -652,7 +663,8 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
     p.out_scores = nullptr; p.out_ids = nullptr; p.thr_key = nullptr; p.monotone = ix->monotone;
     p.q_list = nullptr; p.q_count = nullptr;
     PkParams c;
-    c.post_pk = ix->post_pk; c.thr_q = w.thr_q; c.cand_cnt = w.cand_cnt; c.cand_ids = w.cand_ids; c.cand_q = w.cand_q; c.ovf = w.ovf;
+    c.post_pk = ix->post_pk; c.thr_q = w.thr_q; c.cand_cnt = w.cand_cnt; c.cand_ids = w.cand_ids; c.cand_q = w.cand_q; c.cand_u = w.cand_u; c.ovf = w.ovf;
+    c.term_max = g_bm25_skip ? ix->term_max : nullptr; c.ne_mask = w.ne_mask; c.ne_sum = w.ne_sum;
     c.ovf_n = w.ovf_n; c.ovf_list = w.ovf_list;
     const size_t smem = (size_t)(kBmRange + 32) * 4;
     static bool attr_done = false;
@@ -779,6 +791,22 @@ int ezr_bm25_pack(const int32_t* post_doc, const double* post_w, int64_t n_posti
     bm25_pack_kernel<<<(unsigned)((n_postings + 255) / 256), 256, 0, st>>>(post_doc, post_w, n_postings, scale, out_pk);
     EZR_LAUNCH_CHECK();
     *out_scale_log2 = e;
+    return EZR_OK;
+}
+
+int ezr_bm25_term_max(const int64_t* indptr, const uint32_t* post_pk, int32_t vocab, uint32_t* out_term_max,
+                      void* stream) {
+    EZR_CHECK_ARG(kPkEnabled, "bm25_term_max: this build has no packed postings");
+    if (vocab <= 0) return EZR_OK;
+    const int wpb = 8;
+    bm25_term_max_kernel<<<ceil_div(vocab, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(indptr, post_pk, vocab,
+                                                                                      out_term_max);
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+int ezr_bm25_set_skipping(int32_t on) {
+    g_bm25_skip = on != 0;
     return EZR_OK;
 }
 

@@ -22,6 +22,16 @@
 // the running bound of the query (raised with atomicMax as document ranges complete), phase 2 decides exactly.
 // Queries whose candidate list overflows (mass ties) are handed to bm25_score_kernel, so results never depend on
 // the capacity constants.
+//
+// Skipping the long posting lists (MaxScore).  Let gm_j be the largest packed weight of token j's term.  Once a
+// bound B exists, bm25_bound_kernel marks as NON-ESSENTIAL the tokens with the smallest gm whose sum NE stays
+// below kPkNeNum/kPkNeDen of B - 1.  The candidate pass does not read their postings at all: with
+// Q = Q_ess + Q_ne and Q_ne <= NE, a document with Q >= B - 1 has Q_ess >= B - 1 - NE, so that becomes the
+// crossing threshold.  Candidates then carry L = Q_ess (a lower bound of Q: still valid for raising B) and
+// U = L + NE (an upper bound: what pruning must use).  The high-df terms have the smallest weights and the
+// longest lists; phase 2 looks every token up anyway, so exactness is untouched.  Measured (profiles/r02i_*): the
+// candidate pass gets 14% faster but candidates multiply (their partial lower bounds tighten B more slowly) and the
+// rescoring eats the gain several times over, so ezr_bm25_set_skipping is OFF by default.
 #pragma once
 
 namespace ezr {
@@ -43,6 +53,11 @@ constexpr int kPkListCap = EZR_BM25_CAND_CAP;             // candidates per quer
 #ifndef EZR_BM25_PK_THREADS
 #define EZR_BM25_PK_THREADS 256
 #endif
+#ifndef EZR_BM25_PK_NE_NUM
+#define EZR_BM25_PK_NE_NUM 3
+#endif
+constexpr int kPkNeNum = EZR_BM25_PK_NE_NUM;             // tokens worth up to NUM/10 of the bound may be skipped (0: off)
+constexpr int kPkNeDen = 10;
 #ifndef EZR_BM25_PK_BRANCHY
 #define EZR_BM25_PK_BRANCHY 0
 #endif
@@ -59,7 +74,11 @@ struct PkParams {
     int32_t* thr_q;            // [Q] running bound B (integer domain), zeroed per call
     int32_t* cand_cnt;         // [Q] zeroed per call
     int32_t* cand_ids;         // [Q][kPkListCap] shard-local document ids
-    int32_t* cand_q;           // [Q][kPkListCap] their integer scores Q(d)
+    int32_t* cand_q;           // [Q][kPkListCap] lower bounds L(d) of their integer scores (skipped tokens left out)
+    int32_t* cand_u;           // [Q][kPkListCap] upper bounds U(d) = L(d) + NE at the time of the push
+    const uint32_t* term_max;  // [vocab] largest packed weight of each term in this shard, or NULL (no skipping)
+    uint32_t* ne_mask;         // [Q] zeroed per call: tokens (of the first 32) the candidate pass may skip
+    int32_t* ne_sum;           // [Q] zeroed per call: NE = sum of term_max over those tokens
     int32_t* ovf;              // [Q] zeroed per call: 1 = hand the query to the ordered kernel
     int32_t* ovf_n;            // [1] zeroed per call
     int32_t* ovf_list;         // [Q]
@@ -91,6 +110,19 @@ __global__ void bm25_pack_kernel(const int32_t* __restrict__ post_doc, const dou
     if (i >= n) return;
     const double x = ceil(__dmul_rn(w[i], scale));       // exact product (power of two), exact ceil
     out[i] = ((uint32_t)(post_doc[i] & (kBmRange - 1)) << kPkWBits) | (uint32_t)x;
+}
+
+// largest packed weight of every term (one warp per term, index-build time)
+__global__ void bm25_term_max_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ pk, int vocab,
+                                     uint32_t* __restrict__ out) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= vocab) return;
+    uint32_t mx = 0u;
+    for (int64_t i = indptr[t] + lane; i < indptr[t + 1]; i += 32) mx = max(mx, pk[i] & kPkWMask);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) out[t] = mx;
 }
 
 // ---- phase 1 ----
@@ -149,9 +181,14 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
 
     const int bound = s_b;                               // B: lower bound of S * (k-th best exact score), 0 = none yet
     const bool track = bound > 0;
+    // tokens bm25_bound_kernel declared non-essential for this query (valid for every later, higher bound): their
+    // postings are not read, their largest possible contribution NE is taken off the crossing threshold instead
+    const uint32_t ne_mask = (track && c.term_max) ? __ldg(c.ne_mask + q) : 0u;
+    const int ne = ne_mask ? __ldg(c.ne_sum + q) : 0;
+    if ((ne_mask >> lane) & 1u) len = 0;                 // first token batch only (the mask covers tokens 0..31)
     // crossing test in one unsigned compare: old < tq <= old + wq  <=>  tq - 1 - old < wq  (wraps to a huge value
     // when old >= tq; without a bound tq1 = 2^32-1: ~old is never below a packed weight)
-    const uint32_t tq1 = track ? (uint32_t)max(bound - 1, 1) - 1u : 0xffffffffu;
+    const uint32_t tq1 = track ? (uint32_t)max(bound - 1 - ne, 1) - 1u : 0xffffffffu;
     // Lanes without a posting add 0 to a private spare slot behind the accumulators (no branch around the atomic,
     // no same-address serialisation); crossings are rare: the caller votes and only then takes the push path.
     const uint32_t spare = (uint32_t)(kBmRange + lane);
@@ -273,6 +310,7 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
         if (slot < kPkListCap) {
             c.cand_ids[(int64_t)q * kPkListCap + slot] = rbase + dl;
             c.cand_q[(int64_t)q * kPkListCap + slot] = (int)mine;
+            c.cand_u[(int64_t)q * kPkListCap + slot] = (int)mine + ne;
         } else {
             c.ovf[q] = 1;
         }
@@ -294,6 +332,7 @@ constexpr int kBdThreads = 128;
 __global__ void __launch_bounds__(kBdThreads)
 bm25_bound_kernel(const Bm25Params p, const PkParams c) {
     __shared__ int s_q[kPkListCap];
+    __shared__ int s_u[kPkListCap];
     __shared__ int s_id[kPkListCap];
     __shared__ int s_kth, s_n2;
     const int q = blockIdx.x, tid = threadIdx.x;
@@ -305,6 +344,7 @@ bm25_bound_kernel(const Bm25Params p, const PkParams c) {
     }
     for (int i = tid; i < n; i += kBdThreads) {
         s_q[i] = c.cand_q[(int64_t)q * kPkListCap + i];
+        s_u[i] = c.cand_u[(int64_t)q * kPkListCap + i];
         s_id[i] = c.cand_ids[(int64_t)q * kPkListCap + i];
     }
     if (tid == 0) s_n2 = 0;
@@ -319,12 +359,14 @@ bm25_bound_kernel(const Bm25Params p, const PkParams c) {
         if (rank == p.k - 1) s_kth = mine;               // ranks are a permutation: exactly one writer
     }
     __syncthreads();
-    const int m = p.q_ptr[q + 1] - p.q_ptr[q];
-    const int b = max(s_kth - (m + 1), c.thr_q[q]);
+    const int qs = p.q_ptr[q];
+    const int m = p.q_ptr[q + 1] - qs;
+    const int b = max(s_kth - (m + 1), c.thr_q[q]);      // the k-th largest LOWER bound is a valid bound
     for (int i = tid; i < n; i += kBdThreads) {
-        if (s_q[i] >= b - 1) {
+        if (s_u[i] >= b - 1) {                           // keep what may still reach it: UPPER bounds decide
             const int pos = atomicAdd(&s_n2, 1);
             c.cand_q[(int64_t)q * kPkListCap + pos] = s_q[i];
+            c.cand_u[(int64_t)q * kPkListCap + pos] = s_u[i];
             c.cand_ids[(int64_t)q * kPkListCap + pos] = s_id[i];
         }
     }
@@ -332,6 +374,40 @@ bm25_bound_kernel(const Bm25Params p, const PkParams c) {
     if (tid == 0) {
         c.thr_q[q] = b;
         c.cand_cnt[q] = s_n2;
+    }
+    // Non-essential tokens for the ranges still to come (first 32 tokens; one warp): ascending by term maximum,
+    // the longest prefix whose sum stays within kPkNeNum/kPkNeDen of b - 1.
+    if (kPkNeNum > 0 && c.term_max != nullptr && tid < 32 && b > 1) {
+        const int lane = tid;
+        uint32_t gm = 0xffffffffu;                       // lanes without a token sort last and are never chosen
+        bool have = false;
+        if (lane < m) {
+            const int t = p.q_terms[qs + lane];
+            have = true;
+            gm = (t >= 0 && t < p.vocab) ? __ldg(c.term_max + t) : 0u;   // unknown terms contribute nothing
+        }
+        int rank = 0;
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t o = __shfl_sync(0xffffffffu, gm, j);
+            rank += (o < gm || (o == gm && j < lane)) ? 1 : 0;
+        }
+        unsigned long long pre = 0ull;                   // sum of the maxima ranked at or before this lane
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t o = __shfl_sync(0xffffffffu, gm, j);
+            const int r = __shfl_sync(0xffffffffu, rank, j);
+            const bool hj = __shfl_sync(0xffffffffu, have ? 1 : 0, j) != 0;
+            if (hj && r <= rank) pre += o;
+        }
+        const unsigned long long budget = (unsigned long long)(b - 1) * kPkNeNum / kPkNeDen;
+        const bool skip = have && pre <= budget;
+        const uint32_t mask = __ballot_sync(0xffffffffu, skip);
+        unsigned long long ne = skip ? (unsigned long long)gm : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ne += __shfl_xor_sync(0xffffffffu, ne, o);
+        if (lane == 0) {
+            c.ne_mask[q] = mask;
+            c.ne_sum[q] = (int)ne;
+        }
     }
 }
 

@@ -190,7 +190,7 @@ class Bm25Index:
 
         Only float64 indices with non-negative contributions qualify; ``EASYRAG_B200_BM25_PACKED=0`` keeps the
         ordered single-pass kernel (A/B measurements)."""
-        self.post_pk, self.pk_scale_log2 = None, 0
+        self.post_pk, self.pk_scale_log2, self.term_max = None, 0, None
         want = getattr(self, "_packed_opt", None)
         if want is None:
             want = os.environ.get("EASYRAG_B200_BM25_PACKED", "1") != "0"
@@ -205,7 +205,11 @@ class Bm25Index:
             _lib.check(_lib.lib().ezr_bm25_pack(_lib.ptr(self.post_doc), _lib.ptr(self.post_w), self.n_postings,
                                                 _lib.BM25_RANGE, _lib.ptr(pk), ctypes.byref(e), _lib.ptr(scratch),
                                                 _lib.stream_ptr()), "ezr_bm25_pack")
-        self.post_pk, self.pk_scale_log2 = pk, int(e.value)
+            # per-term maximum of the packed weights: lets the candidate pass skip a query's lowest-weight terms
+            tmax = torch.empty(self.vocab, dtype=torch.int32, device=self.device)
+            _lib.check(_lib.lib().ezr_bm25_term_max(_lib.ptr(self.indptr), _lib.ptr(pk), self.vocab, _lib.ptr(tmax),
+                                                    _lib.stream_ptr()), "ezr_bm25_term_max")
+        self.post_pk, self.pk_scale_log2, self.term_max = pk, int(e.value), tmax
 
     def refresh_struct(self):
         s = _lib.Bm25IndexStruct()
@@ -219,6 +223,7 @@ class Bm25Index:
         s.monotone = int(self.monotone)
         s.pk_scale_log2 = int(self.pk_scale_log2)
         s.post_pk = self.post_pk.data_ptr() if self.post_pk is not None else None
+        s.term_max = self.term_max.data_ptr() if getattr(self, "term_max", None) is not None else None
         self._struct = s
 
     def ordered_view(self) -> "Bm25Index":
@@ -227,7 +232,7 @@ class Bm25Index:
         import copy
         v = copy.copy(self)
         v._packed_opt = False
-        v.post_pk, v.pk_scale_log2 = None, 0
+        v.post_pk, v.pk_scale_log2, v.term_max = None, 0, None
         v._struct = None
         v.refresh_struct()
         return v
@@ -244,7 +249,7 @@ class Bm25Index:
     def index_bytes(self) -> int:
         return (self.post_doc.numel() * 4 + self.post_w.numel() * self.post_w.element_size()
                 + self.range_off.numel() * 4 + self.indptr.numel() * 8
-                + (self.post_pk.numel() * 4 if self.post_pk is not None else 0))
+                + (self.post_pk.numel() * 4 + self.term_max.numel() * 4 if self.post_pk is not None else 0))
 
     # ---- on-disk format (the reference rebuilds the BM25 index in RAM on every start,
     # retrievers.py:98-118).  A directory of .npy arrays + meta.json; loading needs no tokenisation and no log().

@@ -75,6 +75,8 @@ typedef struct ezr_bm25_index {
     int32_t pk_scale_log2;     /* e of ezr_bm25_pack (informational) */
     const uint32_t* post_pk;   /* [n_postings] packed postings from ezr_bm25_pack, or NULL: enables the two-phase
                                   top-k (integer candidate pass + exact float64 rescoring) for F64 / monotone / k<=32 */
+    const uint32_t* term_max;  /* [vocab] from ezr_bm25_term_max, or NULL: lets the candidate pass skip the posting
+                                  lists of a query's lowest-weight terms (MaxScore); results are unchanged */
 } ezr_bm25_index;
 
 /* documents per range the library was built for (the `range_size` an index must use) */
@@ -100,6 +102,15 @@ int ezr_bm25_range_index(const int64_t* indptr, const int32_t* post_doc, int32_t
  * scratch16: 16 bytes of device memory.  Synchronises the stream (index-build time). */
 int ezr_bm25_pack(const int32_t* post_doc, const double* post_w, int64_t n_postings, int32_t range_size,
                   uint32_t* out_pk, int32_t* out_scale_log2, void* scratch16, void* stream);
+
+/* out_term_max[t] = largest packed weight among term t's postings (0 for an empty list). */
+int ezr_bm25_term_max(const int64_t* indptr, const uint32_t* post_pk, int32_t vocab, uint32_t* out_term_max,
+                      void* stream);
+
+/* 1: the candidate pass of ezr_bm25_topk may skip non-essential terms when the index carries term_max;
+ * 0 (default): it reads every posting.  Results are identical either way; on the measured workload the extra
+ * candidates cost more rescoring time than the skipped postings save (profiles/README.md), hence the default. */
+int ezr_bm25_set_skipping(int32_t on);
 
 /* candidates per query the two-phase path can hold before it hands a query to the ordered kernel (0: not built) */
 int ezr_bm25_cand_capacity(void);

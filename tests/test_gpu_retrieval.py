@@ -217,7 +217,15 @@ def test_bm25_two_phase_equals_ordered_kernel_and_oracle():
         rb = batched.bm25_topk(b, ptr, terms, k, id_base=1000)
         assert _topk_bytes(ra) == _topk_bytes(rb)
         _check_bm25_topk(ra, rows, k, id_base=1000)
+        # the same with the (default-off) skipping of non-essential terms: fewer postings read, same result
+        _lib.check(_lib.lib().ezr_bm25_set_skipping(1))
+        try:
+            rc = batched.bm25_topk(a, ptr, terms, k, id_base=1000)
+        finally:
+            _lib.check(_lib.lib().ezr_bm25_set_skipping(0))
+        assert _topk_bytes(rc) == _topk_bytes(ra)
     _lib.lib().ezr_profile_enable(0)
+    assert a.term_max is not None and int(a.term_max.max()) < (1 << 18)
     g = groups.numpy()
     want = np.array([i % 7 - 1 for i in range(len(lists))], dtype=np.int32)      # 5 = no such class
     allowed = [None if w == -1 else (g == w) for w in want]
