@@ -58,6 +58,9 @@ constexpr int kPkListCap = EZR_BM25_CAND_CAP;             // candidates per quer
 #endif
 constexpr int kPkNeNum = EZR_BM25_PK_NE_NUM;             // tokens worth up to NUM/10 of the bound may be skipped (0: off)
 constexpr int kPkNeDen = 10;
+#ifndef EZR_BM25_PK_VOTE_EACH
+#define EZR_BM25_PK_VOTE_EACH 0
+#endif
 #ifndef EZR_BM25_PK_BRANCHY
 #define EZR_BM25_PK_BRANCHY 0
 #endif
@@ -236,6 +239,7 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
             uint32_t x[kPkUnroll];
 #pragma unroll
             for (int u = 0; u < kPkUnroll; ++u) x[u] = (o0 + u * 32 < jl) ? __ldg(src + u * 32) : 0u;
+#if EZR_BM25_PK_VOTE_EACH    // A/B switch: one warp vote per posting slot (the first version)
 #pragma unroll
             for (int u = 0; u < kPkUnroll; ++u) {
                 const bool crossed = apply(x[u]);
@@ -243,6 +247,18 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
                     if (crossed) push(x[u]);
                 }
             }
+#else
+            // one vote per work item: crossings are collected in a bit mask; the (rare) push path re-reads its
+            // posting instead of keeping all loaded words live across the vote
+            unsigned crossed = 0u;
+#pragma unroll
+            for (int u = 0; u < kPkUnroll; ++u) crossed |= (apply(x[u]) ? 1u : 0u) << u;
+            if (__any_sync(0xffffffffu, crossed != 0u)) {
+#pragma unroll 1
+                for (int u = 0; u < kPkUnroll; ++u)
+                    if ((crossed >> u) & 1u) push(__ldg(src + u * 32));
+            }
+#endif
         }
     }
     __syncthreads();                                     // every contribution of this (query, range) is in acc
