@@ -17,7 +17,7 @@ import json
 import math
 import os
 from dataclasses import dataclass
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 import torch
