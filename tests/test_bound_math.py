@@ -124,3 +124,74 @@ def test_skipping_lowest_weight_tokens_keeps_the_superset(case, k):
         keep = q_ess >= max(bound - 1 - ne, 1)
         assert keep[ids].all()
     assert skipped_any > 0
+
+
+def _chunks(n_ranges):
+    """Range chunks of pk_launch (bm25.cu): 4, 4, 8, 16, ... with no tiny last chunk."""
+    out, r0, span = [], 0, 4
+    while r0 < n_ranges:
+        ln = min(n_ranges - r0, span)
+        if n_ranges - (r0 + ln) < span // 2:
+            ln = n_ranges - r0
+        out.append((r0, r0 + ln))
+        r0 += ln
+        if r0 > 4:
+            span *= 2
+    return out
+
+
+@pytest.mark.parametrize("skipping", [False, True])
+def test_chunked_bound_protocol_never_loses_a_topk_document(case, skipping):
+    """Python model of bm25_cand_kernel + bm25_bound_kernel over many small ranges: running bound B, candidates with
+    lower/upper bounds (L, U), pruning by U between chunks, non-essential tokens chosen from the updated bound."""
+    o, e, lists = case
+    k, R, num, den = 10, 256, 3, 10
+    n_ranges = -(-o.corpus_size // R)
+    assert len(_chunks(n_ranges)) >= 4 and sum(b - a for a, b in _chunks(n_ranges)) == n_ranges
+    pruned_total = skipped_total = 0
+    for tokens in lists:
+        m = len(tokens)
+        s = o.get_scores(tokens)
+        ids, _ = ort.bm25_topk_ids(s, k, None)
+        q_full, _ = _int_scores(o, e, tokens)
+        gm = [int(_packed(o, t, e).max()) if (0 <= t < o.idf.shape[0] and o.df[t] > 0) else 0 for t in tokens]
+        bound, skip, ne = 0, set(), 0
+        cand = {}                                          # doc -> (L, U)
+        for c0, c1 in _chunks(n_ranges):
+            q_ess = _int_scores(o, e, tokens, skip=skip)[0] if skip else q_full
+            for r in range(c0, c1):
+                lo, hi = r * R, min((r + 1) * R, o.corpus_size)
+                if bound > 0:                              # track mode: crossing threshold B - 1 - NE
+                    thr = max(bound - 1 - ne, 1)
+                    new = [d for d in range(lo, hi) if q_ess[d] >= thr]
+                    vals = sorted((int(q_ess[d]) for d in new), reverse=True)
+                    if len(vals) >= k:
+                        bound = max(bound, vals[k - 1] - m - 1)
+                else:                                      # no bound yet: this range's own k-th best, all tokens read
+                    vals = np.sort(q_full[lo:hi])[::-1]
+                    bl = int(vals[k - 1]) - m - 1 if (vals > 0).sum() >= k else 0
+                    thr = max(bl - 1, 1)
+                    new = [d for d in range(lo, hi) if q_full[d] >= thr]
+                    bound = max(bound, bl)
+                for d in new:
+                    lval = int(q_ess[d]) if skip else int(q_full[d])
+                    cand[d] = (lval, lval + (ne if skip else 0))
+            if len(cand) >= k:                             # bm25_bound_kernel
+                kth = sorted((lu[0] for lu in cand.values()), reverse=True)[k - 1]
+                b = max(kth - (m + 1), bound)
+                before = len(cand)
+                cand = {d: lu for d, lu in cand.items() if lu[1] >= b - 1}
+                pruned_total += before - len(cand)
+                bound = b
+                if skipping and b > 1 and m <= 32:
+                    budget = (b - 1) * num // den
+                    skip, ne = set(), 0
+                    for j in sorted(range(m), key=lambda j: (gm[j], j)):
+                        if ne + gm[j] <= budget:
+                            ne += gm[j]
+                            skip.add(j)
+                        else:
+                            break
+                    skipped_total += len(skip)
+        assert set(ids.tolist()) <= set(cand), (tokens, sorted(set(ids.tolist()) - set(cand)))
+    assert pruned_total > 0 and (skipped_total > 0) == skipping
