@@ -1,5 +1,6 @@
 """CPU: host-side logic of the product + the C-ABI library loads and exports every declared symbol."""
 import ctypes
+import os
 import re
 from pathlib import Path
 
@@ -144,3 +145,27 @@ def test_rerank_handoff_slices_like_the_reference():
     import pytest
     with pytest.raises(ValueError):
         list(handoff.rerank_batches(nodes, "q", batch_size=0))
+
+
+def test_ctypes_struct_layout_matches_the_c_header(tmp_path):
+    # ezr_bm25_index crosses the boundary by pointer: the ctypes mirror must have the C compiler's layout.
+    import ctypes
+    import shutil
+    import subprocess
+    from easyrag_b200 import _lib
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    fields = [name for name, _ in _lib.Bm25IndexStruct._fields_]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{root}/include/easyrag_b200.h"', 'int main(void) {',
+             '  printf("%zu\\n", sizeof(ezr_bm25_index));']
+    lines += [f'  printf("%zu\\n", offsetof(ezr_bm25_index, {f}));' for f in fields]
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.Bm25IndexStruct)
+    assert out[1:] == [getattr(_lib.Bm25IndexStruct, f).offset for f in fields]
