@@ -129,9 +129,9 @@ __global__ void bm25_term_max_kernel(const int64_t* __restrict__ indptr, const u
 }
 
 // ---- phase 1 ----
-// One CTA per (query, document range).  Work is dealt to warps in 128-posting pieces over ALL terms of the query
-// (a warp's lanes each hold one term's segment; ballot + shuffles map a piece number to its term), so a warp only
-// executes code for pieces that exist: no per-term pass over empty segments, no ordering, one barrier before the
+// One CTA per (query, document range).  Work is dealt to warps in pieces of kPkPiece postings (256 by default) over
+// ALL terms of the query (a warp's lanes each hold one term's segment; ballot + shuffles map a piece number to its
+// term), so a warp only executes code for pieces that exist: no per-term pass over empty segments, no ordering, one barrier before the
 // atomics and one after.
 constexpr int kPkWarps = kPkThreads / 32;
 constexpr int kPkUnroll = EZR_BM25_PK_UNROLL;                             // loads a lane keeps in flight
