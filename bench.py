@@ -1,27 +1,36 @@
 #!/usr/bin/env python
 """Benchmark of the coarse-ranking hot path: queries/sec, dense + BM25 + RRF top-10 over 1M x 768 chunks.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload retrieve|encode]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 Workload = BASELINE.json configs[2] ("dense+BM25 dual-route + RRF fusion top-10, 1M chunks, 10k queries",
 the configuration the metric is quoted on); at N > 1 the SAME corpus is row-sharded (configs[3]) -> strong
-scaling.  One step = one pass of the hot path over the whole batch of 10k synthetic queries.
+scaling.  One step = one pass of the hot path over the whole batch of synthetic queries (10k by default;
+``--queries 64`` is the HBM-bound small-batch regime of SURVEY.md 8(d), configs[4] adds ``--rows 4000000 --dim 1024``).
 
-  value : whole-job queries/s with query vectors + term ids resident in HBM when the timed region starts.
-  e2e   : same metric through the public batched API from pinned HOST buffers, H2D of the queries and D2H of
-          the fused (id, score) lists inside the timed region.
-  roofline : dominant kernel, algorithmic bytes / CUDA-event duration on its launch stream.
+  value : whole-job queries/s with query vectors + term ids resident in HBM when the timed region starts; the
+          two routes run on two streams (``--overlap 1``, the product default).
+  e2e   : same metric through the public host-buffer API (``batched.HostPipeline``): pinned HOST inputs, H2D of
+          the queries / term ids and D2H of the fused (id, score) lists inside the timed region, every step.
+  roofline : dominant kernel, algorithmic FLOPs or bytes / CUDA-event duration on its launch stream, taken from
+          ``--cal-steps`` NON-overlapped calibration steps of the same run (with the routes co-resident a kernel's
+          event time would include the other route's share of the SM); the overlapped durations are listed too.
+  parity_full_size : after timing, the first ``--parity-queries`` queries of the measured workload are compared with
+          the CPU oracle over the FULL corpus: BM25 ids + float64 score bits identical, dense scores within 1e-3 of
+          the fp32 cosine (ids equal outside near-ties), RRF identical; a digest of all fused results pins N>1 == N=1.
   cpu_baseline : the oracle port of the reference's CPU retrievers (numpy BM25Okapi restatement + full argsort,
           fp32 BLAS cosine, Python RRF) on a bounded query sample over the same corpus, on this box's cores.
 
 ``--impl reference`` prints the CPU arm as its own line (rank 0 only under torchrun).
+``--workload encode`` measures the chunk-embedding forward pass (configs[1]) instead; see bench_encode.py.
 Nothing here reads /root/reference.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -39,6 +48,8 @@ sys.path.insert(0, str(ROOT))
 
 SEED = 20240922 + 3
 METRIC = "queries/sec dense+BM25+RRF top-10 over 1M x 768 chunks"
+DENSE_TOL = 1e-3            # north star: cosine scores within 1e-3 for bf16 embeddings
+DIGEST_FILE = ROOT / "tests" / "golden" / "bench_digest.json"
 
 
 def parse():
@@ -47,20 +58,29 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="retrieve", choices=["retrieve", "encode"])
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--vocab", type=int, default=200_000)
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--cpu-queries", type=int, default=256, help="bounded sample for the CPU baseline (~15 s)")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-queries", type=int, default=256, help="bounded sample for the CPU baseline (~12 s a step)")
+    ap.add_argument("--ref-queries", type=int, default=64,
+                    help="--impl reference: queries per step (a bounded sample so that K + W steps end in minutes)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (parity still runs)")
+    ap.add_argument("--parity-queries", type=int, default=256,
+                    help="queries compared with the CPU oracle over the full corpus after timing (0 = off)")
     ap.add_argument("--dense-kernel", type=int, default=0, help="0 auto, 1 simt, 2 tcgen05 SS, 3 tcgen05 TS")
-    ap.add_argument("--overlap", type=int, default=0, help="1: dense and BM25 routes on two streams")
+    ap.add_argument("--overlap", type=int, default=1, help="1 (default): dense and BM25 routes on two streams")
+    ap.add_argument("--cal-steps", type=int, default=5, help="non-overlapped calibration steps for per-kernel times")
     ap.add_argument("--self-check", type=int, default=64,
                     help="after timing: first N queries through both BM25 kernel paths at full size, compared bit for bit")
     ap.add_argument("--bm25-skip", type=int, default=0, help="1: candidate pass skips non-essential terms (A/B)")
     ap.add_argument("--dense-probe", type=int, default=0, help="measurement probe of the dense kernel (results invalid)")
-    ap.add_argument("--dense-stages", type=int, default=0, help="cap of the dense kernel's TMA ring (0 = all smem)")
+    ap.add_argument("--dense-stages", type=int, default=-1,
+                    help="cap of the dense kernel's TMA ring (0 = all smem; -1 = 3 with --overlap 1, else 0)")
+    ap.add_argument("--l2-flush", type=int, default=-1,
+                    help="1: write a 512 MB buffer between steps and time each step on its own (default for <= 512 queries)")
     return ap.parse_args()
 
 
@@ -139,6 +159,24 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------- CPU reference
+def canonical_topk(score: np.ndarray, k: int, positive_only: bool):
+    """Top-k of a score vector under the canonical order (score desc, id desc) without a full sort, plus the tie
+    flags SURVEY.md 8(c) asks for: (ids, scores, tie inside the top-k, tie straddling the k-th / (k+1)-th place)."""
+    n = score.shape[0]
+    kk = min(k + 1, n)
+    top = np.sort(score[np.argpartition(score, n - kk)[n - kk:]])[::-1]     # the k+1 largest values, descending
+    v_k = top[min(k, n) - 1]
+    cand = np.nonzero(score >= v_k)[0]                                      # everything tied with the k-th or better
+    order = cand[np.lexsort((-cand, -score[cand]))][:k]
+    sc = score[order]
+    if positive_only:                                                       # retrievers.py:195-196
+        keep = sc > 0
+        order, sc = order[keep], sc[keep]
+    inside = bool(sc.size > 1 and np.any(sc[1:] == sc[:-1]))
+    straddle = bool(kk > k and top[k] == top[k - 1] and (top[k - 1] > 0 or not positive_only) and sc.size == k)
+    return order.astype(np.int64), sc, inside, straddle
+
+
 class CpuReference:
     """Oracle port of the reference's CPU retrievers over the full corpus (kind = "port").
 
@@ -166,25 +204,45 @@ class CpuReference:
         self.cores = os.cpu_count()
         torch.set_num_threads(self.cores)
 
+    def bm25_scores(self, qi: int) -> np.ndarray:
+        score = np.zeros(self.n)
+        for t in self.term_lists[qi]:
+            if t < 0 or self.idf[t] == 0.0:
+                continue
+            s, e = self.indptr[t], self.indptr[t + 1]
+            tf = self.post_tf[s:e]
+            d = self.post_doc[s:e]
+            score[d] += self.idf[t] * (tf * 2.5 / (tf + self.K_d[d]))
+        return score
+
     def run(self, lo: int, hi: int):
+        """The timed CPU arm: literal control flow of the reference (full argsort per query)."""
         k = self.k
         sims = (self.qvec[lo:hi] @ self.vec.T).numpy()
         out = []
         for j, qi in enumerate(range(lo, hi)):
-            score = np.zeros(self.n)
-            for t in self.term_lists[qi]:
-                if t < 0 or self.idf[t] == 0.0:
-                    continue
-                s, e = self.indptr[t], self.indptr[t + 1]
-                tf = self.post_tf[s:e]
-                d = self.post_doc[s:e]
-                score[d] += self.idf[t] * (tf * 2.5 / (tf + self.K_d[d]))
+            score = self.bm25_scores(qi)
             order = score.argsort()[::-1]                                   # retrievers.py:192
             sparse = [int(i) for i in order[:k] if score[i] > 0]
             part = np.argpartition(-sims[j], k)[:k]
             dense = [int(i) for i in part[np.argsort(-sims[j][part], kind="stable")]]
             out.append(self.ort.rrf_ids([sparse, dense], None, K=60, topk=k))
         return out
+
+    def collect(self, lo: int, hi: int):
+        """The parity arm (untimed): the same arithmetic with the canonical tie order and everything the comparison
+        with the GPU lists needs.  Returns per query a dict(sparse_ids, sparse_sc, dense_ids, dense_sc, fused_ids,
+        fused_sc, ties) and the fp32 similarity matrix of these queries."""
+        k = self.k
+        sims = (self.qvec[lo:hi] @ self.vec.T).numpy()
+        out = []
+        for j, qi in enumerate(range(lo, hi)):
+            s_ids, s_sc, inside, straddle = canonical_topk(self.bm25_scores(qi), k, positive_only=True)
+            d_ids, d_sc, d_in, d_str = canonical_topk(sims[j], k, positive_only=False)
+            f_ids, f_sc = self.ort.rrf_ids([s_ids, d_ids], None, K=60, topk=k)
+            out.append(dict(sparse_ids=s_ids, sparse_sc=s_sc, dense_ids=d_ids, dense_sc=d_sc, fused_ids=f_ids,
+                            fused_sc=f_sc, bm25_tie=inside or straddle, dense_tie=d_in or d_str))
+        return out, sims
 
     def measure(self, n_queries: int, steps: int = 1, warmup: int = 0):
         n_queries = min(n_queries, len(self.term_lists))
@@ -197,8 +255,73 @@ class CpuReference:
         return steps * n_queries / dt, dt / steps
 
 
+def parity_full_size(ref: CpuReference, nq: int, fused, sparse, dense, k: int):
+    """GPU lists (torch tensors, first ``nq`` queries over the full corpus, global ids) against the CPU oracle."""
+    ora, sims = ref.collect(0, nq)
+    f_ids, f_sc, f_cnt = fused.ids.cpu().numpy(), fused.scores.cpu().numpy(), fused.counts.cpu().numpy()
+    s_ids, s_sc, s_cnt = sparse.ids.cpu().numpy(), sparse.scores.cpu().numpy(), sparse.counts.cpu().numpy()
+    d_ids, d_sc = dense.ids.cpu().numpy(), dense.scores.cpu().numpy()
+    bm25_ok = dense_ids_equal = rrf_ok = lists_identical = near_tie_swaps = 0
+    dense_max_abs, dense_ok = 0.0, True
+    first_bad = None
+    for i, o in enumerate(ora):
+        c = int(s_cnt[i])
+        b_ok = (c == o["sparse_ids"].size and np.array_equal(s_ids[i, :c], o["sparse_ids"])
+                and s_sc[i, :c].tobytes() == o["sparse_sc"].tobytes())
+        bm25_ok += b_ok
+        g = d_ids[i]
+        diff = float(np.abs(d_sc[i].astype(np.float64) - sims[i][g].astype(np.float64)).max())
+        dense_max_abs = max(dense_max_abs, diff)
+        same = np.array_equal(g, o["dense_ids"])
+        dense_ids_equal += same
+        if not same:
+            # allowed only as a near-tie: every oracle id the GPU list lacks scores within tol of the GPU's k-th,
+            # every GPU id the oracle list lacks scores within tol of the oracle's k-th
+            miss = np.setdiff1d(o["dense_ids"], g)
+            extra = np.setdiff1d(g, o["dense_ids"])
+            ok = (np.all(sims[i][miss] <= d_sc[i].min() + DENSE_TOL) and np.all(sims[i][extra] >= o["dense_sc"].min() - DENSE_TOL)
+                  and set(g.tolist()) - set(extra.tolist()) == set(o["dense_ids"].tolist()) - set(miss.tolist()))
+            near_tie_swaps += int(ok)
+            dense_ok &= bool(ok)
+        dense_ok &= diff <= DENSE_TOL
+        # fusion at full size: the oracle's RRF over the lists the GPU produced must equal the GPU's fused list
+        r_ids, r_sc = ref.ort.rrf_ids([s_ids[i, :c], g], None, K=60, topk=k)
+        fc = int(f_cnt[i])
+        r_ok = fc == r_ids.size and np.array_equal(f_ids[i, :fc], r_ids) and f_sc[i, :fc].tobytes() == r_sc.tobytes()
+        rrf_ok += r_ok
+        ident = b_ok and same
+        lists_identical += ident
+        if ident and r_ok:
+            assert np.array_equal(r_ids, o["fused_ids"])
+        if first_bad is None and not (b_ok and r_ok):
+            first_bad = i
+    res = {"queries": nq, "corpus_rows": ref.n, "bm25_bit_exact": bm25_ok == nq, "bm25_queries_bit_exact": int(bm25_ok),
+           "dense_max_abs": dense_max_abs, "dense_tol": DENSE_TOL, "dense_within_tol": bool(dense_ok),
+           "dense_ids_equal": int(dense_ids_equal), "dense_near_tie_swaps": int(near_tie_swaps),
+           "rrf_equal": rrf_ok == nq, "fused_lists_identical_to_oracle": int(lists_identical),
+           "ties_in_or_straddling_topk": {"bm25": int(sum(o["bm25_tie"] for o in ora)),
+                                          "dense": int(sum(o["dense_tie"] for o in ora))},
+           "oracle": "oracle port (numpy BM25Okapi restatement, fp32 BLAS cosine, Python RRF), canonical tie order"}
+    res["ok"] = bool(res["bm25_bit_exact"] and res["dense_within_tol"] and res["rrf_equal"])
+    if first_bad is not None:
+        res["first_bad_query"] = int(first_bad)
+    return res
+
+
+def fused_digest(fused) -> str:
+    """sha256 over (counts, ids, float64 score bits) of every fused list of the step."""
+    h = hashlib.sha256()
+    for t in (fused.counts, fused.ids, fused.scores):
+        h.update(np.ascontiguousarray(t.cpu().numpy()).tobytes())
+    return h.hexdigest()
+
+
+def digest_key(args) -> str:
+    return f"rows={args.rows},dim={args.dim},vocab={args.vocab},queries={args.queries},k={args.k},seed={SEED}"
+
+
 # ------------------------------------------------------------------------------ our arm
-def algorithmic_bytes(args, data, index, n_rows_local, n_slices_q):
+def algorithmic_bytes(args, data, index, n_rows_local):
     """Per-step algorithmic bytes of the two dominant kernels (DESIGN.md section 'Measurement')."""
     q = data["queries"]
     terms = q.terms.to(index.device).long()
@@ -210,7 +333,11 @@ def algorithmic_bytes(args, data, index, n_rows_local, n_slices_q):
     bm25_cand = postings * 4 + args.queries * args.k * 4
     passes = -(-args.queries // 128)
     dense = passes * n_rows_local * args.dim * 2 + args.queries * args.dim * 2 + args.queries * args.k * 8
-    return {"bm25_score": bm25, "bm25_cand": bm25_cand, "dense_tc": dense, "postings_per_step": postings, "dense_passes": passes}
+    return {"bm25_score": bm25, "bm25_cand": bm25_cand, "dense_tc": dense, "postings_per_step": postings,
+            "dense_passes": passes}
+
+
+PROF_NAMES = ("bm25_cand", "bm25_rescore", "bm25_score", "dense_tc", "dense_simt", "merge", "fuse")
 
 
 def run_ours(args):
@@ -231,20 +358,26 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_cuda()
     L = _lib.lib()
+    small_batch = args.queries <= 512
+    overlap = bool(args.overlap)
+    stage_cap = args.dense_stages if args.dense_stages >= 0 else (3 if overlap and not small_batch else 0)
+    l2_flush = bool(args.l2_flush) if args.l2_flush >= 0 else small_batch
     _lib.check(L.ezr_dense_set_kernel(args.dense_kernel))
-    _lib.check(L.ezr_dense_set_stage_cap(args.dense_stages))
+    _lib.check(L.ezr_dense_set_stage_cap(stage_cap))
     _lib.check(L.ezr_dense_set_probe(args.dense_probe))
     _lib.check(L.ezr_bm25_set_skipping(args.bm25_skip))
 
     data = make_data(args, dev)
-    lo, hi = ezdist.shard_bounds(args.rows, world, rank, align=8192)
+    lo, hi = ezdist.shard_bounds(args.rows, world, rank, align=64)
     t0 = time.time()
     sparse = Bm25Index(data["stats"], device=dev, doc_lo=lo, doc_hi=hi)
     dense = DenseIndex(data["vec"][lo:hi], device=dev, row_lo=lo)
     torch.cuda.synchronize()
     build_s = time.time() - t0
-    ranker = batched.CoarseRanker(dense, sparse, canon=None, overlap=bool(args.overlap))
+    ranker = batched.CoarseRanker(dense, sparse, canon=None, overlap=overlap)
+    ranker_seq = batched.CoarseRanker(dense, sparse, canon=None, overlap=False)       # calibration: one stream
     sharded = ezdist.ShardedCoarseRanker(ranker) if world > 1 else None
+    sharded_seq = ezdist.ShardedCoarseRanker(ranker_seq) if world > 1 else None
     k = args.k
     q = data["queries"]
     d_qvec = data["qvec"].contiguous()
@@ -253,110 +386,149 @@ def run_ours(args):
     h_ptr, h_terms = q.term_ptr.cpu().pin_memory(), q.terms.cpu().pin_memory()
     h_ids = torch.empty(args.queries, k, dtype=torch.int32).pin_memory()
     h_sc = torch.empty(args.queries, k, dtype=torch.float64).pin_memory()
-    e_qvec, e_ptr, e_terms = torch.empty_like(d_qvec), torch.empty_like(d_ptr), torch.empty_like(d_terms)
+    pipe = batched.HostPipeline(sharded if sharded is not None else ranker, args.queries, args.dim,
+                                int(h_terms.numel()), k, k)
+
+    def hybrid(r, s, qv, qp, qt):
+        if s is not None:
+            return s.hybrid(qv, qp, qt, k=k, k_out=k)
+        return r.hybrid(qv, qp, qt, k, k, k)
 
     def step_device():
-        if sharded is not None:
-            return sharded.hybrid(d_qvec, d_ptr, d_terms, k=k, k_out=k)[0]
-        return ranker.hybrid(d_qvec, d_ptr, d_terms, k, k, k)[0]
+        return hybrid(ranker, sharded, d_qvec, d_ptr, d_terms)[0]
+
+    def step_cal():
+        return hybrid(ranker_seq, sharded_seq, d_qvec, d_ptr, d_terms)[0]
 
     def step_e2e():
-        e_qvec.copy_(h_qvec, non_blocking=True)
-        e_ptr.copy_(h_ptr, non_blocking=True)
-        e_terms.copy_(h_terms, non_blocking=True)
-        if sharded is not None:
-            f = sharded.hybrid(e_qvec, e_ptr, e_terms, k=k, k_out=k)[0]
-        else:
-            f = ranker.hybrid(e_qvec, e_ptr, e_terms, k, k, k)[0]
-        h_ids.copy_(f.ids, non_blocking=True)
-        h_sc.copy_(f.scores, non_blocking=True)
+        pipe.step(h_qvec, h_ptr, h_terms, h_ids, h_sc)
 
-    def timed(fn, steps):
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if l2_flush else None
+
+    def timed(fn, steps, drain=None):
+        """K steps bracketed by barrier + synchronize, max over ranks.  With --l2-flush every step is timed on its
+        own (CUDA events around it) and a 512 MB write between steps evicts the L2; the sum of the steps counts."""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if flush_buf is None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            if drain is not None:
+                drain()
+            b.record()
+            torch.cuda.synchronize()
+            per = None
+            total = a.elapsed_time(b)
+        else:
+            evs = []
+            for _ in range(steps):
+                flush_buf.fill_(1)
+                if world > 1:
+                    dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                if drain is not None:
+                    drain()
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            per = [x.elapsed_time(y) for x, y in evs]
+            total = sum(per)
+        ms = torch.tensor([total], device=dev)
         if world > 1:
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), per
+
+    def read_prof():
+        return {name: _lib.profile_read(name) for name in PROF_NAMES}
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
+        step_cal()
         step_device()
     torch.cuda.synchronize()
+    # ---- calibration: the routes back to back on one stream, per-kernel CUDA events (roofline durations)
     _lib.check(L.ezr_profile_reset())
     _lib.check(L.ezr_profile_enable(1))
+    ms_cal, _ = timed(step_cal, max(args.cal_steps, 1))
+    prof = read_prof()
+    dense_kernel_name = L.ezr_dense_last_kernel().decode()
+    # ---- timed region 1: device-resident inputs, product path
+    _lib.check(L.ezr_profile_reset())
     launches0 = L.ezr_launch_count()
     sampler.begin()
-    ms = timed(step_device, args.steps)
+    ms, per_step = timed(step_device, args.steps)
     sampler.end()
     launches_timed = L.ezr_launch_count() - launches0
+    prof_timed = read_prof()
     _lib.check(L.ezr_profile_enable(0))
-    prof = {name: _lib.profile_read(name) for name in ("bm25_cand", "bm25_rescore", "bm25_score", "dense_tc",
-                                                       "dense_simt", "merge", "fuse")}
+    last = hybrid(ranker, sharded, d_qvec, d_ptr, d_terms)      # results of the measured configuration, all queries
+    torch.cuda.synchronize()
+    digest = fused_digest(last[0])
+    # ---- timed region 2: host buffers in, host buffers out, through the public pipeline API
     for _ in range(2):
         step_e2e()
+    pipe.drain()
     sampler.begin()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e, per_step_e2e = timed(step_e2e, args.steps, drain=pipe.drain)
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
+    # what the host-buffer API delivered must be what the device path computed
+    e2e_digest_ok = bool(np.array_equal(h_ids.numpy(), last[0].ids.cpu().numpy())
+                         and h_sc.numpy().tobytes() == last[0].scores.cpu().numpy().tobytes())
 
-    # Full-size property check outside the timed regions: the two-phase path (integer candidates + exact
-    # rescoring) and the ordered float64 kernel are independent implementations; on this shard they must return
-    # the same ids, scores and counts bit for bit.
+    # ---- full-size parity against the CPU oracle (outside the timed regions; every rank joins the GPU call)
+    parity, ref = None, None
+    if args.parity_queries > 0 and args.dense_probe == 0:
+        nq = min(args.parity_queries, args.queries)
+        qp = q.term_ptr[:nq + 1].to(dev)
+        f, s, d = hybrid(ranker, sharded, d_qvec[:nq], qp, d_terms)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref = CpuReference(data, args)
+            parity = parity_full_size(ref, nq, f, s, d, k)
+
+    # Full-size property check: the two-phase path (integer candidates + exact rescoring) and the ordered float64
+    # kernel are independent implementations; on this shard they must return the same ids, scores and counts.
     self_check = None
     if args.self_check > 0 and sparse.post_pk is not None and args.dense_probe == 0:
         nq = min(args.self_check, args.queries)
-        qp = data["queries"].term_ptr[:nq + 1].to(dev)
-        qt = data["queries"].terms.to(dev)
-        a = batched.bm25_topk(sparse, qp, qt, k)
-        b = batched.bm25_topk(sparse.ordered_view(), qp, qt, k)
+        qp = q.term_ptr[:nq + 1].to(dev)
+        a = batched.bm25_topk(sparse, qp, d_terms, k)
+        b = batched.bm25_topk(sparse.ordered_view(), qp, d_terms, k)
         torch.cuda.synchronize()
         same = bool(torch.equal(a.ids, b.ids) and torch.equal(a.counts, b.counts)
                     and torch.equal(a.scores.view(torch.int64), b.scores.view(torch.int64)))
         self_check = {"bm25_two_phase_equals_ordered": same, "queries": nq, "postings_local": sparse.n_postings}
         if not same:
             raise SystemExit(f"bench.py self-check FAILED on rank {rank}: BM25 kernel paths disagree")
-        # dense route: the tcgen05 kernel against the generic fp32 SIMT kernel + row selection over the full shard;
-        # different accumulation orders, so the bar is the north star's cosine tolerance on the sorted score lists
-        if k <= 16:
-            r_tc = batched.dense_topk(dense, d_qvec[:nq], k)
-            tc_name = L.ezr_dense_last_kernel().decode()
-            _lib.check(L.ezr_dense_set_kernel(1))
-            try:
-                r_simt = batched.dense_topk(dense, d_qvec[:nq], k)
-            finally:
-                _lib.check(L.ezr_dense_set_kernel(args.dense_kernel))
-            torch.cuda.synchronize()
-            diff = float((r_tc.scores - r_simt.scores).abs().max())
-            agree = float((r_tc.ids == r_simt.ids).float().mean())
-            self_check.update({"dense_kernel": tc_name, "dense_vs_simt_max_abs_score_diff": diff,
-                               "dense_vs_simt_id_agreement": agree, "dense_tol": 1e-3})
-            if not diff <= 1e-3:
-                raise SystemExit(f"bench.py self-check FAILED on rank {rank}: dense kernels differ by {diff}")
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
+
     peaks = {}
     pk_file = ROOT / "MEASURED_PEAKS.json"
     if pk_file.exists():
         peaks = json.loads(pk_file.read_text())
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    alg = algorithmic_bytes(args, data, sparse, dense.n_rows, None)
-    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    tf_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
-              if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s")
+    alg = algorithmic_bytes(args, data, sparse, dense.n_rows)
+    long_step = ms > 2000.0          # a seconds-long loop settles at the sustained clock
+    tf_key = "bf16_tflops_sustained" if long_step else "bf16_tflops"
+    tf_peak = float(peaks.get(tf_key, 1590.0 if not long_step else 1400.0))
+    tf_src = (f"measured (MEASURED_PEAKS.json {tf_key}: "
+              + ("kernel timed inside a seconds-long loop)" if long_step else "burst figure, the timed loop lasts well under 2 s)")
+              if tf_key in peaks else "fallback")
     dense_flops = 2.0 * dense.n_rows * args.dim * args.queries          # per launch: every query x every local row
     kernels = {}
     two_phase = prof["bm25_cand"][1] > 0
@@ -366,32 +538,39 @@ def run_ours(args):
             avg_ms = tot / n
             kernels[name] = {"launches": n, "avg_ms": avg_ms, "alg_bytes_per_launch": alg[name],
                              "GBps": alg[name] / (avg_ms * 1e-3) / 1e9}
+            t2, n2 = prof_timed[name]
+            if n2:
+                kernels[name]["avg_ms_in_timed_region"] = t2 / n2       # routes co-resident: includes the other route's share
     others = {name: {"launches": prof[name][1], "avg_ms": prof[name][0] / prof[name][1]}
               for name in ("bm25_rescore", "bm25_score", "merge", "fuse") if prof[name][1] and name not in kernels}
     if "dense_tc" in kernels:
-        # The persistent kernel shares each corpus pass between all resident query blocks through L2, so HBM is not
-        # its bound (ncu: DRAM traffic ~ a few corpus passes per launch); it is a [Q x D] . [D x N] contraction on the
-        # tensor pipe.  GBps above is kept as "bytes if every 128-query block streamed the corpus from HBM".
         kernels["dense_tc"]["flops_per_launch"] = dense_flops
         kernels["dense_tc"]["TFLOPs"] = dense_flops / (kernels["dense_tc"]["avg_ms"] * 1e-3) / 1e12
+        kernels["dense_tc"]["queries_per_corpus_pass"] = min(args.queries, 128)
     dom = max(kernels, key=lambda n_: kernels[n_]["avg_ms"]) if kernels else None
     traffic = None
     tfile = ROOT / "profiles" / "traffic.json"
     if tfile.exists() and dom:
-        traffic = json.loads(tfile.read_text()).get(dom)
+        traffic = json.loads(tfile.read_text()).get(dom if not small_batch else dom + "_b64")
+    timing_note = (f"per-kernel durations: CUDA events on the launch stream over {max(args.cal_steps, 1)} calibration "
+                   f"steps with the two routes back to back on one stream (same kernels, same launch shapes as the "
+                   f"timed region); avg_ms_in_timed_region = the same events over the {args.steps} timed steps"
+                   + (", where the routes share the SMs" if overlap else ""))
     roofline = None
-    if dom == "dense_tc":
+    # the dense scan is HBM-bound while queries per corpus pass stay below the ridge (~220)
+    dense_hbm_bound = args.queries <= 220
+    if dom == "dense_tc" and not dense_hbm_bound:
         roofline = {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["TFLOPs"], "peak": tf_peak,
                     "unit": "TFLOP/s", "frac": kernels[dom]["TFLOPs"] / tf_peak, "traffic": traffic,
-                    "peak_source": tf_src, "kernels": kernels}
+                    "peak_source": tf_src, "timing": timing_note, "kernels": kernels}
     elif dom:
+        note = {"dense_tc": "algorithmic bytes = one pass over the corpus shard (N_s x D x 2) + queries + outputs "
+                            "(SURVEY.md 8(d)); B = queries per pass is in config",
+                "bm25_cand": "algorithmic bytes = postings touched (4 B packed word each) + candidate ids",
+                "bm25_score": "algorithmic bytes = postings touched (12 B each) + outputs"}[dom]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom]["GBps"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "kernels": kernels,
-                    "note": ("algorithmic bytes = postings touched (4 B packed word each) + candidate ids"
-                             if dom == "bm25_cand" else "algorithmic bytes = postings touched (12 B each) + outputs")
-                            + "; ncu shows most of them are served from L2 (range-major grid), DRAM traffic per "
-                              "launch is in `traffic`"}
+                    "timing": timing_note, "kernels": kernels, "note": note}
     if roofline:
         roofline["other_kernels"] = others
     value = args.steps * args.queries / (ms * 1e-3)
@@ -400,34 +579,69 @@ def run_ours(args):
     d2h = h_ids.numel() * 4 + h_sc.numel() * 8
     cpu = None
     if world == 1 and not args.no_cpu:
-        ref = CpuReference(data, args)
-        v, dt = ref.measure(args.cpu_queries)
+        if ref is None:
+            ref = CpuReference(data, args)
+        v, dt = ref.measure(args.cpu_queries, steps=1, warmup=0 if parity is not None else 1)
         cpu = {"value": v, "unit": "queries/s", "cores": ref.cores, "kind": "port",
                "sample": f"first {min(args.cpu_queries, args.queries)} of the {args.queries} queries over the full "
-                         f"{args.rows} x {args.dim} corpus, {dt:.1f} s; numpy BM25Okapi restatement + full argsort, "
-                         f"fp32 BLAS cosine, Python RRF"}
+                         f"{args.rows} x {args.dim} corpus, 1 step of {dt:.1f} s after a warm-up pass; numpy BM25Okapi "
+                         f"restatement + full argsort, fp32 BLAS cosine, Python RRF"}
+    # digest of every fused list of the step: identical for every N (configs[3]: "must equal C3 bit-for-bit")
+    dig = {"fused_sha256": digest, "key": digest_key(args), "e2e_results_equal_device_results": e2e_digest_ok,
+           "matches_committed_n1": None}
+    if DIGEST_FILE.exists():
+        want = json.loads(DIGEST_FILE.read_text()).get(dig["key"])
+        if want is not None:
+            dig["matches_committed_n1"] = bool(want["fused_sha256"] == digest)
+            dig["committed_from"] = want.get("from")
+    max_rows = max(b - a for a, b in (ezdist.shard_bounds(args.rows, world, r, align=64) for r in range(world)))
+    step_ms = ms / args.steps
+    seq_ms = ms_cal / max(args.cal_steps, 1)
+    scaling_terms = {
+        "max_shard_rows": max_rows, "ideal_shard_rows": args.rows / world, "imbalance": max_rows / (args.rows / world),
+        "dense_TFLOPs": kernels.get("dense_tc", {}).get("TFLOPs"), "dense_ms": kernels.get("dense_tc", {}).get("avg_ms"),
+        "bm25_cand_ms": kernels.get("bm25_cand", {}).get("avg_ms"),
+        "fixed_ms": seq_ms - sum(kernels[n_]["avg_ms"] for n_ in kernels),
+        "sequential_step_ms": seq_ms, "overlapped_step_ms": step_ms,
+        "note": "fixed_ms = one-stream step minus dense and candidate kernels (rescore, merges, fusion, all-gather, gaps); "
+                "compare the terms across N: imbalance -> 1.0 is balanced, dense_TFLOPs falling = shorter units per CTA"}
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "warmup": n_warm, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16 dense / f64 bm25", "data": "synthetic",
-        "config": {"workload": "configs[2]: dense+BM25 dual-route + RRF top-10, 1M x 768 chunks, 10k queries/step"
+        "config": {"workload": f"configs[2]: dense+BM25 dual-route + RRF top-{k}, {args.rows} x {args.dim} chunks, "
+                               f"{args.queries} queries/step"
                                + (f", row-sharded over {world} GPUs (configs[3])" if world > 1 else ""),
                    "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "queries_per_step": args.queries,
                    "k": k, "rrf_K": 60, "tokens": data["n_tokens"], "postings_local": sparse.n_postings,
-                   "queries_per_corpus_pass": 128, "timed_region_starts_from": "query vectors + term ids",
-                   "l2": "inputs larger than L2 (corpus shard and postings >> 126 MB), no explicit flush",
+                   "queries_per_corpus_pass": min(args.queries, 128), "routes_overlapped": overlap,
+                   "dense_ring_stages_cap": stage_cap, "timed_region_starts_from": "query vectors + term ids",
+                   "l2": ("explicit flush: 512 MB written between steps, every step timed on its own" if l2_flush else
+                          "inputs larger than L2 (corpus shard and postings >> 126 MB), no explicit flush"),
                    "parallelism": f"rows{world}"},
         "e2e": {"value": e2e_v, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "api": "batched.HostPipeline.step: pinned host inputs -> H2D -> both routes -> (all-gather, merge) -> "
+                       "RRF -> D2H into pinned host outputs, every step; copies of step i+1 overlap the kernels of step i"},
         "gpu_launches": int(launches_timed),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "parity_full_size": parity, "digest": dig, "scaling_terms": scaling_terms,
         "setup": {"generate_s": round(data["gen_s"], 1), "index_build_s": round(build_s, 1),
-                  "index_bytes": sparse.index_bytes(), "dense_kernel": L.ezr_dense_last_kernel().decode(),
+                  "index_bytes": sparse.index_bytes(), "dense_kernel": dense_kernel_name,
                   "self_check": self_check},
     }
+    if per_step is not None:
+        line["latency_ms"] = {"median": statistics.median(per_step), "min": min(per_step), "max": max(per_step),
+                              "e2e_median": statistics.median(per_step_e2e) if per_step_e2e else None}
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(f"bench.py parity_full_size FAILED: {json.dumps(parity)}")
+    if dig["matches_committed_n1"] is False:
+        raise SystemExit(f"bench.py digest differs from the committed N=1 digest: {json.dumps(dig)}")
 
 
 def run_reference(args):
@@ -437,15 +651,16 @@ def run_reference(args):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))     # data generation only
     data = make_data(args, dev)
     ref = CpuReference(data, args)
-    n = min(args.cpu_queries, args.queries)
-    v, dt = ref.measure(n, steps=args.steps, warmup=min(args.warmup, 1))
+    n = min(args.ref_queries, args.queries)
+    v, dt = ref.measure(n, steps=args.steps, warmup=args.warmup)
     sample = (f"each step = first {n} of the {args.queries} queries over the full {args.rows} x {args.dim} corpus; "
               f"numpy BM25Okapi restatement + full argsort, fp32 BLAS cosine ({ref.cores} threads), Python RRF")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32 dense / f64 bm25", "data": "synthetic",
-        "config": {"workload": "configs[2]: dense+BM25 dual-route + RRF top-10, 1M x 768 chunks (bounded query sample)",
+        "config": {"workload": f"configs[2]: dense+BM25 dual-route + RRF top-{args.k}, {args.rows} x {args.dim} chunks "
+                               f"(bounded query sample)",
                    "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "queries_per_step": n, "k": args.k},
         "cpu_baseline": {"value": v, "unit": "queries/s", "cores": ref.cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -456,7 +671,10 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "encode":
+        import bench_encode
+        bench_encode.main(from_bench=a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

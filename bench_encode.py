@@ -21,7 +21,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 
-def main():
+def main(from_bench=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--arch", default="bert", choices=["bert", "qwen2"])
     ap.add_argument("--chunks", type=int, default=20_000)
@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--steps", type=int, default=3)
-    args = ap.parse_args()
+    args = ap.parse_known_args()[0]
     from easyrag_b200 import _lib, batched
     from easyrag_b200.encoder import (BertConfig, BertEncoder, PackedBatch, Qwen2Config, Qwen2Encoder, random_state)
     from easyrag_b200.index import DenseIndex

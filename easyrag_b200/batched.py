@@ -133,6 +133,28 @@ def select_rows(scores: torch.Tensor, k: int, positive_only: bool = False, doc_g
     return out
 
 
+def merge_topk_parts(cand_scores: torch.Tensor, cand_ids: torch.Tensor, n_parts: int, part_stride_bytes: int, k: int,
+                     out: Optional[TopK] = None, stream=None) -> TopK:
+    """Merge ``n_parts`` per-shard top-k lists per query, read in place from an all-gathered byte record.
+
+    ``cand_scores`` / ``cand_ids``: [Q, k_in] views of part 0 inside the gathered buffer; part p of the same
+    arrays lies ``p * part_stride_bytes`` further (easyrag_b200/dist.py)."""
+    L = _lib.lib()
+    dev = cand_scores.device
+    assert cand_scores.shape == cand_ids.shape and cand_scores.stride(1) == 1 and cand_ids.stride(1) == 1
+    assert cand_ids.dtype == torch.int32 and cand_scores.stride(0) == cand_ids.stride(0)
+    st = _lib.F64 if cand_scores.dtype == torch.float64 else _lib.F32
+    nq, c = cand_scores.shape
+    if out is None:
+        out = TopK(torch.empty(nq, k, dtype=cand_scores.dtype, device=dev),
+                   torch.empty(nq, k, dtype=torch.int32, device=dev), torch.empty(nq, dtype=torch.int32, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_merge_topk_parts(_lib.ptr(cand_scores), _lib.ptr(cand_ids), st, nq, c, cand_scores.stride(0),
+                                          n_parts, part_stride_bytes, k, _lib.ptr(out.scores), _lib.ptr(out.ids),
+                                          _lib.ptr(out.counts), _lib.stream_ptr(stream)), "ezr_merge_topk_parts")
+    return out
+
+
 def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int, stream=None) -> TopK:
     """Merge candidate lists [Q, C] (id < 0 = empty) into the canonical top-k."""
     L = _lib.lib()
@@ -220,10 +242,16 @@ class CoarseRanker:
         return self._bufs[key]
 
     def routes(self, queries: torch.Tensor, q_ptr: torch.Tensor, q_terms: torch.Tensor, k: int, k_out: int,
-               q_group: Optional[torch.Tensor] = None) -> Tuple[TopK, TopK, TopK]:
-        """Both routes over this ranker's (shard of the) corpus -> (dense, sparse, fused-output buffer)."""
+               q_group: Optional[torch.Tensor] = None, d_out: Optional[TopK] = None,
+               s_out: Optional[TopK] = None) -> Tuple[TopK, TopK, TopK]:
+        """Both routes over this ranker's (shard of the) corpus -> (dense, sparse, fused-output buffer).
+
+        ``d_out`` / ``s_out``: caller-owned result buffers (the sharded ranker passes views of its exchange
+        record, so the kernels write straight into the message)."""
         nq = queries.shape[0]
-        d_out, s_out, f_out = self._buffers(nq, k, k, k_out)
+        d_own, s_own, f_out = self._buffers(nq, k, k, k_out)
+        d_out = d_own if d_out is None else d_out
+        s_out = s_own if s_out is None else s_out
         cur = torch.cuda.current_stream(self.device)
         if self.overlap:
             self.s_dense.wait_stream(cur)
@@ -251,6 +279,71 @@ class CoarseRanker:
         d_out, s_out, f_out = self.routes(queries, q_ptr, q_terms, k_dense, k_out, q_group=q_group)
         rrf_fuse(s_out.ids, s_out.counts, d_out.ids, d_out.counts, k_out, K=K, canon=self.canon, out=f_out)
         return f_out, s_out, d_out
+
+
+class HostPipeline:
+    """Host-buffer front end of the batched path: pinned host inputs in, pinned host results out, every call.
+
+    ``step`` enqueues, without blocking the host: H2D of the query vectors / term pointers / term ids on a copy
+    stream, both routes + (all-gather, merge) + RRF on the caller's stream, D2H of the fused ids and float64 scores
+    on a second copy stream.  Inputs are double buffered on the device, so the copies of step i+1 run under the
+    kernels of step i; a result buffer is only reused once its D2H has completed.  ``ranker`` is a
+    :class:`CoarseRanker` or an :class:`easyrag_b200.dist.ShardedCoarseRanker`.
+    """
+
+    def __init__(self, ranker, n_queries: int, dim: int, max_terms: int, k: int = 10, k_out: int = 10, depth: int = 2):
+        base = getattr(ranker, "ranker", ranker)
+        self.ranker, self.k, self.k_out = ranker, k, k_out
+        self.device = dev = base.device
+        self.sharded = base is not ranker
+        self.s_in = torch.cuda.Stream(device=dev)
+        self.s_out = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(
+                qvec=torch.empty(n_queries, dim, dtype=torch.bfloat16, device=dev),
+                ptr=torch.empty(n_queries + 1, dtype=torch.int32, device=dev),
+                terms=torch.empty(max(max_terms, 1), dtype=torch.int32, device=dev),
+                ev_in=torch.cuda.Event(), ev_free=torch.cuda.Event()))
+        self.ev_done = torch.cuda.Event()
+        self.ev_out = torch.cuda.Event()
+        self.n = 0
+
+    def step(self, h_qvec: torch.Tensor, h_ptr: torch.Tensor, h_terms: torch.Tensor, h_ids_out: torch.Tensor,
+             h_scores_out: torch.Tensor, q_group: Optional[torch.Tensor] = None) -> None:
+        """One batch.  ``h_*`` are pinned host tensors: bf16 [Q, D], int32 [Q+1], int32 [T] in; int32 [Q, k_out] and
+        float64 [Q, k_out] out (valid after :meth:`drain` or a synchronize)."""
+        slot = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        nq, nt = h_qvec.shape[0], h_terms.numel()
+        if nq != slot["qvec"].shape[0] or nt > slot["terms"].numel():
+            raise ValueError("HostPipeline is sized at construction: same batch size, at most max_terms term ids")
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(slot["ev_free"])            # the kernels that last read this slot have finished
+            slot["qvec"].copy_(h_qvec, non_blocking=True)
+            slot["ptr"].copy_(h_ptr, non_blocking=True)
+            slot["terms"][:nt].copy_(h_terms, non_blocking=True)
+            slot["ev_in"].record(self.s_in)
+        cur.wait_event(slot["ev_in"])
+        cur.wait_event(self.ev_out)                          # the previous results have left the fused buffer
+        if self.sharded:
+            fused = self.ranker.hybrid(slot["qvec"], slot["ptr"], slot["terms"], k=self.k, k_out=self.k_out,
+                                       q_group=q_group)[0]
+        else:
+            fused = self.ranker.hybrid(slot["qvec"], slot["ptr"], slot["terms"], self.k, self.k, self.k_out,
+                                       q_group=q_group)[0]
+        slot["ev_free"].record(cur)
+        self.ev_done.record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_done)
+            h_ids_out.copy_(fused.ids, non_blocking=True)
+            h_scores_out.copy_(fused.scores, non_blocking=True)
+            self.ev_out.record(self.s_out)
+
+    def drain(self) -> None:
+        """Make the caller's stream wait for every copy enqueued so far (then a stream / event sync covers them)."""
+        torch.cuda.current_stream(self.device).wait_event(self.ev_out)
 
 
 def dual_sparse_fusion(chunk_index: Bm25Index, path_index: Bm25Index, q_ptr: torch.Tensor, q_terms: torch.Tensor,

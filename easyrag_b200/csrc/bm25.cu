@@ -430,11 +430,14 @@ namespace ezr {
 
 // One warp per row: merge n_cand candidates (id<0 = empty) into the final top-k (k<=32).
 // row_list / row_count (optional): warp i handles row row_list[i] for i < *row_count.
+// n_parts > 1: the row's candidates are n_parts segments of n_cand entries, segment p at byte offset
+// p * part_bytes from the row's first segment (the all-gathered per-shard records of easyrag_b200/dist.py).
 template <typename S>
 __global__ void merge_warp_kernel(const S* __restrict__ cs, const int32_t* __restrict__ cid, int n_rows, int n_cand,
                                   int64_t stride, int k, int id_add, S* __restrict__ out_s,
                                   int32_t* __restrict__ out_id, int32_t* __restrict__ out_cnt,
-                                  const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
+                                  const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count,
+                                  int n_parts, int64_t part_bytes) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
@@ -444,14 +447,18 @@ __global__ void merge_warp_kernel(const S* __restrict__ cs, const int32_t* __res
     }
     WarpTopK<S> tk;
     tk.init(k);
-    const S* rs = cs + (int64_t)row * stride;
-    const int32_t* ri = cid + (int64_t)row * stride;
-    for (int i0 = 0; i0 < n_cand; i0 += 32) {
-        const int i = i0 + lane;
-        S s = (S)0;
-        int id = -1;
-        if (i < n_cand) { s = rs[i]; id = ri[i]; }
-        tk.offer(s, id, id >= 0);
+    for (int part = 0; part < n_parts; ++part) {
+        const S* rs = reinterpret_cast<const S*>(reinterpret_cast<const char*>(cs) + part * part_bytes) +
+                      (int64_t)row * stride;
+        const int32_t* ri = reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(cid) + part * part_bytes) +
+                            (int64_t)row * stride;
+        for (int i0 = 0; i0 < n_cand; i0 += 32) {
+            const int i = i0 + lane;
+            S s = (S)0;
+            int id = -1;
+            if (i < n_cand) { s = rs[i]; id = ri[i]; }
+            tk.offer(s, id, id >= 0);
+        }
     }
     if (lane < k) {
         out_s[(int64_t)row * k + lane] = tk.id >= 0 ? tk.s : ScoreTraits<S>::lowest();
@@ -569,15 +576,21 @@ static int select_rows_impl(const S* scores, int n_rows, int64_t n_cols, int64_t
 template <typename S>
 static int merge_impl(const S* cs, const int32_t* cid, int n_rows, int n_cand, int64_t stride, int k, int id_add,
                       S* out_s, int32_t* out_id, int32_t* out_cnt, cudaStream_t st,
-                      const int32_t* row_list = nullptr, const int32_t* row_count = nullptr) {
+                      const int32_t* row_list = nullptr, const int32_t* row_count = nullptr, int n_parts = 1,
+                      int64_t part_bytes = 0) {
     if (n_rows == 0) return EZR_OK;
     if (k <= 32) {
         const int wpb = 8;
         ProfScope prof(EZR_PROF_MERGE, st);
         merge_warp_kernel<S><<<ceil_div(n_rows, wpb), wpb * 32, 0, st>>>(cs, cid, n_rows, n_cand, stride, k, id_add,
-                                                                        out_s, out_id, out_cnt, row_list, row_count);
+                                                                        out_s, out_id, out_cnt, row_list, row_count,
+                                                                        n_parts, part_bytes);
         EZR_LAUNCH_CHECK();
         return EZR_OK;
+    }
+    if (n_parts != 1) {
+        set_error("merge_topk_parts: k=%d > 32 needs contiguous candidates", k);
+        return EZR_ERR_UNSUPPORTED;
     }
     return launch_select<S>(cs, cid, n_rows, n_cand, stride, 1, k, 0, nullptr, nullptr, id_add, out_s, out_id,
                             out_cnt, st);
@@ -948,6 +961,24 @@ int ezr_merge_topk(const void* cand_scores, const int32_t* cand_ids, int32_t sco
                                     (double*)out_scores, out_ids, out_counts, st)
                : merge_impl<float>((const float*)cand_scores, cand_ids, n_rows, n_cand, cand_stride, k, 0,
                                    (float*)out_scores, out_ids, out_counts, st);
+}
+
+int ezr_merge_topk_parts(const void* cand_scores, const int32_t* cand_ids, int32_t score_type, int32_t n_rows,
+                         int32_t n_cand, int64_t cand_stride, int32_t n_parts, int64_t part_stride_bytes, int32_t k,
+                         void* out_scores, int32_t* out_ids, int32_t* out_counts, void* stream) {
+    EZR_CHECK_ARG(k >= 1 && k <= 32, "merge_topk_parts: k=%d out of [1,32]", k);
+    EZR_CHECK_ARG(score_type == EZR_F64 || score_type == EZR_F32, "merge_topk_parts: bad score_type");
+    EZR_CHECK_ARG(n_cand >= 0 && cand_stride >= n_cand, "merge_topk_parts: bad n_cand/stride");
+    EZR_CHECK_ARG(n_parts >= 1 && part_stride_bytes >= 0 && part_stride_bytes % 8 == 0,
+                  "merge_topk_parts: bad n_parts/part_stride_bytes");
+    cudaStream_t st = (cudaStream_t)stream;
+    return score_type == EZR_F64
+               ? merge_impl<double>((const double*)cand_scores, cand_ids, n_rows, n_cand, cand_stride, k, 0,
+                                    (double*)out_scores, out_ids, out_counts, st, nullptr, nullptr, n_parts,
+                                    part_stride_bytes)
+               : merge_impl<float>((const float*)cand_scores, cand_ids, n_rows, n_cand, cand_stride, k, 0,
+                                   (float*)out_scores, out_ids, out_counts, st, nullptr, nullptr, n_parts,
+                                   part_stride_bytes);
 }
 
 }  // extern "C"

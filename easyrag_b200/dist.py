@@ -3,10 +3,11 @@
 The reference is single-process; this is new.  Corpus rows (and the BM25 document axis) are cut
 into contiguous shards, one per rank; queries are replicated.  Corpus-global BM25 statistics
 (idf, avgdl) are shared, so every shard scores exactly as the unsharded index would.  Each rank
-computes its local dense and BM25 top-k with *global* ids, packs both routes into one byte
-record and a SINGLE all-gather (NCCL over NVLink on GPUs, gloo in the CPU tests) exchanges
-them; every rank then merges G*k candidates per route under the canonical order -- the same
-order the 1-GPU path uses, hence identical rank lists -- and runs RRF.
+computes its local dense and BM25 top-k with *global* ids straight into one byte record and a
+SINGLE all-gather (NCCL over NVLink on GPUs, gloo in the CPU tests) exchanges the records;
+every rank then merges G*k candidates per route under the canonical order -- the same order
+the 1-GPU path uses, hence identical rank lists -- reading the gathered buffer in place, and
+runs RRF.
 """
 from __future__ import annotations
 
@@ -18,12 +19,17 @@ import torch.distributed as dist
 
 
 def shard_bounds(n_rows: int, world: int, rank: int, align: int = 1) -> Tuple[int, int]:
-    """Contiguous, ordered, exhaustive split of ``n_rows``; shard sizes are multiples of ``align`` except the last."""
-    per = -(-n_rows // world)
-    per = -(-per // align) * align
-    lo = min(n_rows, rank * per)
-    hi = min(n_rows, lo + per)
-    return lo, hi
+    """Contiguous, ordered, exhaustive, BALANCED split of ``n_rows``.
+
+    The rows are cut into ``ceil(n_rows / align)`` units of ``align`` rows (the last may be short); every rank gets
+    ``units // world`` of them and the first ``units % world`` ranks one more, so shard sizes differ by at most
+    ``align`` rows.  Shard-local indexes use local ids (ranges and tiles restart at the shard's first row), so
+    nothing requires a coarse alignment: the default is 1."""
+    units = -(-n_rows // align)
+    base, extra = divmod(units, world)
+    lo_u = rank * base + min(rank, extra)
+    hi_u = lo_u + base + (1 if rank < extra else 0)
+    return min(n_rows, lo_u * align), min(n_rows, hi_u * align)
 
 
 @dataclass
@@ -51,43 +57,27 @@ class RecordLayout:
         return self.offsets[1]
 
 
-def pack_records(layout: RecordLayout, d_scores, d_ids, s_scores, s_ids, out: Optional[torch.Tensor] = None):
-    """Copy the four per-route tensors into one contiguous uint8 buffer (one message per rank)."""
-    offs, total = layout.offsets
-    dev = d_scores.device
-    if out is None:
-        out = torch.zeros(total, dtype=torch.uint8, device=dev)
-    for off, size, t in zip(offs, layout.sizes, (d_scores, d_ids, s_scores, s_ids)):
-        out[off:off + size].copy_(t.contiguous().view(-1).view(torch.uint8))
+def record_views(layout: RecordLayout, buf: torch.Tensor):
+    """The four per-route arrays of one rank's record as typed [Q, k] views of the byte buffer ``buf``
+    (dense scores f32, dense ids i32, sparse scores f64/f32, sparse ids i32): writing through them fills the
+    message in place, reading them from a gathered buffer needs no unpacking."""
+    offs, _ = layout.offsets
+    q, k = layout.n_queries, layout.k
+    sdt = torch.float64 if layout.sparse_bytes == 8 else torch.float32
+    out = []
+    for off, size, dt in zip(offs, layout.sizes, (torch.float32, torch.int32, sdt, torch.int32)):
+        out.append(buf[off:off + size].view(dt).view(q, k))
     return out
 
 
-def unpack_records(layout: RecordLayout, gathered: torch.Tensor, world: int):
-    """gathered uint8 [world, nbytes] -> per-route candidate matrices [Q, world*k] (ids < 0 = empty)."""
-    offs, total = layout.offsets
-    q, k = layout.n_queries, layout.k
-    sdt = torch.float64 if layout.sparse_bytes == 8 else torch.float32
-    g = gathered.view(world, total)
-
-    def route(off, size, dtype):
-        x = g[:, off:off + size].contiguous().view(-1).view(dtype).view(world, q, k)
-        return x.permute(1, 0, 2).contiguous().view(q, world * k)
-
-    sizes = layout.sizes
-    return (route(offs[0], sizes[0], torch.float32), route(offs[1], sizes[1], torch.int32),
-            route(offs[2], sizes[2], sdt), route(offs[3], sizes[3], torch.int32))
-
-
-def all_gather_bytes(local: torch.Tensor, group=None) -> torch.Tensor:
-    """The one collective on the data path: all-gather of the packed per-shard top-k records."""
-    world = dist.get_world_size(group)
-    out = torch.empty(world * local.numel(), dtype=torch.uint8, device=local.device)
-    dist.all_gather_into_tensor(out, local, group=group)
-    return out.view(world, local.numel())
-
-
 class ShardedCoarseRanker:
-    """dense + BM25 + RRF over a row-sharded corpus; every rank returns the full fused result."""
+    """dense + BM25 + RRF over a row-sharded corpus; every rank returns the full fused result.
+
+    Per (batch size, k) one record buffer and one gather buffer are allocated once.  The two route kernels write
+    their top-k straight into the record (typed views), ONE ``all_gather_into_tensor`` exchanges the records, and the
+    merge kernel reads the gathered buffer in place (``ezr_merge_topk_parts``): no pack/unpack kernels, no per-step
+    allocations.
+    """
 
     def __init__(self, ranker, group=None):
         """``ranker``: :class:`easyrag_b200.batched.CoarseRanker` over this rank's shard (indexes built with
@@ -96,23 +86,42 @@ class ShardedCoarseRanker:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self._pack = {}
+        self._state = {}
+
+    def _buffers(self, nq: int, k: int, sparse_dtype):
+        from .batched import TopK
+        key = (nq, k, sparse_dtype)
+        if key not in self._state:
+            dev = self.ranker.device
+            layout = RecordLayout(nq, k, 8 if sparse_dtype == torch.float64 else 4)
+            record = torch.zeros(layout.nbytes, dtype=torch.uint8, device=dev)
+            gathered = torch.zeros(self.world * layout.nbytes, dtype=torch.uint8, device=dev)
+            ds, di, ss, si = record_views(layout, record)
+            cnt = lambda: torch.empty(nq, dtype=torch.int32, device=dev)
+            mk = lambda dt: torch.empty(nq, k, dtype=dt, device=dev)
+            self._state[key] = dict(
+                layout=layout, record=record, gathered=gathered,
+                d_local=TopK(ds, di, cnt()), s_local=TopK(ss, si, cnt()),
+                views=record_views(layout, gathered[:layout.nbytes]),
+                dense=TopK(mk(torch.float32), mk(torch.int32), cnt()),
+                sparse=TopK(mk(sparse_dtype), mk(torch.int32), cnt()))
+        return self._state[key]
 
     def hybrid(self, queries, q_ptr, q_terms, k: int = 10, k_out: int = 10, K: int = 60, q_group=None,
                canon: Optional[torch.Tensor] = None):
         from . import batched
         r = self.ranker
         nq = queries.shape[0]
-        d_out, s_out, f_out = r.routes(queries, q_ptr, q_terms, k, k_out, q_group=q_group)
-        layout = RecordLayout(nq, k, 8 if s_out.scores.dtype == torch.float64 else 4)
-        key = (nq, k, layout.sparse_bytes)
-        if key not in self._pack:
-            self._pack[key] = torch.zeros(layout.nbytes, dtype=torch.uint8, device=r.device)
-        local = pack_records(layout, d_out.scores, d_out.ids, s_out.scores, s_out.ids, out=self._pack[key])
-        gathered = all_gather_bytes(local, self.group)
-        ds, di, ss, si = unpack_records(layout, gathered, self.world)
-        dense = batched.merge_topk(ds, di, k)
-        sparse = batched.merge_topk(ss, si, k)
+        if k > 32:
+            raise ValueError("the sharded path merges per-shard lists of k <= 32")
+        st = self._buffers(nq, k, r.sparse.score_dtype)
+        _, _, f_out = r.routes(queries, q_ptr, q_terms, k, k_out, q_group=q_group, d_out=st["d_local"],
+                               s_out=st["s_local"])
+        dist.all_gather_into_tensor(st["gathered"], st["record"], group=self.group)   # the one collective
+        g_ds, g_di, g_ss, g_si = st["views"]
+        nbytes = st["layout"].nbytes
+        dense = batched.merge_topk_parts(g_ds, g_di, self.world, nbytes, k, out=st["dense"])
+        sparse = batched.merge_topk_parts(g_ss, g_si, self.world, nbytes, k, out=st["sparse"])
         cn = canon if canon is not None else r.canon
         fused = batched.rrf_fuse(sparse.ids, sparse.counts, dense.ids, dense.counts, k_out, K=K, canon=cn, out=f_out)
         return fused, sparse, dense

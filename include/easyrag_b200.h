@@ -64,7 +64,7 @@ typedef struct ezr_bm25_index {
     int64_t n_postings;
     int32_t vocab;
     int32_t score_type;        /* ezr_score_type of post_w */
-    int32_t range_size;        /* ezr_bm25_range_size(): 4096 */
+    int32_t range_size;        /* ezr_bm25_range_size(): 8192 in this build */
     int32_t n_ranges;          /* ceil(n_docs / range_size) */
     const int64_t* indptr;     /* [vocab+1] */
     const int32_t* post_doc;   /* [n_postings] ascending inside a term */
@@ -145,6 +145,14 @@ size_t ezr_merge_topk_workspace(int32_t n_rows, int32_t n_cand, int32_t k, int32
 int ezr_merge_topk(const void* cand_scores, const int32_t* cand_ids, int32_t score_type, int32_t n_rows,
                    int32_t n_cand, int64_t cand_stride, int32_t k, void* out_scores, int32_t* out_ids,
                    int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same merge over candidates that sit in n_parts separate segments: segment p of row q starts at
+ * (char*)cand_x + p*part_stride_bytes + q*cand_stride*sizeof(elem) and holds n_cand entries.  This is the layout of
+ * the all-gathered per-shard records (easyrag_b200/dist.py: one byte record per rank, gathered back to back), so
+ * the shard merge reads the NCCL output in place -- no unpack / transpose kernels.  k <= 32. */
+int ezr_merge_topk_parts(const void* cand_scores, const int32_t* cand_ids, int32_t score_type, int32_t n_rows,
+                         int32_t n_cand, int64_t cand_stride, int32_t n_parts, int64_t part_stride_bytes, int32_t k,
+                         void* out_scores, int32_t* out_ids, int32_t* out_counts, void* stream);
 
 /* ------------------------------------------------------------- dense ----
  * QdrantRetriever (retrievers.py:37-52) over a COSINE collection (ingestion.py:180-182):

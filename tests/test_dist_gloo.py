@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: the N>1 plumbing (shard bounds, packed records, the single all-gather).
+"""CPU, world_size 2, gloo: the N>1 plumbing (shard bounds, the in-place record layout, the single all-gather).
 
 The merge itself is a CUDA kernel (tests/test_gpu_dist.py covers it); here the gathered records
 are merged by the oracle and must reproduce the unsharded oracle result, which proves that the
@@ -54,10 +54,15 @@ def _worker(rank, world, port, ret):
         d_ids, d_sc = ort.dense_topk(dense[lo:hi], qv, k)
         d_ids = np.where(d_ids >= 0, d_ids + lo, -1).astype(np.int32)
         lay = ezdist.RecordLayout(nq, k, 8)
-        local = ezdist.pack_records(lay, torch.from_numpy(d_sc), torch.from_numpy(d_ids), torch.from_numpy(s_sc),
-                                    torch.from_numpy(s_ids))
-        gathered = ezdist.all_gather_bytes(local)
-        ds, di, ss, si = ezdist.unpack_records(lay, gathered, world)
+        # the product path (ShardedCoarseRanker): results are written through typed views of ONE byte record,
+        # a single all_gather_into_tensor exchanges the records, the merge reads part p at p * nbytes
+        record = torch.zeros(lay.nbytes, dtype=torch.uint8)
+        for view, arr in zip(ezdist.record_views(lay, record), (d_sc, d_ids, s_sc, s_ids)):
+            view.copy_(torch.from_numpy(arr))
+        gathered = torch.zeros(world * lay.nbytes, dtype=torch.uint8)
+        dist.all_gather_into_tensor(gathered, record)
+        parts = [ezdist.record_views(lay, gathered[p * lay.nbytes:(p + 1) * lay.nbytes]) for p in range(world)]
+        ds, di, ss, si = (torch.cat([parts[p][j] for p in range(world)], dim=1) for j in range(4))
         # canonical merge by the oracle: (score desc, id desc) over the gathered candidates
         ok = True
         full_s_ids, full_s_sc = _oracle_topk(rows, k, 0)

@@ -85,26 +85,38 @@ def test_shard_bounds_cover_exactly():
             assert prev == n
 
 
-def test_pack_unpack_roundtrip():
+def test_shard_bounds_are_balanced():
+    for world in (2, 4, 8):
+        sizes = [b - a for a, b in (ezdist.shard_bounds(1_000_000, world, r, align=64) for r in range(world))]
+        assert max(sizes) - min(sizes) <= 64 and sum(sizes) == 1_000_000
+
+
+def test_record_views_alias_the_record_bytes():
+    """The typed views the kernels write through and the merge reads from (in place, part p at p * nbytes)."""
     q, k, world = 5, 3, 4
-    lay = ezdist.RecordLayout(q, k, 8)
-    g = torch.Generator().manual_seed(0)
-    parts, bufs = [], []
-    for r in range(world):
-        ds = torch.rand(q, k, generator=g)
-        di = torch.randint(0, 100, (q, k), generator=g, dtype=torch.int32)
-        ss = torch.rand(q, k, generator=g, dtype=torch.float64)
-        si = torch.randint(0, 100, (q, k), generator=g, dtype=torch.int32)
-        parts.append((ds, di, ss, si))
-        bufs.append(ezdist.pack_records(lay, ds, di, ss, si))
-    gathered = torch.stack(bufs)
-    ds, di, ss, si = ezdist.unpack_records(lay, gathered, world)
-    assert ds.shape == (q, world * k) and ss.dtype == torch.float64
-    for r in range(world):
-        assert torch.equal(ds[:, r * k:(r + 1) * k], parts[r][0])
-        assert torch.equal(di[:, r * k:(r + 1) * k], parts[r][1])
-        assert torch.equal(ss[:, r * k:(r + 1) * k], parts[r][2])
-        assert torch.equal(si[:, r * k:(r + 1) * k], parts[r][3])
+    for sparse_bytes, sdt in ((8, torch.float64), (4, torch.float32)):
+        lay = ezdist.RecordLayout(q, k, sparse_bytes)
+        offs, total = lay.offsets
+        assert total == lay.nbytes and total % 16 == 0 and all(o % 16 == 0 for o in offs)
+        g = torch.Generator().manual_seed(0)
+        gathered = torch.zeros(world * lay.nbytes, dtype=torch.uint8)
+        parts = []
+        for r in range(world):
+            rec = gathered[r * lay.nbytes:(r + 1) * lay.nbytes]
+            ds, di, ss, si = ezdist.record_views(lay, rec)
+            assert ds.dtype == torch.float32 and ss.dtype == sdt and di.dtype == si.dtype == torch.int32
+            assert ds.shape == (q, k) and ds.data_ptr() == rec.data_ptr() + offs[0] and si.data_ptr() == rec.data_ptr() + offs[3]
+            ds.copy_(torch.rand(q, k, generator=g))
+            di.copy_(torch.randint(0, 100, (q, k), generator=g, dtype=torch.int32))
+            ss.copy_(torch.rand(q, k, generator=g, dtype=sdt))
+            si.copy_(torch.randint(0, 100, (q, k), generator=g, dtype=torch.int32))
+            parts.append([t.clone() for t in (ds, di, ss, si)])
+        v0 = ezdist.record_views(lay, gathered[:lay.nbytes])
+        for r in range(world):
+            for j in range(4):
+                # what ezr_merge_topk_parts addresses: part r of array j = view 0 of array j + r * nbytes
+                raw = gathered[r * lay.nbytes + offs[j]: r * lay.nbytes + offs[j] + lay.sizes[j]]
+                assert torch.equal(raw.view(v0[j].dtype).view(q, k), parts[r][j])
 
 
 def test_schema_surface():
