@@ -69,7 +69,9 @@ SIGNATURES = {
     "ezr_dense_set_probe": (C.c_int, [_i32]),
     "ezr_rrf_fuse": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "ezr_gemm_bf16": (C.c_int, [_p, _i32, _i32, _i64, _p, _i32, _i64, _p, _p, _i64, _p, _i64, _i32, _p]),
-    "ezr_attn_bidir": (C.c_int, [_p, _i64, _p, _i32, _i32, _i32, _i32, _i32, C.c_float, _p, _i64, _p]),
+    "ezr_attn_bidir": (C.c_int, [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _i32, C.c_float, _p, _i64, _p]),
+    "ezr_attn_set_kernel": (C.c_int, [_i32]),
+    "ezr_attn_last_kernel": (C.c_char_p, []),
     "ezr_embed_gather": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _i64, _p]),
     "ezr_bert_embed": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, C.c_float, _i32, _i32, _i32, _p, _p]),
     "ezr_rmsnorm": (C.c_int, [_p, _i64, _p, C.c_float, _i32, _i32, _p, _i64, _p]),
@@ -80,6 +82,7 @@ SIGNATURES = {
     "ezr_profile_enable": (C.c_int, [_i32]),
     "ezr_profile_reset": (C.c_int, []),
     "ezr_profile_read": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "ezr_fuse_lists": (C.c_int, [_i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "ezr_fusion_simple": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p]),
 }
 

@@ -197,17 +197,18 @@ attn_bidir_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const int32
 
 }  // namespace ezr
 
-extern "C" int ezr_attn_bidir(const void* qkv, int64_t ld, const int32_t* cu_seqlens, int32_t n_seq, int32_t max_len,
-                              int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, float softmax_scale, void* out,
-                              int64_t ldo, void* stream) {
-    using namespace ezr;
+// The first attention kernel of this library (warp-level mma.sync), kept as an independent implementation the
+// tcgen05 kernel (attention_tc.cu) is cross-checked against: ezr_attn_set_kernel(1).
+namespace ezr {
+int attn_bidir_legacy(const void* qkv, int64_t ld, const int32_t* cu_seqlens, int32_t n_seq, int32_t max_len,
+                      int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, float softmax_scale, void* out, int64_t ldo,
+                      cudaStream_t st) {
     EZR_CHECK_ARG(head_dim == 64 || head_dim == 128, "attn: head_dim must be 64 or 128 (got %d)", head_dim);
     EZR_CHECK_ARG(n_kv_heads >= 1 && n_heads % n_kv_heads == 0, "attn: n_heads must be a multiple of n_kv_heads");
     EZR_CHECK_ARG(ld % 8 == 0 && ldo % 2 == 0, "attn: qkv row stride must be a multiple of 8 elements");
     EZR_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "attn: qkv must be 16-byte aligned");
     if (n_seq == 0 || max_len == 0) return EZR_OK;
     EZR_CHECK_ARG(n_seq <= 65535 && n_heads <= 65535, "attn: grid too large");
-    cudaStream_t st = (cudaStream_t)stream;
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
     dim3 grid((max_len + 63) / 64, n_seq, n_heads);
     const size_t smem = (size_t)5 * 64 * head_dim * 2;      // Q + double-buffered K/V
@@ -227,3 +228,4 @@ extern "C" int ezr_attn_bidir(const void* qkv, int64_t ld, const int32_t* cu_seq
     EZR_LAUNCH_CHECK();
     return EZR_OK;
 }
+}  // namespace ezr

@@ -1,0 +1,326 @@
+// Bidirectional (non-causal) multi-head attention over PACKED variable-length sequences on tcgen05 / TMEM.
+//
+// Reference: Qwen2 attention run with is_causal=False (modeling_qwen.py:289-308 eager / :704-712 SDPA, padding
+// handled by an additive mask :1037-1040) and BERT self-attention behind SentenceTransformer.encode
+// (hf_embeddings.py:118-123).  Sequences are packed, so the mask reduces to "keys beyond this sequence".
+//
+// One CTA = 128 query rows of one (sequence, head); two CTAs share an SM (256 TMEM columns and <= 96 KB of shared
+// memory each), so one CTA's softmax overlaps the other's MMAs.
+//   warp 0      TMA producer: Q tile once, then K / V tiles of 128 keys (one 2-D tensor map over the packed
+//               [tokens, (H + 2 KV) hd] matrix serves Q, K and V; 128B swizzle; rows past the matrix are zero-filled)
+//   warp 1      tcgen05.mma issuer:  S = Q K^T   (SS form, both operands K-major in shared memory, N = keys of the tile)
+//                                    O += P V    (TS form: P is read from TENSOR MEMORY, V is the MN-major B operand
+//                                                 straight from its row-major TMA tile -- no transpose anywhere)
+//   warps 2-9   softmax: two warps per TMEM lane quadrant, a thread owns one query row and 64 of the 128 key columns:
+//               row max (pair exchange through shared memory), exp2 with the 1/sqrt(d) scale folded in, probabilities
+//               written back as packed bf16 over the S columns they came from (tcgen05.st), running sum in fp32.
+// TMEM columns: [0,128) S (fp32) aliased by P (bf16 pairs: keys 0-63 -> columns 0-31, keys 64-127 -> columns 64-95),
+// [128, 128+hd) O.  The running maximum is lazy: O is rescaled in tensor memory (tcgen05.ld / multiply / tcgen05.st)
+// only when a row's maximum grows by more than 2^8; otherwise the stale maximum stays (p <= 256 is harmless in
+// bf16 / fp32) -- the final division by the row sum makes both choices the same function.
+#include "../ezr_common.cuh"
+#include "../ptx.cuh"
+
+namespace ezr {
+
+constexpr int AT_M = 128;                 // query rows per CTA (UMMA M, one TMEM lane each)
+constexpr int AT_N = 128;                 // keys per tile (UMMA N of S = Q K^T)
+constexpr int AT_THREADS = 320;           // TMA warp, MMA warp, 8 softmax warps
+constexpr int AT_BOX_BYTES = 128 * 64 * 2;   // one TMA box: 128 rows x 64 bf16
+constexpr int AT_TMEM_COLS = 256;
+constexpr int AT_O_COL = 128;
+constexpr float AT_RESCALE_LOG2 = 8.0f;   // rescale O only when the row maximum grows by more than 2^8
+
+struct AttnBarriers {
+    uint64_t q_full;
+    uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+    uint64_t s_full, p_full, o_full;
+    uint32_t tmem_base;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restrict__ cu, int n_heads, int n_kv_heads,
+               float scale_log2, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+    constexpr int CH = HD / 64;                          // 64-column TMA boxes per tile
+    constexpr int TILE_BYTES = CH * AT_BOX_BYTES;        // one Q / K / V tile
+    constexpr int STAGES = HD == 64 ? 2 : 1;             // K/V ring depth (K and V have their own barriers)
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem_q = smem;
+    unsigned char* smem_k = smem_q + TILE_BYTES;
+    unsigned char* smem_v = smem_k + STAGES * TILE_BYTES;
+    AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_v + STAGES * TILE_BYTES);
+    __shared__ float s_xch[2][AT_M];                     // pair exchange: row maxima, then row sums
+
+    const int qb = blockIdx.x, b = blockIdx.y, h = blockIdx.z;
+    const int lo = cu[b];
+    const int len = cu[b + 1] - lo;
+    const int q0 = qb * AT_M;
+    if (q0 >= len) return;                               // block-uniform
+    const int kvh = h / (n_heads / n_kv_heads);
+    const int col_q = h * HD, col_k = (n_heads + kvh) * HD, col_v = (n_heads + n_kv_heads + kvh) * HD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_kt = (len + AT_N - 1) / AT_N;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map);
+        ptx::mbar_init(&bars->q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&bars->k_full[i], 1);
+            ptx::mbar_init(&bars->k_empty[i], 1);
+            ptx::mbar_init(&bars->v_full[i], 1);
+            ptx::mbar_init(&bars->v_empty[i], 1);
+        }
+        ptx::mbar_init(&bars->s_full, 1);
+        ptx::mbar_init(&bars->p_full, 8);
+        ptx::mbar_init(&bars->o_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<AT_TMEM_COLS>(&bars->tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            ptx::mbar_expect_tx(&bars->q_full, TILE_BYTES);
+            for (int c = 0; c < CH; ++c)
+                ptx::tma_load_2d(smem_q + c * AT_BOX_BYTES, &map, &bars->q_full, col_q + c * 64, lo + q0);
+            for (int j = 0; j < n_kt; ++j) {
+                const int s = j % STAGES;
+                const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+                const int row = lo + j * AT_N;
+                ptx::mbar_wait(&bars->k_empty[s], ph ^ 1);
+                ptx::mbar_expect_tx(&bars->k_full[s], TILE_BYTES);
+                for (int c = 0; c < CH; ++c)
+                    ptx::tma_load_2d(smem_k + s * TILE_BYTES + c * AT_BOX_BYTES, &map, &bars->k_full[s], col_k + c * 64, row);
+                ptx::mbar_wait(&bars->v_empty[s], ph ^ 1);
+                ptx::mbar_expect_tx(&bars->v_full[s], TILE_BYTES);
+                for (int c = 0; c < CH; ++c)
+                    ptx::tma_load_2d(smem_v + s * TILE_BYTES + c * AT_BOX_BYTES, &map, &bars->v_full[s], col_v + c * 64, row);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
+        constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(AT_M, HD) | ptx::kIdescBMajorMN;
+        const uint32_t q_addr = ptx::smem_u32(smem_q);
+        const uint32_t tm_s = tmem_base, tm_o = tmem_base + AT_O_COL;
+        ptx::mbar_wait(&bars->q_full, 0);
+        for (int j = 0; j < n_kt; ++j) {
+            const int s = j % STAGES;
+            const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+            const int valid = len - j * AT_N;
+            const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);        // keys of this tile, multiple of 16
+            const uint32_t k_addr = ptx::smem_u32(smem_k + s * TILE_BYTES);
+            const uint32_t v_addr = ptx::smem_u32(smem_v + s * TILE_BYTES);
+            ptx::mbar_wait(&bars->k_full[s], ph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t idesc_qk = ptx::make_idesc_bf16(AT_M, n_j);
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk) {
+                    const uint32_t off = (uint32_t)((kk >> 2) * AT_BOX_BYTES + (kk & 3) * 32);
+                    ptx::umma_f16_ss(tm_s, ptx::make_desc_sw128(q_addr + off), ptx::make_desc_sw128(k_addr + off), idesc_qk,
+                                     (uint32_t)(kk != 0));
+                }
+                ptx::umma_commit(&bars->k_empty[s]);
+                ptx::umma_commit(&bars->s_full);
+            }
+            __syncwarp();
+            ptx::mbar_wait(&bars->p_full, (uint32_t)j & 1u);                    // probabilities are in tensor memory
+            ptx::mbar_wait(&bars->v_full[s], ph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                for (int i = 0; i < n_j / 16; ++i) {
+                    const uint32_t a_tmem = tm_s + (uint32_t)(i < 4 ? 8 * i : 64 + 8 * (i - 4));
+                    ptx::umma_f16_ts(tm_o, a_tmem, ptx::make_desc_sw128_mn(v_addr + (uint32_t)i * 2048u, AT_BOX_BYTES), idesc_pv,
+                                     (uint32_t)((j | i) != 0));
+                }
+                ptx::umma_commit(&bars->v_empty[s]);
+                if (j == n_kt - 1) ptx::umma_commit(&bars->o_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- softmax + epilogue: 8 warps, two per TMEM lane quadrant ----------------
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;                      // key columns [64 half, 64 half + 64) of every tile
+        const int row = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const uint32_t s_col = (uint32_t)(half * 64);
+        const uint32_t o_col = (uint32_t)(AT_O_COL + half * (HD / 2));
+        float m_run = -INFINITY, l_part = 0.f;
+        for (int j = 0; j < n_kt; ++j) {
+            const int valid = len - j * AT_N;
+            const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);
+            ptx::mbar_wait(&bars->s_full, (uint32_t)j & 1u);   // also: every earlier O += P V has retired
+            ptx::tc_fence_after();
+            // pass 1: maximum of the row over this warp's columns
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col0 = (int)s_col + c * 32;
+                if (col0 < n_j) {                              // warp-uniform
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(lane_addr + (uint32_t)col0, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, col0 + i < valid ? __uint_as_float(r[i]) : -INFINITY);
+                }
+            }
+            s_xch[half][row] = mx;
+            ptx::named_bar_sync(1 + quad, 64);
+            mx = fmaxf(mx, s_xch[half ^ 1][row]);
+            float m_new = fmaxf(m_run, mx);
+            const bool grow = (m_new - m_run) * scale_log2 > AT_RESCALE_LOG2;   // true on the first tile (m_run = -inf)
+            if (!grow) m_new = m_run;
+            const float alpha = exp2f((m_run - m_new) * scale_log2);            // 1 when the maximum is kept
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+                // rare: bring this warp's half of the O columns to the new maximum
+#pragma unroll
+                for (int c = 0; c < HD / 64; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(lane_addr + o_col + c * 32, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    ptx::tmem_st_32x32(lane_addr + o_col + c * 32, r);
+                }
+            }
+            l_part *= alpha;
+            m_run = m_new;
+            const float mb = m_new * scale_log2;
+            // pass 2: probabilities, packed to bf16 over the S columns they came from
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col0 = (int)s_col + c * 32;
+                if (col0 < n_j) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(lane_addr + (uint32_t)col0, r);
+                    ptx::tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = col0 + i < valid ? exp2f(fmaf(__uint_as_float(r[i]), scale_log2, -mb)) : 0.f;
+                        const float p1 = col0 + i + 1 < valid ? exp2f(fmaf(__uint_as_float(r[i + 1]), scale_log2, -mb)) : 0.f;
+                        l_part += p0 + p1;
+                        __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&v);
+                    }
+                    ptx::tmem_st_32x16(lane_addr + s_col + (uint32_t)(c * 16), pk);
+                }
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->p_full);
+        }
+        // epilogue: O / row sum -> bf16 -> global
+        s_xch[half][row] = l_part;
+        ptx::named_bar_sync(1 + quad, 64);
+        const float inv = 1.0f / (l_part + s_xch[half ^ 1][row]);
+        ptx::mbar_wait(&bars->o_full, 0);
+        ptx::tc_fence_after();
+        const bool row_ok = q0 + row < len;
+        __nv_bfloat16* orow = out + (int64_t)(lo + q0 + row) * ldo + h * HD + half * (HD / 2);
+#pragma unroll
+        for (int c = 0; c < HD / 64; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(lane_addr + o_col + c * 32, r);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    __nv_bfloat162 v;
+                    v = __floats2bfloat162_rn(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+                    pk.x = *reinterpret_cast<uint32_t*>(&v);
+                    v = __floats2bfloat162_rn(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+                    pk.y = *reinterpret_cast<uint32_t*>(&v);
+                    v = __floats2bfloat162_rn(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+                    pk.z = *reinterpret_cast<uint32_t*>(&v);
+                    v = __floats2bfloat162_rn(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+                    pk.w = *reinterpret_cast<uint32_t*>(&v);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + i) = pk;
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<AT_TMEM_COLS>(tmem_base);
+    }
+}
+
+int attn_bidir_legacy(const void* qkv, int64_t ld, const int32_t* cu_seqlens, int32_t n_seq, int32_t max_len,
+                      int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, float softmax_scale, void* out, int64_t ldo,
+                      cudaStream_t st);
+
+static int g_attn_kernel = 0;     // ezr_attn_set_kernel: 0 = tcgen05 (default), 1 = legacy mma.sync kernel (cross-checks)
+static thread_local const char* g_attn_last = "none";
+
+template <int HD>
+static int attn_tc_launch(const CUtensorMap& map, const int32_t* cu, int n_seq, int max_len, int n_heads, int n_kv_heads,
+                          float scale_log2, __nv_bfloat16* out, int64_t ldo, cudaStream_t st) {
+    constexpr int stages = HD == 64 ? 2 : 1;
+    const size_t smem = 1024 + (size_t)(1 + 2 * stages) * (HD / 64) * AT_BOX_BYTES + sizeof(AttnBarriers) + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        EZR_CUDA(cudaFuncSetAttribute(attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EZR_CUDA(cudaFuncSetAttribute(attn_tc_kernel<HD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        attr_done = true;
+    }
+    dim3 grid((max_len + AT_M - 1) / AT_M, n_seq, n_heads);
+    ProfScope prof(EZR_PROF_ENC_ATTN, st);
+    attn_tc_kernel<HD><<<grid, AT_THREADS, smem, st>>>(map, cu, n_heads, n_kv_heads, scale_log2, out, ldo);
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
+}
+
+}  // namespace ezr
+
+extern "C" int ezr_attn_set_kernel(int32_t which) {
+    EZR_CHECK_ARG(which == 0 || which == 1, "attn_set_kernel: 0 = tcgen05, 1 = legacy mma.sync");
+    ezr::g_attn_kernel = which;
+    return EZR_OK;
+}
+
+extern "C" const char* ezr_attn_last_kernel(void) { return ezr::g_attn_last; }
+
+extern "C" int ezr_attn_bidir(const void* qkv, int64_t n_tokens, int64_t ld, const int32_t* cu_seqlens, int32_t n_seq,
+                              int32_t max_len, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, float softmax_scale,
+                              void* out, int64_t ldo, void* stream) {
+    using namespace ezr;
+    EZR_CHECK_ARG(head_dim == 64 || head_dim == 128, "attn: head_dim must be 64 or 128 (got %d)", head_dim);
+    EZR_CHECK_ARG(n_kv_heads >= 1 && n_heads % n_kv_heads == 0, "attn: n_heads must be a multiple of n_kv_heads");
+    EZR_CHECK_ARG(ld % 8 == 0 && ldo % 8 == 0, "attn: row strides must be multiples of 8 elements");
+    EZR_CHECK_ARG(ld >= (int64_t)(n_heads + 2 * n_kv_heads) * head_dim, "attn: qkv rows narrower than (H + 2 KV) * head_dim");
+    EZR_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                  "attn: qkv / out must be 16-byte aligned");
+    EZR_CHECK_ARG(softmax_scale > 0.f, "attn: softmax_scale must be positive");
+    if (n_seq == 0 || max_len == 0 || n_tokens == 0) return EZR_OK;
+    EZR_CHECK_ARG(n_seq <= 65535 && n_heads <= 65535, "attn: grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_attn_kernel == 1) {
+        g_attn_last = "mma.sync";
+        return attn_bidir_legacy(qkv, ld, cu_seqlens, n_seq, max_len, n_heads, n_kv_heads, head_dim, softmax_scale, out,
+                                 ldo, st);
+    }
+    g_attn_last = "tcgen05";
+    CUtensorMap map;
+    int rc = encode_tmap_2d_bf16(&map, qkv, (uint64_t)(n_heads + 2 * n_kv_heads) * head_dim, (uint64_t)n_tokens,
+                                 (uint64_t)ld, 64, 128);
+    if (rc) return rc;
+    const float scale_log2 = softmax_scale * 1.4426950408889634f;
+    return head_dim == 64 ? attn_tc_launch<64>(map, cu_seqlens, n_seq, max_len, n_heads, n_kv_heads, scale_log2,
+                                               (__nv_bfloat16*)out, ldo, st)
+                          : attn_tc_launch<128>(map, cu_seqlens, n_seq, max_len, n_heads, n_kv_heads, scale_log2,
+                                                (__nv_bfloat16*)out, ldo, st);
+}

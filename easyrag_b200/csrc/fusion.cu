@@ -18,34 +18,50 @@ namespace ezr {
 constexpr int kFuseThreads = 128;
 constexpr int kFuseMaxIn = 1024;   // entries per input list
 
+constexpr int kFuseMaxLists = 8;   // rank lists per call (the pipeline passes two: pipeline.py:362,408)
+constexpr int kFuseMaxTotal = 2048; // entries over all lists
+
+struct FuseLists {
+    const int32_t* ids[kFuseMaxLists];
+    const double* sc[kFuseMaxLists];
+    const int32_t* cnt[kFuseMaxLists];
+    int n;
+};
+
 template <bool RRF>
 __global__ void __launch_bounds__(kFuseThreads)
-fuse_kernel(const int32_t* __restrict__ ids_a, const double* __restrict__ sc_a, const int32_t* __restrict__ cnt_a,
-            const int32_t* __restrict__ ids_b, const double* __restrict__ sc_b, const int32_t* __restrict__ cnt_b,
-            int stride_in, const int32_t* __restrict__ canon, int canon_base, int K, int k_out,
+fuse_kernel(const FuseLists lists, int stride_in, const int32_t* __restrict__ canon, int canon_base, int K, int k_out,
             int32_t* __restrict__ out_ids, double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int q = blockIdx.x;
-    const int ca = min(max(cnt_a[q], 0), stride_in);
-    const int cb = min(max(cnt_b[q], 0), stride_in);
-    const int n = ca + cb;
-    // carve: key[n] id[n] rep[n] lead[n] | score[n]
-    const int cap = 2 * stride_in;
+    // off[l] = entries of the lists before list l (list order = insertion order of the reference's loops)
+    int off[kFuseMaxLists + 1];
+    off[0] = 0;
+#pragma unroll
+    for (int l = 0; l < kFuseMaxLists; ++l)
+        off[l + 1] = off[l] + (l < lists.n ? min(max(lists.cnt[l][q], 0), stride_in) : 0);
+    const int n = off[kFuseMaxLists];
+    // carve: score[cap] | key[cap] id[cap] rep[cap] lead[cap] rank[cap]
+    const int cap = lists.n * stride_in;
     double* s_sc = reinterpret_cast<double*>(smem_raw);
     int* s_key = reinterpret_cast<int*>(smem_raw + (size_t)cap * 8);
     int* s_id = s_key + cap;
     int* s_rep = s_id + cap;
     int* s_lead = s_rep + cap;
+    int* s_rank = s_lead + cap;
     __shared__ int s_nlead;
     if (threadIdx.x == 0) s_nlead = 0;
 
     for (int e = threadIdx.x; e < n; e += kFuseThreads) {
-        const bool in_a = e < ca;
-        const int j = in_a ? e : e - ca;
-        const int id = in_a ? ids_a[(int64_t)q * stride_in + j] : ids_b[(int64_t)q * stride_in + j];
+        int l = 0;
+#pragma unroll
+        for (int t = 1; t < kFuseMaxLists; ++t) l += (e >= off[t]) ? 1 : 0;      // off is non-decreasing
+        const int j = e - off[l];
+        const int id = lists.ids[l][(int64_t)q * stride_in + j];
         s_id[e] = id;
         s_key[e] = (canon && id >= 0) ? canon[id - canon_base] : id;
-        if (!RRF) s_sc[e] = in_a ? sc_a[(int64_t)q * stride_in + j] : sc_b[(int64_t)q * stride_in + j];
+        s_rank[e] = j + 1;                                                       // enumerate(rank_list, 1)
+        if (!RRF) s_sc[e] = lists.sc[l][(int64_t)q * stride_in + j];
     }
     __syncthreads();
 
@@ -61,8 +77,7 @@ fuse_kernel(const int32_t* __restrict__ ids_a, const double* __restrict__ sc_a, 
                 int last = e;
                 for (int j = e; j < n; ++j) {
                     if (s_key[j] == key) {
-                        const int rank = (j < ca ? j : j - ca) + 1;
-                        acc = __dadd_rn(acc, __ddiv_rn(1.0, (double)(rank + K)));
+                        acc = __dadd_rn(acc, __ddiv_rn(1.0, (double)(s_rank[j] + K)));
                         last = j;
                     }
                 }
@@ -99,24 +114,27 @@ fuse_kernel(const int32_t* __restrict__ ids_a, const double* __restrict__ sc_a, 
 }
 
 template <bool RRF>
-static int fuse_launch(const int32_t* ids_a, const double* sc_a, const int32_t* cnt_a, const int32_t* ids_b,
-                       const double* sc_b, const int32_t* cnt_b, int n_queries, int stride_in,
-                       const int32_t* canon, int canon_base, int K, int k_out, int32_t* out_ids,
-                       double* out_scores, int32_t* out_counts, cudaStream_t st) {
+static int fuse_launch(const FuseLists& lists, int n_queries, int stride_in, const int32_t* canon, int canon_base, int K,
+                       int k_out, int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st) {
+    EZR_CHECK_ARG(lists.n >= 1 && lists.n <= kFuseMaxLists, "fusion: %d lists (1..%d supported)", lists.n, kFuseMaxLists);
     EZR_CHECK_ARG(stride_in >= 1 && stride_in <= kFuseMaxIn, "fusion: stride_in=%d out of [1,%d]", stride_in,
                   kFuseMaxIn);
+    EZR_CHECK_ARG(lists.n * stride_in <= kFuseMaxTotal, "fusion: %d lists x %d entries > %d", lists.n, stride_in,
+                  kFuseMaxTotal);
     EZR_CHECK_ARG(k_out >= 1, "fusion: k_out must be >= 1");
+    for (int l = 0; l < lists.n; ++l)
+        EZR_CHECK_ARG(lists.ids[l] && lists.cnt[l] && (RRF || lists.sc[l]), "fusion: list %d has a NULL array", l);
     if (n_queries == 0) return EZR_OK;
-    const size_t smem = (size_t)2 * stride_in * (8 + 4 * 4);
+    const size_t smem = (size_t)lists.n * stride_in * (8 + 5 * 4);
     static bool attr_done[2] = {false, false};
     if (!attr_done[RRF ? 1 : 0]) {
         EZR_CUDA(cudaFuncSetAttribute(fuse_kernel<RRF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      2 * kFuseMaxIn * 24));
+                                      kFuseMaxTotal * 28));
         attr_done[RRF ? 1 : 0] = true;
     }
     ProfScope prof(EZR_PROF_FUSE, st);
-    fuse_kernel<RRF><<<n_queries, kFuseThreads, smem, st>>>(ids_a, sc_a, cnt_a, ids_b, sc_b, cnt_b, stride_in, canon,
-                                                            canon_base, K, k_out, out_ids, out_scores, out_counts);
+    fuse_kernel<RRF><<<n_queries, kFuseThreads, smem, st>>>(lists, stride_in, canon, canon_base, K, k_out, out_ids,
+                                                            out_scores, out_counts);
     EZR_LAUNCH_CHECK();
     return EZR_OK;
 }
@@ -131,16 +149,45 @@ int ezr_rrf_fuse(const int32_t* ids_a, const int32_t* cnt_a, const int32_t* ids_
                  int32_t n_queries, int32_t stride_in, const int32_t* canon, int32_t canon_base, int32_t K,
                  int32_t k_out, int32_t* out_ids, double* out_scores, int32_t* out_counts, void* stream) {
     EZR_CHECK_ARG(K >= 0, "rrf: K must be >= 0");
-    return fuse_launch<true>(ids_a, nullptr, cnt_a, ids_b, nullptr, cnt_b, n_queries, stride_in, canon, canon_base,
-                             K, k_out, out_ids, out_scores, out_counts, (cudaStream_t)stream);
+    FuseLists l = {};
+    l.n = 2;
+    l.ids[0] = ids_a; l.cnt[0] = cnt_a;
+    l.ids[1] = ids_b; l.cnt[1] = cnt_b;
+    return fuse_launch<true>(l, n_queries, stride_in, canon, canon_base, K, k_out, out_ids, out_scores, out_counts,
+                             (cudaStream_t)stream);
 }
 
 int ezr_fusion_simple(const int32_t* ids_a, const double* scores_a, const int32_t* cnt_a, const int32_t* ids_b,
                       const double* scores_b, const int32_t* cnt_b, int32_t n_queries, int32_t stride_in,
                       const int32_t* canon, int32_t canon_base, int32_t k_out, int32_t* out_ids,
                       double* out_scores, int32_t* out_counts, void* stream) {
-    return fuse_launch<false>(ids_a, scores_a, cnt_a, ids_b, scores_b, cnt_b, n_queries, stride_in, canon,
-                              canon_base, 0, k_out, out_ids, out_scores, out_counts, (cudaStream_t)stream);
+    FuseLists l = {};
+    l.n = 2;
+    l.ids[0] = ids_a; l.sc[0] = scores_a; l.cnt[0] = cnt_a;
+    l.ids[1] = ids_b; l.sc[1] = scores_b; l.cnt[1] = cnt_b;
+    return fuse_launch<false>(l, n_queries, stride_in, canon, canon_base, 0, k_out, out_ids, out_scores, out_counts,
+                              (cudaStream_t)stream);
+}
+
+int ezr_fuse_lists(int32_t rrf, int32_t n_lists, const int32_t* const* ids_host, const double* const* scores_host,
+                   const int32_t* const* cnt_host, int32_t n_queries, int32_t stride_in, const int32_t* canon,
+                   int32_t canon_base, int32_t K, int32_t k_out, int32_t* out_ids, double* out_scores,
+                   int32_t* out_counts, void* stream) {
+    EZR_CHECK_ARG(n_lists >= 1 && n_lists <= kFuseMaxLists, "fuse_lists: %d lists (1..%d supported)", n_lists,
+                  kFuseMaxLists);
+    EZR_CHECK_ARG(ids_host && cnt_host && (rrf || scores_host), "fuse_lists: NULL pointer table");
+    EZR_CHECK_ARG(!rrf || K >= 0, "rrf: K must be >= 0");
+    FuseLists l = {};
+    l.n = n_lists;
+    for (int i = 0; i < n_lists; ++i) {
+        l.ids[i] = ids_host[i];
+        l.cnt[i] = cnt_host[i];
+        l.sc[i] = scores_host ? scores_host[i] : nullptr;
+    }
+    return rrf ? fuse_launch<true>(l, n_queries, stride_in, canon, canon_base, K, k_out, out_ids, out_scores, out_counts,
+                                   (cudaStream_t)stream)
+               : fuse_launch<false>(l, n_queries, stride_in, canon, canon_base, 0, k_out, out_ids, out_scores,
+                                    out_counts, (cudaStream_t)stream);
 }
 
 }  // extern "C"

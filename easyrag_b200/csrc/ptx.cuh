@@ -148,6 +148,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// MN-major operand tile (the contraction index is the ROW of the tile, e.g. V[key][head_dim] as the B operand of
+// O += P.V), 128-byte swizzle: rows of 64 bf16 = 128 B along M/N, 8-row atoms of 1024 B along K.  Canonical form
+// (CUTLASS cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): in 16-byte units
+// Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) -- SBO = byte distance between 8-row groups along K (1024 when the
+// rows are contiguous), LBO = byte distance between 64-element groups along M/N (the next TMA box).
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+constexpr uint32_t kIdescBMajorMN = 1u << 16;     // UMMA::InstrDescriptor b_major_: B is MN-major
+
 // UMMA::InstrDescriptor for kind::f16: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major A and B,
 // n_dim = N>>3 @17, m_dim = M>>4 @24.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
@@ -178,6 +189,19 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
+}
+// registers -> 32 lanes x 16 columns (softmax probabilities packed two bf16 per column)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// sub-CTA barrier: `count` threads (a multiple of 32) meet at hardware barrier `id` (1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -50,7 +50,7 @@ def attention(qkv: torch.Tensor, cu: torch.Tensor, max_len: int, n_heads: int, n
     t = qkv.shape[0]
     if out is None:
         out = torch.empty(t, n_heads * head_dim, dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(L.ezr_attn_bidir(_lib.ptr(qkv), qkv.stride(0), _lib.ptr(cu), cu.numel() - 1, max_len, n_heads, n_kv,
+    _lib.check(L.ezr_attn_bidir(_lib.ptr(qkv), t, qkv.stride(0), _lib.ptr(cu), cu.numel() - 1, max_len, n_heads, n_kv,
                                 head_dim, 1.0 / math.sqrt(head_dim), _lib.ptr(out), out.stride(0), _lib.stream_ptr()),
                "ezr_attn_bidir")
     return out

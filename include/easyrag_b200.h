@@ -200,6 +200,15 @@ int ezr_fusion_simple(const int32_t* ids_a, const double* scores_a, const int32_
                       const int32_t* canon, int32_t canon_base, int32_t k_out, int32_t* out_ids,
                       double* out_scores, int32_t* out_counts, void* stream);
 
+/* Both fusions over ANY number of rank lists (the reference's loops take a list of lists, retrievers.py:243,261;
+ * the pipeline passes two).  ids_host / scores_host / cnt_host are HOST arrays of n_lists DEVICE pointers (each list
+ * laid out like ids_a / scores_a / cnt_a above; scores_host may be NULL for RRF); list order = insertion order.
+ * rrf != 0: reciprocal_rank_fusion, else fusion.  n_lists <= 8, n_lists * stride_in <= 2048. */
+int ezr_fuse_lists(int32_t rrf, int32_t n_lists, const int32_t* const* ids_host, const double* const* scores_host,
+                   const int32_t* const* cnt_host, int32_t n_queries, int32_t stride_in, const int32_t* canon,
+                   int32_t canon_base, int32_t K, int32_t k_out, int32_t* out_ids, double* out_scores,
+                   int32_t* out_counts, void* stream);
+
 /* ------------------------------------------------------------ encoder ---
  * Building blocks of the chunk/query embedding forward pass (GTEEmbedding._embed, gte_embeddings.py:59-72 ->
  * Qwen2Model.forward, modeling_qwen.py:956-1116; HuggingFaceEmbedding._embed, hf_embeddings.py:112-123 ->
@@ -212,10 +221,16 @@ int ezr_fusion_simple(const int32_t* ids_a, const double* scores_a, const int32_
 int ezr_gemm_bf16(const void* a, int32_t m, int32_t k, int64_t lda, const void* w, int32_t n, int64_t ldw,
                   const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo, int32_t epilogue,
                   void* stream);
-/* non-causal attention over packed q|k|v rows ([T, (H + 2*KV) * hd]); head_dim 64 or 128; GQA via n_kv_heads */
-int ezr_attn_bidir(const void* qkv, int64_t ld, const int32_t* cu_seqlens, int32_t n_seq, int32_t max_len,
-                   int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, float softmax_scale, void* out, int64_t ldo,
-                   void* stream);
+/* non-causal attention over packed q|k|v rows ([n_tokens, (H + 2*KV) * hd], row stride ld); head_dim 64 or 128; GQA
+ * via n_kv_heads.  Default kernel: tcgen05 (S = QK^T and O += PV on the 5th-gen tensor cores, S/P/O in tensor memory,
+ * Q/K/V tiles by TMA).  n_tokens bounds the TMA tensor map (tiles that run past the last token are zero-filled). */
+int ezr_attn_bidir(const void* qkv, int64_t n_tokens, int64_t ld, const int32_t* cu_seqlens, int32_t n_seq,
+                   int32_t max_len, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, float softmax_scale, void* out,
+                   int64_t ldo, void* stream);
+/* 0 = tcgen05 kernel (default), 1 = the warp-level mma.sync kernel it replaced (kept as an independent cross-check) */
+int ezr_attn_set_kernel(int32_t which);
+/* "tcgen05" / "mma.sync": what the last ezr_attn_bidir call on this thread launched */
+const char* ezr_attn_last_kernel(void);
 int ezr_embed_gather(const int32_t* ids, int32_t n_tokens, const void* table, int64_t ldt, int32_t vocab, int32_t dim,
                      void* out, int64_t ldo, void* stream);
 /* BERT embeddings: LayerNorm(word[id] + type[0] + position[pos]) */

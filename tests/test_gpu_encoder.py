@@ -95,6 +95,75 @@ def test_attention_packed_bidirectional(hd, H, KV):
         o += n
 
 
+def _attn_ref(qkv, lens, H, KV, hd):
+    t = sum(lens)
+    q = qkv.float()[:, :H * hd].view(t, H, hd)
+    k = qkv.float()[:, H * hd:(H + KV) * hd].view(t, KV, hd).repeat_interleave(H // KV, 1)
+    v = qkv.float()[:, (H + KV) * hd:].view(t, KV, hd).repeat_interleave(H // KV, 1)
+    out = torch.empty(t, H, hd)
+    o = 0
+    for n in lens:
+        qq, kk, vv = (z[o:o + n].transpose(0, 1) for z in (q, k, v))
+        out[o:o + n] = (torch.softmax(qq @ kk.transpose(1, 2) / hd ** 0.5, -1) @ vv).transpose(0, 1)
+        o += n
+    return out
+
+
+@pytest.mark.parametrize("hd,H,KV", [(64, 3, 3), (64, 4, 2), (128, 2, 2), (128, 4, 1)])
+def test_attention_tcgen05_ragged_lengths_and_kernel_name(hd, H, KV):
+    """Every tile-boundary case of the 128-row / 128-key tiling (and the 16-key granularity of the last tile), a
+    sequence that ends exactly at the last token of the buffer, sequences longer than four key tiles."""
+    lens = [1, 15, 16, 17, 127, 128, 129, 255, 256, 257, 300, 512, 700, 3, 31]
+    qkv = _rand(sum(lens), (H + 2 * KV) * hd, seed=7 * hd + H, scale=0.8)
+    cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=DEV)
+    got = enc.attention(qkv.to(DEV), cu, max(lens), H, KV, hd).float().cpu()
+    assert _lib.lib().ezr_attn_last_kernel() == b"tcgen05"
+    ref = _attn_ref(qkv, lens, H, KV, hd)
+    _close(got.view(-1, H, hd), ref, rtol=2e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("hd", [64, 128])
+def test_attention_tcgen05_rescales_when_the_row_maximum_grows(hd):
+    """Keys are arranged so that every later key tile raises the row maximum by far more than 2^8: the lazy
+    rescaling of O in tensor memory must fire on every tile (and must not fire wrongly on flat tiles)."""
+    H = KV = 2
+    lens = [640, 384, 130]
+    t = sum(lens)
+    g = torch.Generator().manual_seed(11)
+    qkv = (torch.randn(t, 3 * H * hd, generator=g) * 0.5)
+    o = 0
+    for n in lens:                                           # key norm grows with the tile index -> logits grow
+        for j in range(0, n, 128):
+            qkv[o + j:o + min(n, j + 128), H * hd:2 * H * hd] *= 1.0 + 2.5 * (j // 128)
+        o += n
+    qkv[:, :H * hd] = qkv[:, :H * hd].abs()                  # same-sign q . k so the growth is systematic
+    qkv[:, H * hd:2 * H * hd] = qkv[:, H * hd:2 * H * hd].abs()
+    qkv = qkv.to(torch.bfloat16)
+    cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=DEV)
+    got = enc.attention(qkv.to(DEV), cu, max(lens), H, KV, hd).float().cpu()
+    ref = _attn_ref(qkv, lens, H, KV, hd)
+    assert torch.isfinite(got).all()
+    _close(got.view(-1, H, hd), ref, rtol=2e-2, atol=1e-2)
+
+
+def test_attention_tcgen05_agrees_with_the_mma_sync_kernel():
+    """Two independent implementations of the same function (tcgen05 vs the warp-level kernel it replaced)."""
+    L = _lib.lib()
+    hd, H, KV = 64, 12, 12
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(8, 513, (40,), generator=g).tolist()
+    qkv = _rand(sum(lens), (H + 2 * KV) * hd, seed=3, scale=0.6).to(DEV)
+    cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=DEV)
+    a = enc.attention(qkv, cu, max(lens), H, KV, hd).float()
+    try:
+        _lib.check(L.ezr_attn_set_kernel(1))
+        b = enc.attention(qkv, cu, max(lens), H, KV, hd).float()
+        assert L.ezr_attn_last_kernel() == b"mma.sync"
+    finally:
+        _lib.check(L.ezr_attn_set_kernel(0))
+    assert (a - b).abs().max().item() < 2e-2
+
+
 # ------------------------------------------------------------------------- norms, rope, pool
 def test_rmsnorm_layernorm():
     x, g, b = _rand(333, 768, seed=1, scale=3), 1 + _rand(768, seed=2, scale=0.1), _rand(768, seed=3)
