@@ -8,7 +8,7 @@ arithmetic is in easyrag_b200/csrc/*.cu.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -204,6 +204,32 @@ def fusion_simple(ids_a: torch.Tensor, sc_a: torch.Tensor, cnt_a: torch.Tensor, 
                                        _lib.ptr(ids_b.contiguous()), _lib.ptr(sb), _lib.ptr(cnt_b), nq, stride,
                                        _lib.ptr(canon), 0, k_out, _lib.ptr(out.ids), _lib.ptr(out.scores),
                                        _lib.ptr(out.counts), _lib.stream_ptr(stream)), "ezr_fusion_simple")
+    return out
+
+
+def fuse_lists(ids: Sequence[torch.Tensor], counts: Sequence[torch.Tensor], k_out: int, rrf: bool = True, K: int = 60,
+               scores: Optional[Sequence[torch.Tensor]] = None, canon: Optional[torch.Tensor] = None, stream=None) -> TopK:
+    """``reciprocal_rank_fusion`` / ``fusion`` over ANY number of rank lists (retrievers.py:239-274 loop over a list
+    of lists).  ``ids[l]`` int32 [Q, width], ``counts[l]`` int32 [Q], ``scores[l]`` float64 [Q, width] (fusion only);
+    all lists share ``width``."""
+    import ctypes as C
+    L = _lib.lib()
+    n = len(ids)
+    dev = ids[0].device
+    nq, width = ids[0].shape
+    ids = [t.contiguous() for t in ids]
+    assert all(t.shape == (nq, width) and t.dtype == torch.int32 for t in ids) and len(counts) == n
+    sc = None
+    if not rrf:
+        sc = [t.to(torch.float64).contiguous() for t in scores]
+        assert all(t.shape == (nq, width) for t in sc)
+    out = TopK(torch.empty(nq, k_out, dtype=torch.float64, device=dev),
+               torch.empty(nq, k_out, dtype=torch.int32, device=dev), torch.empty(nq, dtype=torch.int32, device=dev))
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    with torch.cuda.device(dev):
+        _lib.check(L.ezr_fuse_lists(int(rrf), n, arr(ids), arr(sc) if sc is not None else None, arr(counts), nq, width,
+                                    _lib.ptr(canon), 0, K, k_out, _lib.ptr(out.ids), _lib.ptr(out.scores),
+                                    _lib.ptr(out.counts), _lib.stream_ptr(stream)), "ezr_fuse_lists")
     return out
 
 

@@ -118,6 +118,28 @@ static thread_local const char* g_last_kernel = "none";
 
 }  // namespace ezr
 
+namespace ezr {
+// Insert path of the vector store (a Distance.COSINE collection normalises at insert, ingestion.py:180-182):
+// out[r] = bf16( x[r] / max(||x[r]||_2, 1e-12) ), fp32 math, one warp per row.  SRC = float or __nv_bfloat16.
+template <typename SRC>
+__global__ void normalize_rows_kernel(const SRC* __restrict__ x, int64_t ldx, int64_t n_rows, int dim,
+                                      __nv_bfloat16* __restrict__ out, int64_t ldo) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const SRC* xr = x + row * ldx;
+    float q = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float v = (float)xr[i];
+        q = fmaf(v, v, q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float inv = 1.0f / fmaxf(sqrtf(q), 1e-12f);
+    for (int i = lane; i < dim; i += 32) out[row * ldo + i] = __float2bfloat16((float)xr[i] * inv);
+}
+}  // namespace ezr
+
 using namespace ezr;
 
 extern "C" {
@@ -187,6 +209,22 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
     g_last_kernel = "simt";
     return simt_topk(c, n_rows, dim, ld_corpus, q, n_queries, ld_queries, k, doc_group, q_group, id_base, out_scores,
                      out_ids, out_counts, workspace, workspace_bytes, st);
+}
+
+int ezr_normalize_rows(const void* x, int32_t x_is_f32, int64_t ldx, int64_t n_rows, int32_t dim, void* out_bf16,
+                       int64_t ldo, void* stream) {
+    EZR_CHECK_ARG(dim >= 1 && ldx >= dim && ldo >= dim, "normalize_rows: bad dim / strides");
+    if (n_rows <= 0) return EZR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((n_rows + wpb - 1) / wpb);
+    if (x_is_f32)
+        normalize_rows_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, n_rows, dim, (__nv_bfloat16*)out_bf16, ldo);
+    else
+        normalize_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, n_rows, dim,
+                                                                     (__nv_bfloat16*)out_bf16, ldo);
+    EZR_LAUNCH_CHECK();
+    return EZR_OK;
 }
 
 }  // extern "C"

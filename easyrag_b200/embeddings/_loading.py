@@ -23,7 +23,7 @@ def load_state_dict(model_dir: str) -> Dict[str, torch.Tensor]:
             state.update(load_file(str(s)))
     else:
         for s in sorted(d.glob("pytorch_model*.bin")):
-            state.update(torch.load(str(s), map_location="cpu"))
+            state.update(torch.load(str(s), map_location="cpu", weights_only=True))   # tensors only: never unpickle code
     if not state:
         raise FileNotFoundError(f"no weights found under {model_dir}")
     return state

@@ -13,11 +13,17 @@ import torch
 
 from ..encoder import PackedBatch, Qwen2Config, Qwen2Encoder
 from ..retrievers import get_node_content
-from ..schema import BaseEmbedding
+from ..schema import BaseEmbedding, PrivateAttr
 from . import _loading
 
 
 class GTEEmbedding(BaseEmbedding):
+    # gte_embeddings.py:23-26: private attributes of a (pydantic, when llama_index is installed) BaseEmbedding
+    _model: Any = PrivateAttr()
+    _tokenizer: Any = PrivateAttr()
+    _device: str = PrivateAttr()
+    _embed_type: int = PrivateAttr()
+
     def __init__(self, model_name: str = None, embed_type: int = 0, encoder: Qwen2Encoder = None, tokenizer=None,
                  device: str = "cuda", **kwargs: Any) -> None:
         if encoder is None:
@@ -31,12 +37,12 @@ class GTEEmbedding(BaseEmbedding):
             encoder = Qwen2Encoder(cfg, _loading.strip_prefix(_loading.load_state_dict(model_name)), device=device)
         if tokenizer is None:
             tokenizer = _loading.load_tokenizer(model_name)
+        kwargs.setdefault("model_name", model_name or "gte-qwen2")
+        super().__init__(**kwargs)                 # base fields first, private attributes after (pydantic v1 and v2)
         self._model = encoder
         self._tokenizer = tokenizer
         self._device = str(encoder.device)
         self._embed_type = embed_type
-        kwargs.setdefault("model_name", model_name or "gte-qwen2")
-        super().__init__(**kwargs)
 
     def get_detailed_instruct(self, query: str) -> str:
         """gte_embeddings.py:52-53."""
@@ -48,7 +54,7 @@ class GTEEmbedding(BaseEmbedding):
 
     def embed_tensor(self, texts: List[str]):
         """-> (bf16 [B, d] on the device, float32 [B, d] on the device); gte_embeddings.py:59-71 without the lists."""
-        max_length = 8192
+        max_length = min(8192, int(self._model.cfg.max_position_embeddings))     # gte_embeddings.py:60 caps at 8192
         batch_dict = self._tokenizer(texts, max_length=max_length, padding=True, truncation=True, return_tensors='pt')
         batch = PackedBatch.from_padded(torch.as_tensor(batch_dict['input_ids']),
                                         torch.as_tensor(batch_dict['attention_mask']), self._model.device)

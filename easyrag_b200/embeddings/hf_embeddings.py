@@ -14,7 +14,7 @@ import torch
 
 from ..encoder import BertConfig, BertEncoder, PackedBatch
 from ..retrievers import get_node_content
-from ..schema import BaseEmbedding
+from ..schema import BaseEmbedding, Field, PrivateAttr
 from . import _loading
 
 DEFAULT_HUGGINGFACE_LENGTH = 512
@@ -49,6 +49,20 @@ def _pooling_from_dir(model_dir: str) -> str:
 
 
 class HuggingFaceEmbedding(BaseEmbedding):
+    # declared like the reference (hf_embeddings.py:26-43): with llama_index installed BaseEmbedding is a pydantic
+    # model, which only accepts declared fields / private attributes
+    max_length: int = Field(default=DEFAULT_HUGGINGFACE_LENGTH, description="Maximum length of input.", gt=0)
+    normalize: bool = Field(default=True, description="Normalize embeddings or not.")
+    query_instruction: Optional[str] = Field(default=None, description="Instruction to prepend to query text.")
+    text_instruction: Optional[str] = Field(default=None, description="Instruction to prepend to text.")
+    cache_folder: Optional[str] = Field(default=None, description="Cache folder for Hugging Face files.")
+
+    _model: Any = PrivateAttr()
+    _tok: Any = PrivateAttr()
+    _prompts: Any = PrivateAttr()
+    _device: str = PrivateAttr()
+    _embed_type: int = PrivateAttr()
+
     def __init__(self, model_name: str = DEFAULT_HUGGINGFACE_EMBEDDING_MODEL, tokenizer_name: Optional[str] = "deprecated",
                  pooling: str = "deprecated", max_length: Optional[int] = None, query_instruction: Optional[str] = None,
                  text_instruction: Optional[str] = None, normalize: bool = True, model: Optional[Any] = "deprecated",
@@ -56,8 +70,7 @@ class HuggingFaceEmbedding(BaseEmbedding):
                  cache_folder: Optional[str] = None, trust_remote_code: bool = False, device: Optional[str] = None,
                  callback_manager=None, embed_type: int = 0, encoder: BertEncoder = None, hf_tokenizer=None,
                  **model_kwargs):
-        self._device = device or "cuda"
-        self._embed_type = embed_type
+        device = device or "cuda"
         for variable, value in [("model", model), ("tokenizer", tokenizer), ("pooling", pooling),
                                 ("tokenizer_name", tokenizer_name)]:
             if value != "deprecated":
@@ -72,17 +85,22 @@ class HuggingFaceEmbedding(BaseEmbedding):
                              max_position_embeddings=c.get("max_position_embeddings", 512),
                              layer_norm_eps=c.get("layer_norm_eps", 1e-12))
             encoder = BertEncoder(cfg, _loading.strip_prefix(_loading.load_state_dict(model_name)),
-                                  device=self._device, pooling=_pooling_from_dir(model_name))
+                                  device=device, pooling=_pooling_from_dir(model_name))
+        max_pos = int(encoder.cfg.max_position_embeddings)
+        max_length = max_length or min(DEFAULT_HUGGINGFACE_LENGTH, max_pos)
+        if max_length > max_pos:
+            # the position table has max_pos rows; a longer input would index past it
+            raise ValueError(f"max_length={max_length} exceeds the model's max_position_embeddings={max_pos}")
+        # public fields go through the base constructor (pydantic validates them), private attributes after it
+        super().__init__(embed_batch_size=embed_batch_size, callback_manager=callback_manager, model_name=model_name,
+                         max_length=max_length, normalize=normalize, query_instruction=query_instruction,
+                         text_instruction=text_instruction, cache_folder=cache_folder)
+        self._device = device
+        self._embed_type = embed_type
         self._model = encoder
         self._tok = hf_tokenizer if hf_tokenizer is not None else _loading.load_tokenizer(model_name)
         self._prompts = {"query": query_instruction or get_query_instruct_for_model_name(model_name),
                          "text": text_instruction or get_text_instruct_for_model_name(model_name)}
-        self.max_length = max_length or min(DEFAULT_HUGGINGFACE_LENGTH, encoder.cfg.max_position_embeddings)
-        self.normalize = normalize
-        self.query_instruction = query_instruction
-        self.text_instruction = text_instruction
-        self.cache_folder = cache_folder
-        super().__init__(embed_batch_size=embed_batch_size, callback_manager=callback_manager, model_name=model_name)
 
     @classmethod
     def class_name(cls) -> str:

@@ -83,6 +83,16 @@ class PackedBatch:
     positions: torch.Tensor    # int32 [T]
     max_len: int
     n_seq: int
+    max_pos: Optional[int] = None   # largest position id + 1 (host-known when built by from_lists / from_padded)
+
+    def check_positions(self, limit: int) -> None:
+        """The rope / position-embedding kernels index tables of ``limit`` rows; an id past the table would read
+        the clamped last row and give a silently wrong embedding, so it is an error here."""
+        if self.max_pos is None:
+            self.max_pos = int(self.positions.max()) + 1 if self.positions.numel() else 0
+        if self.max_pos > limit:
+            raise ValueError(f"position id {self.max_pos - 1} outside the model's table of {limit} positions "
+                             f"(lower max_length or use a model with a longer max_position_embeddings)")
 
     @staticmethod
     def from_lists(seqs: Sequence[Sequence[int]], device, pos_offset: Optional[Sequence[int]] = None) -> "PackedBatch":
@@ -98,7 +108,7 @@ class PackedBatch:
         return PackedBatch(ids=torch.tensor(flat, dtype=torch.int32, device=device),
                            cu=torch.tensor(cu, dtype=torch.int32, device=device),
                            positions=torch.tensor(pos, dtype=torch.int32, device=device),
-                           max_len=max(lens) if lens else 0, n_seq=len(lens))
+                           max_len=max(lens) if lens else 0, n_seq=len(lens), max_pos=(max(pos) + 1) if pos else 0)
 
     @staticmethod
     def from_padded(input_ids: torch.Tensor, attention_mask: torch.Tensor, device,
@@ -192,6 +202,7 @@ class Qwen2Encoder:
         t = batch.ids.numel()
         d, hd, H, KV = cfg.hidden_size, cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads
         dev = self.device
+        batch.check_positions(cfg.max_position_embeddings)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr()
             x = torch.empty(t, d, dtype=torch.bfloat16, device=dev)
@@ -295,6 +306,7 @@ class BertEncoder:
         t = batch.ids.numel()
         d, hd, H = cfg.hidden_size, cfg.head_dim, cfg.num_attention_heads
         dev = self.device
+        batch.check_positions(cfg.max_position_embeddings)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr()
             x = torch.empty(t, d, dtype=torch.bfloat16, device=dev)

@@ -288,21 +288,85 @@ class Bm25Index:
         return self
 
 
-class DenseIndex:
-    """Row-major bf16 matrix of L2-normalised chunk embeddings (rows ``[row_lo, row_hi)`` of the corpus)."""
+def normalize_rows(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out (bf16 [n, d], may be a slice of a larger matrix) = L2-normalised rows of x (float32 or bf16, on the device)."""
+    assert x.dim() == 2 and out.shape == x.shape and x.stride(1) == 1 and out.stride(1) == 1
+    assert out.dtype == torch.bfloat16 and x.dtype in (torch.float32, torch.bfloat16) and x.device == out.device
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().ezr_normalize_rows(_lib.ptr(x), int(x.dtype == torch.float32), x.stride(0), x.shape[0],
+                                                 x.shape[1], _lib.ptr(out), out.stride(0), _lib.stream_ptr()),
+                   "ezr_normalize_rows")
+    return out
 
-    def __init__(self, vectors: torch.Tensor, device=None, row_lo: int = 0, doc_group: Optional[torch.Tensor] = None,
-                 normalize: bool = False):
+
+class DenseIndex:
+    """Row-major bf16 matrix of L2-normalised chunk embeddings (rows ``[row_lo, row_hi)`` of the corpus).
+
+    The matrix lives in a buffer with spare capacity: :meth:`reserve` + :meth:`rows_for_append` hand out slices
+    the encoder writes into directly (``embed_packed`` -> slice, no Python lists, no rebuild), :meth:`append`
+    copies / normalises a block of new rows behind the existing ones in amortised O(new rows).
+    """
+
+    def __init__(self, vectors: Optional[torch.Tensor], device=None, row_lo: int = 0,
+                 doc_group: Optional[torch.Tensor] = None, normalize: bool = False, dim: Optional[int] = None,
+                 capacity: int = 0):
         _lib.require_cuda()
         device = torch.device(device if device is not None else "cuda")
-        v = vectors.to(device)
-        if normalize:
-            v = torch.nn.functional.normalize(v.float(), dim=1)
-        self.vectors = v.to(torch.bfloat16).contiguous()
-        self.n_rows, self.dim = self.vectors.shape
-        self.row_lo = row_lo
         self.device = device
+        self.row_lo = row_lo
+        if vectors is None:
+            if dim is None:
+                raise ValueError("DenseIndex: pass vectors or dim")
+            self._buf = torch.empty(max(capacity, 0), dim, dtype=torch.bfloat16, device=device)
+            self.n_rows, self.dim = 0, dim
+        else:
+            v = vectors.to(device)
+            if normalize:
+                src = v if v.dtype in (torch.float32, torch.bfloat16) else v.float()
+                buf = torch.empty(max(capacity, v.shape[0]), v.shape[1], dtype=torch.bfloat16, device=device)
+                normalize_rows(src.contiguous(), buf[:v.shape[0]])
+            elif capacity > v.shape[0]:
+                buf = torch.empty(capacity, v.shape[1], dtype=torch.bfloat16, device=device)
+                buf[:v.shape[0]].copy_(v)
+            else:
+                buf = v.to(torch.bfloat16).contiguous()
+            self._buf = buf
+            self.n_rows, self.dim = v.shape
         self.doc_group = None if doc_group is None else doc_group.to(device=device, dtype=torch.int32).contiguous()
+
+    @property
+    def vectors(self) -> torch.Tensor:
+        """The live rows (a view of the capacity buffer)."""
+        return self._buf[:self.n_rows]
+
+    def reserve(self, n_rows: int) -> None:
+        """Make room for ``n_rows`` rows in total (geometric growth, one copy of the live rows when it grows)."""
+        if n_rows <= self._buf.shape[0]:
+            return
+        cap = max(n_rows, int(self._buf.shape[0] * 1.5) + 64)
+        buf = torch.empty(cap, self.dim, dtype=torch.bfloat16, device=self.device)
+        buf[:self.n_rows].copy_(self._buf[:self.n_rows])
+        self._buf = buf
+
+    def rows_for_append(self, n: int) -> torch.Tensor:
+        """A writable [n, dim] bf16 slice right behind the live rows; call :meth:`commit` once it is filled."""
+        self.reserve(self.n_rows + n)
+        return self._buf[self.n_rows:self.n_rows + n]
+
+    def commit(self, n: int) -> None:
+        self.n_rows += n
+        self.doc_group = None            # per-row classes are rebuilt by the owner (they depend on the filter keys)
+
+    def append(self, vectors: torch.Tensor, normalize: bool = False) -> None:
+        v = vectors.to(self.device)
+        if v.shape[1] != self.dim:
+            raise ValueError(f"append: dim {v.shape[1]} != {self.dim}")
+        dst = self.rows_for_append(v.shape[0])
+        if normalize:
+            normalize_rows((v if v.dtype in (torch.float32, torch.bfloat16) else v.float()).contiguous(), dst)
+        else:
+            dst.copy_(v)
+        self.commit(v.shape[0])
 
     def save(self, path: str) -> None:
         arrays = dict(vectors=self.vectors)

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib, batched
-from .index import Bm25Index, Bm25Stats, DenseIndex, K1, B, EPSILON
+from .index import Bm25Index, Bm25Stats, DenseIndex, K1, B, EPSILON, normalize_rows
 from .schema import (BaseEmbedding, BaseNode, BaseRetriever, NodeWithScore, QueryBundle, VectorStoreQuery,
                      VectorStoreQueryResult, filter_conditions)
 
@@ -68,8 +68,11 @@ class _GroupTable:
     becomes the index of the wanted tuple (or -2: no document can match).  Built once per key set.
     """
 
-    def __init__(self, nodes: Sequence[Any]):
+    def __init__(self, nodes: Sequence[Any], missing: Any = None):
+        """``missing``: None keeps the reference's BM25 behaviour (a node without the key raises KeyError,
+        retrievers.py:200); a sentinel makes such a node match nothing, as a Qdrant payload filter does."""
         self._nodes = nodes
+        self._missing = missing
         self._tables: Dict[Tuple[str, ...], Tuple[Dict[tuple, int], torch.Tensor]] = {}
 
     def resolve(self, conditions: Optional[Dict[str, Any]]):
@@ -81,8 +84,10 @@ class _GroupTable:
             table: Dict[tuple, int] = {}
             ids = np.empty(len(self._nodes), dtype=np.int32)
             for i, n in enumerate(self._nodes):
-                # a missing key raises KeyError in the reference (retrievers.py:200); keep that
-                tup = tuple(_hashable(n.metadata[k]) for k in keys)
+                if self._missing is None:      # a missing key raises KeyError in the reference (retrievers.py:200)
+                    tup = tuple(_hashable(n.metadata[k]) for k in keys)
+                else:
+                    tup = tuple(_hashable(n.metadata.get(k, self._missing)) for k in keys)
                 ids[i] = table.setdefault(tup, len(table))
             self._tables[keys] = (table, torch.from_numpy(ids))
         table, ids = self._tables[keys]
@@ -108,11 +113,17 @@ def _canon_ids(texts: Sequence[str]) -> np.ndarray:
 
 
 # ---------------------------------------------------------------- dense route
+_MISSING = ("<missing metadata key>",)      # sentinel: a node without the filter key matches no filter value
+
+
 class B200VectorStore:
     """In-HBM replacement for the Qdrant collection (ingestion.py:155-191): exact cosine search.
 
     ``query`` / ``aquery`` keep ``QdrantVectorStore``'s call shape used at retrievers.py:44-47,61-64.
-    Vectors are L2-normalised at insert, as a Distance.COSINE collection does, and held in bf16.
+    Vectors are L2-normalised at insert, as a Distance.COSINE collection does, and held in bf16.  ``add`` appends
+    (amortised O(new nodes)); :meth:`add_embedded` takes the encoder's device tensor directly and
+    :meth:`from_embed_model` lets the embedding model write its bf16 rows straight into the corpus matrix -- no
+    Python float lists between the encoder and the index.
     """
 
     def __init__(self, nodes: Optional[Sequence[Any]] = None, device="cuda"):
@@ -120,17 +131,70 @@ class B200VectorStore:
         self.nodes: List[Any] = []
         self.index: Optional[DenseIndex] = None
         self._groups: Optional[_GroupTable] = None
+        self._group_cache: Dict[Tuple[str, ...], torch.Tensor] = {}
         self._ws = None
         if nodes:
             self.add(nodes)
 
-    def add(self, nodes: Sequence[Any]) -> List[str]:
-        self.nodes = list(self.nodes) + list(nodes)
-        emb = torch.tensor([n.embedding for n in self.nodes], dtype=torch.float32)
-        self.index = DenseIndex(emb, device=self.device, normalize=True)
-        self._groups = _GroupTable(self.nodes)
-        self._ws = batched.Workspace(self.index.device)
+    def _ensure_index(self, dim: int) -> DenseIndex:
+        if self.index is None:
+            self.index = DenseIndex(None, device=self.device, dim=dim)
+            self._ws = batched.Workspace(self.index.device)
+        elif self.index.dim != dim:
+            raise ValueError(f"embedding dim {dim} != collection dim {self.index.dim}")
+        return self.index
+
+    def _registered(self, nodes: Sequence[Any]) -> List[str]:
+        self.nodes.extend(nodes)
+        self._groups = _GroupTable(self.nodes, missing=_MISSING)
+        self._group_cache.clear()
         return [n.node_id for n in nodes]
+
+    def add(self, nodes: Sequence[Any]) -> List[str]:
+        """VectorStore.add: nodes carrying ``.embedding`` lists (what the ingestion pipeline produces)."""
+        nodes = list(nodes)
+        if not nodes:
+            return []
+        emb = torch.tensor([n.embedding for n in nodes], dtype=torch.float32)        # the new nodes only
+        self._ensure_index(emb.shape[1]).append(emb, normalize=True)
+        return self._registered(nodes)
+
+    def add_embedded(self, nodes: Sequence[Any], embeddings: torch.Tensor) -> List[str]:
+        """Nodes plus their embeddings as a tensor ([n, d] float32 / bf16, host or device): no Python lists."""
+        nodes = list(nodes)
+        if embeddings.shape[0] != len(nodes):
+            raise ValueError("add_embedded: one embedding row per node")
+        self._ensure_index(embeddings.shape[1]).append(embeddings, normalize=True)
+        return self._registered(nodes)
+
+    @classmethod
+    def from_embed_model(cls, nodes: Sequence[Any], embed_model, device="cuda", batch_size: Optional[int] = None
+                         ) -> "B200VectorStore":
+        """Corpus encode written in place (replaces pipeline.py:141-158 + ingestion.py:155-191): every batch of
+        ``embed_model.embed_tensor`` lands in its slice of the corpus matrix, normalised on the way."""
+        store = cls(device=device)
+        nodes = list(nodes)
+        bs = int(batch_size or getattr(embed_model, "embed_batch_size", 128) or 128)
+        embed_type = getattr(embed_model, "_embed_type", 0)
+        for i in range(0, len(nodes), bs):
+            part = nodes[i:i + bs]
+            texts = [get_node_content(n, embed_type) for n in part]
+            out = embed_model.embed_tensor(texts, "text") if _takes_prompt(embed_model) else embed_model.embed_tensor(texts)
+            emb_bf16 = out[0]                                   # (bf16 [B, d], float32 [B, d]) on the device
+            index = store._ensure_index(emb_bf16.shape[1])
+            if i == 0:
+                index.reserve(len(nodes))
+            index.append(emb_bf16, normalize=True)
+        store._registered(nodes)
+        return store
+
+    def _doc_group(self, keys: Tuple[str, ...], ids: torch.Tensor) -> torch.Tensor:
+        """Per-row class ids of a filter-key tuple on the device, uploaded once per key set (not per query)."""
+        t = self._group_cache.get(keys)
+        if t is None:
+            t = ids.to(self.index.device)
+            self._group_cache[keys] = t
+        return t
 
     def query(self, query: VectorStoreQuery, qdrant_filters=None, **kwargs) -> VectorStoreQueryResult:
         if self.index is None:
@@ -138,12 +202,14 @@ class B200VectorStore:
         k = int(query.similarity_top_k)
         if not 1 <= k <= MAX_TOP_K:
             raise ValueError(f"similarity_top_k={k} outside [1, {MAX_TOP_K}]")
-        q = torch.tensor([query.query_embedding], dtype=torch.float32, device=self.index.device)
-        q = torch.nn.functional.normalize(q, dim=1).to(torch.bfloat16)
-        doc_group, want = self._groups.resolve(filter_conditions(qdrant_filters))
+        dev = self.index.device
+        q32 = torch.tensor([query.query_embedding], dtype=torch.float32, device=dev)
+        q = normalize_rows(q32, torch.empty(1, self.index.dim, dtype=torch.bfloat16, device=dev))
+        conditions = filter_conditions(qdrant_filters)
+        doc_group, want = self._groups.resolve(conditions)
         q_group = None
         if doc_group is not None:
-            self.index.doc_group = doc_group.to(self.index.device)
+            self.index.doc_group = self._doc_group(tuple(conditions.keys()), doc_group)
             q_group = torch.tensor([want], dtype=torch.int32)
         res = batched.dense_topk(self.index, q, k, q_group=q_group, ws=self._ws)
         n = int(res.counts[0])
@@ -154,6 +220,14 @@ class B200VectorStore:
 
     async def aquery(self, query: VectorStoreQuery, qdrant_filters=None, **kwargs) -> VectorStoreQueryResult:
         return self.query(query, qdrant_filters=qdrant_filters, **kwargs)
+
+
+def _takes_prompt(embed_model) -> bool:
+    import inspect
+    try:
+        return "prompt_name" in inspect.signature(embed_model.embed_tensor).parameters
+    except (TypeError, ValueError):
+        return False
 
 
 class QdrantRetriever(BaseRetriever):
@@ -220,10 +294,10 @@ class BM25Retriever(BaseRetriever):
         self._ws = batched.Workspace(self.bm25.device)
         super().__init__(callback_manager=callback_manager, object_map=object_map, objects=objects, verbose=verbose)
 
-    def _build(self, tokens, doc_ptr, vocab) -> Bm25Index:
+    def _build(self, tokens, doc_ptr, vocab, packed: Optional[bool] = None) -> Bm25Index:
         stats = Bm25Stats.from_tokens(tokens, doc_ptr, max(vocab, 1), bm25_type=1 if self.bm25_type == 1 else 0,
                                       k1=self.k1, b=self.b, epsilon=self.epsilon)
-        return Bm25Index(stats, device=self._device, k1=self.k1, b=self.b)
+        return Bm25Index(stats, device=self._device, k1=self.k1, b=self.b, packed=packed)
 
     def _query_ids(self, query: str, vocab: Dict[str, int]):
         toks = tokenize_and_remove_stopwords(self._tokenizer, query, stopwords=self.stopwords)
@@ -238,7 +312,7 @@ class BM25Retriever(BaseRetriever):
         else:
             corpus = [tokenize_and_remove_stopwords(self._tokenizer, doc, stopwords=self.stopwords) for doc in docs]
             vocab, tokens, doc_ptr = _encode_corpus(corpus)
-            index = self._build(tokens, doc_ptr, len(vocab))
+            index = self._build(tokens, doc_ptr, len(vocab), packed=False)    # only score rows are read: skip the packed postings
         ptr, ids = self._query_ids(query, vocab)
         return batched.bm25_scores(index, ptr, ids)[0].cpu().numpy()
 
@@ -302,47 +376,41 @@ class BM25Retriever(BaseRetriever):
 
 # ------------------------------------------------------------------- fusion
 def _fuse_lists(list_of_lists, topk: int, rrf: bool, K: int = 60) -> List[NodeWithScore]:
-    """Shared host wrapper: text keys -> integer keys -> ezr_rrf_fuse / ezr_fusion_simple -> items.
+    """Shared host wrapper: text keys -> integer keys -> ``ezr_fuse_lists`` -> items.
 
-    The reference accepts any number of lists; the kernels take two (the pipeline always passes two:
-    pipeline.py:362,408; retrievers.py:290).  More lists are folded pairwise only for ``fusion``;
-    RRF with != 2 lists raises.
+    Any number of rank lists, like the reference's loops (retrievers.py:243-248, 261-265); the pipeline passes two
+    (pipeline.py:362,408; retrievers.py:290).  The kernel holds up to 8 lists / 2048 entries per call.
     """
     _lib.require_cuda()
     lists = [list(l) for l in list_of_lists]
-    if len(lists) == 1:
-        lists.append([])
-    if len(lists) != 2:
-        raise ValueError("easyrag_b200 fuses exactly two rank lists (sparse, dense)")
-    a, b = lists
-    items = a + b
+    items = [it for l in lists for it in l]
     if not items:
         return []
-    width = max(len(a), len(b), 1)
-    if width > 1024:
-        raise ValueError("rank lists longer than 1024 are not supported")
+    if len(lists) > 8:
+        raise ValueError("easyrag_b200 fuses at most 8 rank lists per call")
+    width = max(max(len(l) for l in lists), 1)
+    if width > 1024 or width * len(lists) > 2048:
+        raise ValueError("rank lists longer than 1024 entries (2048 over all lists) are not supported")
     keys: Dict[str, int] = {}
     canon = np.empty(len(items), dtype=np.int32)
     for i, it in enumerate(items):
         canon[i] = keys.setdefault(it.get_content(), i)
     dev = torch.device("cuda")
-    ids_a = torch.full((1, width), -1, dtype=torch.int32)
-    ids_b = torch.full((1, width), -1, dtype=torch.int32)
-    ids_a[0, :len(a)] = torch.arange(len(a), dtype=torch.int32)
-    ids_b[0, :len(b)] = torch.arange(len(a), len(items), dtype=torch.int32)
-    cnt_a = torch.tensor([len(a)], dtype=torch.int32, device=dev)
-    cnt_b = torch.tensor([len(b)], dtype=torch.int32, device=dev)
-    canon_t = torch.from_numpy(canon).to(dev)
+    ids, cnts, scs = [], [], []
+    base = 0
+    for l in lists:
+        row = torch.full((1, width), -1, dtype=torch.int32)
+        row[0, :len(l)] = torch.arange(base, base + len(l), dtype=torch.int32)
+        ids.append(row.to(dev))
+        cnts.append(torch.tensor([len(l)], dtype=torch.int32, device=dev))
+        if not rrf:
+            sc = torch.zeros(1, width, dtype=torch.float64)
+            sc[0, :len(l)] = torch.tensor([float(x.score) for x in l], dtype=torch.float64)
+            scs.append(sc.to(dev))
+        base += len(l)
     k_out = max(1, min(int(topk), len(items)))
-    if rrf:
-        res = batched.rrf_fuse(ids_a.to(dev), cnt_a, ids_b.to(dev), cnt_b, k_out, K=K, canon=canon_t)
-    else:
-        sc_a = torch.zeros(1, width, dtype=torch.float64)
-        sc_b = torch.zeros(1, width, dtype=torch.float64)
-        sc_a[0, :len(a)] = torch.tensor([float(x.score) for x in a], dtype=torch.float64)
-        sc_b[0, :len(b)] = torch.tensor([float(x.score) for x in b], dtype=torch.float64)
-        res = batched.fusion_simple(ids_a.to(dev), sc_a.to(dev), cnt_a, ids_b.to(dev), sc_b.to(dev), cnt_b, k_out,
-                                    canon=canon_t)
+    res = batched.fuse_lists(ids, cnts, k_out, rrf=rrf, K=K, scores=scs if not rrf else None,
+                             canon=torch.from_numpy(canon).to(dev))
     n = int(res.counts[0])
     if int(topk) < n:
         n = max(int(topk), 0)

@@ -18,9 +18,17 @@ try:  # pragma: no cover - exercised only where llama_index is installed
     from llama_index.core.base.base_retriever import BaseRetriever  # type: ignore
     from llama_index.core.base.embeddings.base import BaseEmbedding  # type: ignore
     from llama_index.core.schema import NodeWithScore, TextNode, BaseNode  # type: ignore
+    from llama_index.core.bridge.pydantic import Field, PrivateAttr  # type: ignore
     HAVE_LLAMA_INDEX = True
 except Exception:  # ModuleNotFoundError here
     HAVE_LLAMA_INDEX = False
+
+    def Field(default=None, **kwargs):
+        """Stand-in for pydantic's ``Field``: the class attribute simply holds the default."""
+        return default
+
+    def PrivateAttr(default=None, **kwargs):
+        return default
 
     class BaseNode:
         pass
@@ -110,6 +118,8 @@ except Exception:  # ModuleNotFoundError here
             self.model_name = model_name
             self.embed_batch_size = embed_batch_size
             self.callback_manager = callback_manager
+            for name, value in kwargs.items():        # the declared fields of a subclass (pydantic would validate them)
+                setattr(self, name, value)
 
         # subclass hooks
         def _get_query_embedding(self, query: str) -> List[float]:

@@ -165,6 +165,11 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
                    const int32_t* doc_group, const int32_t* q_group, int32_t id_base, float* out_scores,
                    int32_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes,
                    void* stream);
+/* Insert path of the in-HBM vector store: out[r] = bf16(x[r] / max(||x[r]||, 1e-12)) in fp32 math (what a
+ * Distance.COSINE collection does at insert, ingestion.py:180-182).  x is float32 (x_is_f32 != 0) or bf16; strides
+ * in elements; out may be a slice of a larger preallocated corpus matrix (append without rebuilding). */
+int ezr_normalize_rows(const void* x, int32_t x_is_f32, int64_t ldx, int64_t n_rows, int32_t dim, void* out_bf16,
+                       int64_t ldo, void* stream);
 /* 0 = pick automatically, 1 = force the generic SIMT kernel, 2 = force tcgen05 with the query block in shared
  * memory (SS), 3 = force tcgen05 with the query block in tensor memory (TS) and 64-row corpus tiles, 4 = TS with
  * 128-row corpus tiles (the automatic choice); 2/3/4 error if the shape is unsupported */

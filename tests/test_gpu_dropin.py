@@ -147,6 +147,79 @@ def test_dense_retriever_and_filters(world):
         assert [g.score for g in got] == sorted((g.score for g in got), reverse=True)
 
 
+def _dense_lists(store, world, k=15, filters=None):
+    out = []
+    for query in world["queries"][:8]:
+        r = QdrantRetriever(store, _FakeEmbedding(world["dim"]), similarity_top_k=k)
+        r.filters = filters
+        got = asyncio.run(r.aretrieve(QueryBundle(query)))
+        out.append([(g.node.node_id, g.score) for g in got])
+    return out
+
+
+def test_vector_store_append_equals_bulk_insert(world):
+    """``add`` appends (amortised O(new nodes)) and ``add_embedded`` takes a tensor: same collection either way."""
+    nodes = world["nodes"]
+    bulk = B200VectorStore(nodes)
+    piecewise = B200VectorStore(nodes[:400])
+    piecewise.add(nodes[400:900])
+    emb = torch.tensor([n.embedding for n in nodes[900:]], dtype=torch.float32)
+    piecewise.add_embedded(nodes[900:], emb.to("cuda"))
+    assert piecewise.index.n_rows == bulk.index.n_rows == len(nodes)
+    assert torch.equal(piecewise.index.vectors, bulk.index.vectors)
+    assert _dense_lists(piecewise, world) == _dense_lists(bulk, world)
+    f = build_qdrant_filters("rcp")
+    assert _dense_lists(piecewise, world, filters=f) == _dense_lists(bulk, world, filters=f)
+    # the per-key class table is uploaded once per key set, not per query
+    assert list(piecewise._group_cache) == [("dir",)]
+    before = piecewise._group_cache[("dir",)].data_ptr()
+    _dense_lists(piecewise, world, filters=build_qdrant_filters("umac"))
+    assert piecewise._group_cache[("dir",)].data_ptr() == before
+
+
+def test_vector_store_node_without_the_filter_key_matches_no_filter(world):
+    nodes = list(world["nodes"][:300])
+    bare = TextNode(text="no dir here", id_="node-bare", metadata={}, embedding=nodes[0].embedding)
+    store = B200VectorStore(nodes + [bare])
+    r = QdrantRetriever(store, _FakeEmbedding(world["dim"]), similarity_top_k=301)
+    got_all = asyncio.run(r.aretrieve(QueryBundle(world["queries"][0])))
+    assert "node-bare" in [g.node.node_id for g in got_all]
+    for d in DIRS:
+        r.filters = build_qdrant_filters(d)
+        got = asyncio.run(r.aretrieve(QueryBundle(world["queries"][0])))          # a qdrant payload filter: no error
+        assert "node-bare" not in [g.node.node_id for g in got]
+        assert all(g.node.metadata["dir"] == d for g in got)
+
+
+class _TensorEmbedding(_FakeEmbedding):
+    """An embedding model with the ``embed_tensor`` fast path of GTEEmbedding / HuggingFaceEmbedding."""
+
+    def __init__(self, dim, table):
+        super().__init__(dim)
+        self._table = table
+        self.embed_batch_size = 7
+        self.calls = 0
+
+    def embed_tensor(self, texts):
+        self.calls += 1
+        rows = torch.stack([self._table[t] for t in texts])
+        return rows.to(torch.bfloat16).to("cuda"), rows.to("cuda")
+
+
+def test_vector_store_from_embed_model_writes_encoder_rows_in_place(world):
+    nodes = world["nodes"][:100]
+    g = torch.Generator().manual_seed(5)
+    table = {n.get_content(): torch.randn(world["dim"], generator=g) * 3 for n in nodes}
+    model = _TensorEmbedding(world["dim"], table)
+    store = B200VectorStore.from_embed_model(nodes, model)
+    assert model.calls == -(-100 // 7) and store.index.n_rows == 100 and len(store.nodes) == 100
+    want = torch.stack([table[n.get_content()] for n in nodes]).to(torch.bfloat16).float()
+    want = (want / want.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+    got = store.index.vectors.cpu()
+    assert (got.float() - want.float()).abs().max().item() <= 2 ** -8          # one bf16 ulp of a unit-vector entry
+    assert (got.float().norm(dim=1) - 1).abs().max().item() < 5e-3
+
+
 def test_hybrid_retriever_rrf_matches_reference_flow(world):
     sparse = BM25Retriever.from_defaults(nodes=world["nodes"], tokenizer=world["tk"], similarity_top_k=24,
                                          stopwords=world["stop"])
@@ -188,3 +261,16 @@ def test_fusion_classmethods_on_the_class(world):
         assert [g.score for g in got] == [o.score for o in ref]
     assert HybridRetriever.fusion([[], []]) == []
     assert HybridRetriever.reciprocal_rank_fusion([[], []]) == []
+    # the reference accepts any number of lists (retrievers.py:243,261): one and three
+    q = world["queries"][0]
+    a, b = chunk.retrieve(q), path.retrieve(q)
+    c = list(reversed(chunk.retrieve(world["queries"][1])))[:7]
+    for lists in ([a], [a, b, c], [b, [], c, a]):
+        ref = ort.reciprocal_rank_fusion([to_o(l) for l in lists], topk=9)
+        got = HybridRetriever.reciprocal_rank_fusion([list(l) for l in lists], topk=9)
+        assert [int(g.node.node_id.split("-")[1]) for g in got] == [o.node.idx for o in ref]
+        assert [g.score for g in got] == [o.score for o in ref]
+    a, b = chunk.retrieve(q), path.retrieve(q)             # fresh scores (RRF overwrote them, as in the reference)
+    ref = ort.fusion([to_o(l) for l in (a, b, c)], topk=15)
+    got = HybridRetriever.fusion([a, b, c], topk=15)
+    assert [int(g.node.node_id.split("-")[1]) for g in got] == [o.node.idx for o in ref]

@@ -516,6 +516,38 @@ def test_simple_fusion_bit_exact(width, k_out):
         assert sc[q, :cnt[q]].tobytes() == ref_s.tobytes()
 
 
+@pytest.mark.parametrize("n_lists,width,k_out", [(1, 12, 10), (3, 10, 10), (5, 40, 64), (8, 256, 256)])
+def test_fusion_over_any_number_of_lists_bit_exact(n_lists, width, k_out):
+    """retrievers.py:243,261 loop over a list of lists: 1, 3, 5 and 8 lists against the oracle's own loops."""
+    rng = np.random.default_rng(77 + n_lists)
+    n_docs, nq = max(60, width * 2), 30
+    canon = np.arange(n_docs)
+    dup = rng.random(n_docs) < 0.1
+    canon[dup] = rng.integers(0, np.maximum(np.arange(n_docs)[dup], 1))
+    canon = canon[canon]                                            # one level of chains is enough for a key map
+    ids = [np.full((nq, width), -1, np.int32) for _ in range(n_lists)]
+    cnt = [rng.integers(0, width + 1, nq).astype(np.int32) for _ in range(n_lists)]
+    sc = [np.round(rng.random((nq, width)) * 20, 0) / 4 for _ in range(n_lists)]
+    for l in range(n_lists):
+        for q in range(nq):
+            ids[l][q, :cnt[l][q]] = rng.choice(n_docs, cnt[l][q], replace=False)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    cn = t(canon.astype(np.int32))
+    for rrf in (True, False):
+        res = batched.fuse_lists([t(a) for a in ids], [t(c) for c in cnt], k_out, rrf=rrf, K=60,
+                                 scores=[t(x) for x in sc], canon=cn)
+        g_ids, g_sc, g_cnt = res.ids.cpu().numpy(), res.scores.cpu().numpy(), res.counts.cpu().numpy()
+        for q in range(nq):
+            lists = [ids[l][q, :cnt[l][q]] for l in range(n_lists)]
+            if rrf:
+                ref_i, ref_s = ort.rrf_ids(lists, canon, K=60, topk=k_out)
+            else:
+                ref_i, ref_s = ort.fusion_ids(lists, [sc[l][q, :cnt[l][q]] for l in range(n_lists)], canon, topk=k_out)
+            assert g_cnt[q] == ref_i.size
+            assert np.array_equal(g_ids[q, :g_cnt[q]], ref_i)
+            assert g_sc[q, :g_cnt[q]].tobytes() == ref_s.tobytes()
+
+
 # ------------------------------------------------------- hybrid, one GPU ----
 def test_hybrid_dense_bm25_rrf_matches_oracle(c1):
     n, dim, k = c1["stats"].n_docs, 256, 10
