@@ -79,6 +79,8 @@ def parse():
     ap.add_argument("--dense-probe", type=int, default=0, help="measurement probe of the dense kernel (results invalid)")
     ap.add_argument("--dense-stages", type=int, default=-1,
                     help="cap of the dense kernel's TMA ring (0 = all smem; -1 = 3 with --overlap 1, else 0)")
+    ap.add_argument("--enc-chunks", type=int, default=100_000,
+                    help="chunks of the `encode` block (configs[1]: GTE-base-shaped encoder); 0 = skip the block")
     ap.add_argument("--l2-flush", type=int, default=-1,
                     help="1: write a 512 MB buffer between steps and time each step on its own (default for <= 512 queries)")
     return ap.parse_args()
@@ -516,6 +518,23 @@ def run_ours(args):
         self_check = {"bm25_two_phase_equals_ordered": same, "queries": nq, "postings_local": sparse.n_postings}
         if not same:
             raise SystemExit(f"bench.py self-check FAILED on rank {rank}: BM25 kernel paths disagree")
+    # ---- configs[1]: the chunk-embedding forward pass (every rank encodes its share of the chunks)
+    encode = None
+    if rank == 0 and world == 1 and not args.no_cpu and ref is None:
+        ref = CpuReference(data, args)                  # host copies for the cpu_baseline leg, before HBM is freed
+    if args.enc_chunks > 0 and args.dense_probe == 0 and not small_batch:
+        import bench_encode
+        index_bytes = sparse.index_bytes()
+        postings_local, n_rows_local = sparse.n_postings, dense.n_rows
+        alg = algorithmic_bytes(args, data, sparse, dense.n_rows)
+        del ranker, ranker_seq, sharded, sharded_seq, pipe, sparse, dense, last, flush_buf
+        data["vec"] = data["qvec"] = None
+        torch.cuda.empty_cache()
+        encode = bench_encode.encode_block(dev, "bert", args.enc_chunks, 1000, 512, 12, 768, 3, rank, world)
+    else:
+        index_bytes = sparse.index_bytes()
+        postings_local, n_rows_local = sparse.n_postings, dense.n_rows
+        alg = algorithmic_bytes(args, data, sparse, dense.n_rows)
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -528,14 +547,13 @@ def run_ours(args):
         peaks = json.loads(pk_file.read_text())
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    alg = algorithmic_bytes(args, data, sparse, dense.n_rows)
     long_step = ms > 2000.0          # a seconds-long loop settles at the sustained clock
     tf_key = "bf16_tflops_sustained" if long_step else "bf16_tflops"
     tf_peak = float(peaks.get(tf_key, 1590.0 if not long_step else 1400.0))
     tf_src = (f"measured (MEASURED_PEAKS.json {tf_key}: "
               + ("kernel timed inside a seconds-long loop)" if long_step else "burst figure, the timed loop lasts well under 2 s)")
               if tf_key in peaks else "fallback")
-    dense_flops = 2.0 * dense.n_rows * args.dim * args.queries          # per launch: every query x every local row
+    dense_flops = 2.0 * n_rows_local * args.dim * args.queries          # per launch: every query x every local row
     kernels = {}
     two_phase = prof["bm25_cand"][1] > 0
     for name in ("bm25_cand", "bm25_score", "dense_tc"):
@@ -585,8 +603,6 @@ def run_ours(args):
     d2h = h_ids.numel() * 4 + h_sc.numel() * 8
     cpu = None
     if world == 1 and not args.no_cpu:
-        if ref is None:
-            ref = CpuReference(data, args)
         v, dt = ref.measure(args.cpu_queries, steps=1, warmup=0 if parity is not None else 1)
         cpu = {"value": v, "unit": "queries/s", "cores": ref.cores, "kind": "port",
                "sample": f"first {min(args.cpu_queries, args.queries)} of the {args.queries} queries over the full "
@@ -622,7 +638,7 @@ def run_ours(args):
                                f"{args.queries} queries/step"
                                + (f", row-sharded over {world} GPUs (configs[3])" if world > 1 else ""),
                    "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "queries_per_step": args.queries,
-                   "k": k, "rrf_K": 60, "tokens": data["n_tokens"], "postings_local": sparse.n_postings,
+                   "k": k, "rrf_K": 60, "tokens": data["n_tokens"], "postings_local": postings_local,
                    "queries_per_corpus_pass": min(args.queries, 128), "routes_overlapped": overlap,
                    "dense_ring_stages_cap": stage_cap, "timed_region_starts_from": "query vectors + term ids",
                    "l2": ("explicit flush: 512 MB written between steps, every step timed on its own" if l2_flush else
@@ -634,9 +650,9 @@ def run_ours(args):
                        "RRF -> D2H into pinned host outputs, every step; copies of step i+1 overlap the kernels of step i"},
         "gpu_launches": int(launches_timed),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "parity_full_size": parity, "digest": dig, "scaling_terms": scaling_terms,
+        "parity_full_size": parity, "digest": dig, "scaling_terms": scaling_terms, "encode": encode,
         "setup": {"generate_s": round(data["gen_s"], 1), "index_build_s": round(build_s, 1),
-                  "index_bytes": sparse.index_bytes(), "dense_kernel": dense_kernel_name,
+                  "index_bytes": index_bytes, "dense_kernel": dense_kernel_name,
                   "self_check": self_check},
     }
     if per_step is not None:

@@ -49,6 +49,13 @@ SIGNATURES = {
     "ezr_bm25_doc_norm": (C.c_int, [_p, _i64, _dbl, _dbl, _dbl, _dbl, _p, _p]),
     "ezr_bm25_weights": (C.c_int, [_p, _p, _p, _i32, _i64, _p, _p, _dbl, _i32, _p, _p]),
     "ezr_bm25_range_index": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
+    "ezr_bm25_build_block": (C.c_int, []),
+    "ezr_bm25_build_workspace": (_sz, [_i64, _i64, _i32]),
+    "ezr_bm25_build_count": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _sz,
+                                       C.POINTER(C.c_int32), _p]),
+    "ezr_bm25_build_fill": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "ezr_bm25_shard_count": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "ezr_bm25_shard_copy": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
     "ezr_bm25_pack": (C.c_int, [_p, _p, _i64, _i32, _p, C.POINTER(C.c_int32), _p, _p]),
     "ezr_bm25_term_max": (C.c_int, [_p, _p, _i32, _p, _p]),
     "ezr_bm25_set_skipping": (C.c_int, [_i32]),

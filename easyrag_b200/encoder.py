@@ -75,6 +75,14 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+def _dest(out_bf16: Optional[torch.Tensor], n: int, d: int, device) -> torch.Tensor:
+    if out_bf16 is None:
+        return torch.empty(n, d, dtype=torch.bfloat16, device=device)
+    if out_bf16.shape != (n, d) or out_bf16.dtype != torch.bfloat16 or not out_bf16.is_contiguous():
+        raise ValueError("out_bf16 must be a contiguous bf16 [n_seq, dim] tensor (a row slice of the corpus matrix)")
+    return out_bf16
+
+
 # ------------------------------------------------------------------------------------- packing
 @dataclass
 class PackedBatch:
@@ -225,12 +233,15 @@ class Qwen2Encoder:
         return x
 
     @torch.no_grad()
-    def embed_packed(self, batch: PackedBatch) -> Tuple[torch.Tensor, torch.Tensor]:
-        """-> (bf16 [B, d] unit rows for the dense index, float32 copy the embedding API returns)."""
+    def embed_packed(self, batch: PackedBatch, out_bf16: Optional[torch.Tensor] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (bf16 [B, d] unit rows for the dense index, float32 copy the embedding API returns).
+        ``out_bf16``: a contiguous [B, d] bf16 destination, e.g. ``DenseIndex.rows_for_append(B)`` -- the pooling
+        kernel then writes the corpus rows in place."""
         L = _lib.lib()
         x = self.hidden(batch)
         d = self.cfg.hidden_size
-        out_b = torch.empty(batch.n_seq, d, dtype=torch.bfloat16, device=self.device)
+        out_b = _dest(out_bf16, batch.n_seq, d, self.device)
         out_f = torch.empty(batch.n_seq, d, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(L.ezr_pool_normalize(_lib.ptr(x), x.stride(0), _lib.ptr(batch.cu), batch.n_seq, POOL_LAST, 1,
@@ -329,11 +340,12 @@ class BertEncoder:
         return x
 
     @torch.no_grad()
-    def embed_packed(self, batch: PackedBatch, normalize: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    def embed_packed(self, batch: PackedBatch, normalize: bool = True, out_bf16: Optional[torch.Tensor] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
         L = _lib.lib()
         x = self.hidden(batch)
         d = self.cfg.hidden_size
-        out_b = torch.empty(batch.n_seq, d, dtype=torch.bfloat16, device=self.device)
+        out_b = _dest(out_bf16, batch.n_seq, d, self.device)
         out_f = torch.empty(batch.n_seq, d, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(L.ezr_pool_normalize(_lib.ptr(x), x.stride(0), _lib.ptr(batch.cu), batch.n_seq, self.pool, 0,

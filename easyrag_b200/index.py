@@ -4,7 +4,8 @@
   ``bm25s.BM25.index`` derive them (reference call sites retrievers.py:98-118): document
   frequencies, ``avgdl``, ``idf`` with the epsilon floor.  The transcendental part (``math.log``)
   and the order-sensitive float64 sum stay on the host so they are bit-identical to CPython
-  (SURVEY.md section 7 "hard parts"); counting/sorting uses torch ops on whatever device holds the tokens.
+  (SURVEY.md section 7 "hard parts"); counting tf/df, sorting and placing the postings run in this
+  library's own kernels (csrc/bm25_build.cu: per-document shared-memory sort, block-ordered placement).
 * :class:`Bm25Index` -- device-resident term-major postings with the per-posting contribution
   precomputed by ``ezr_bm25_weights`` (CUDA, round-to-nearest, no FMA), plus the range table the
   query kernel uses.  Needs a GPU; there is no CPU path.
@@ -43,28 +44,69 @@ class Bm25Stats:
 
     @staticmethod
     def from_tokens(tokens: torch.Tensor, doc_ptr: torch.Tensor, vocab: int, bm25_type: int = 0,
-                    k1: float = K1, b: float = B, epsilon: float = EPSILON) -> "Bm25Stats":
-        """``tokens`` int32/int64 [T] term ids, ``doc_ptr`` int64 [N+1]."""
-        dev = tokens.device
+                    k1: float = K1, b: float = B, epsilon: float = EPSILON, device=None) -> "Bm25Stats":
+        """``tokens`` int32/int64 [T] term ids, ``doc_ptr`` int64 [N+1].  Counting, sorting and placing run in this
+        library's own kernels (csrc/bm25_build.cu); there is no CPU implementation."""
         n = doc_ptr.numel() - 1
         if n == 0:
             raise ZeroDivisionError("division by zero")      # rank_bm25: avgdl = num_doc / corpus_size
-        lens = (doc_ptr[1:] - doc_ptr[:-1]).to(torch.int64)
-        total = int(lens.sum())
-        avgdl = total / n
-        tok = tokens.to(torch.int64)
-        if total:
-            if int(tok.min()) < 0 or int(tok.max()) >= vocab:
-                raise ValueError("token id out of range [0, vocab)")
-        doc_of = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), lens)
-        key = tok * n + doc_of
-        ukey, counts = torch.unique(key, return_counts=True)       # sorted: term-major, doc ascending
-        post_term = torch.div(ukey, n, rounding_mode="floor")
-        post_doc = (ukey - post_term * n).to(torch.int32)
-        post_tf = counts.to(torch.int32)
-        df = torch.bincount(post_term, minlength=vocab)
-        indptr = torch.zeros(vocab + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(df, 0, out=indptr[1:])
+        _lib.require_cuda()
+        L = _lib.lib()
+        if device is None:
+            device = tokens.device if tokens.is_cuda else torch.device("cuda")
+        device = torch.device(device)
+        import ctypes
+        with torch.cuda.device(device):
+            tok = tokens.to(device=device, dtype=torch.int32).contiguous()
+            ptr = doc_ptr.to(device=device, dtype=torch.int64).contiguous()
+            lens = ptr[1:] - ptr[:-1]
+            total = int(ptr[-1])
+            max_len = int(lens.max())
+            cap = 8192                                       # kBuildCap: longer documents sort in a global scratch
+            long_docs = long_off = long_keys = None
+            n_long = 0
+            if max_len > cap:
+                idx = torch.nonzero(lens > cap).flatten()
+                n_long = int(idx.numel())
+                ll = lens[idx].cpu().tolist()
+                sizes = [1 << (int(x) - 1).bit_length() for x in ll]
+                offs = [0]
+                for z in sizes[:-1]:
+                    offs.append(offs[-1] + z)
+                long_docs = idx.to(torch.int32).contiguous()
+                long_off = torch.tensor(offs, dtype=torch.int64, device=device)
+                long_keys = torch.empty(sum(sizes), dtype=torch.int64, device=device)
+            ws = torch.empty(L.ezr_bm25_build_workspace(n, total, vocab), dtype=torch.uint8, device=device)
+            df = torch.empty(vocab, dtype=torch.int64, device=device)
+            indptr = torch.empty(vocab + 1, dtype=torch.int64, device=device)
+            first_pos = torch.empty(vocab, dtype=torch.int64, device=device)
+            status = ctypes.c_int32(0)
+            st = _lib.stream_ptr()
+            _lib.check(L.ezr_bm25_build_count(_lib.ptr(tok), _lib.ptr(ptr), n, total, vocab, max_len, _lib.ptr(df),
+                                              _lib.ptr(indptr), _lib.ptr(first_pos), _lib.ptr(long_docs),
+                                              _lib.ptr(long_off), _lib.ptr(long_keys), n_long, _lib.ptr(ws), ws.numel(),
+                                              ctypes.byref(status), st), "ezr_bm25_build_count")
+            if status.value != 0:
+                raise ValueError(f"token id out of range [0, vocab) in document {status.value - 1}")
+            n_post = int(indptr[-1])
+            post_doc = torch.empty(n_post, dtype=torch.int32, device=device)
+            post_tf = torch.empty(n_post, dtype=torch.int32, device=device)
+            _lib.check(L.ezr_bm25_build_fill(_lib.ptr(ptr), n, total, vocab, _lib.ptr(indptr), _lib.ptr(post_doc),
+                                             _lib.ptr(post_tf), _lib.ptr(ws), ws.numel(), st), "ezr_bm25_build_fill")
+            torch.cuda.current_stream().synchronize()
+            del ws
+        return Bm25Stats.from_counts(n, vocab, total, lens.to(torch.int32), df, indptr, post_doc, post_tf,
+                                     first_pos.cpu().numpy(), bm25_type=bm25_type, epsilon=epsilon)
+
+    @staticmethod
+    def from_counts(n_docs: int, vocab: int, total_tokens: int, doc_len: torch.Tensor, df: torch.Tensor,
+                    indptr: torch.Tensor, post_doc: torch.Tensor, post_tf: torch.Tensor, first_pos: np.ndarray,
+                    bm25_type: int = 0, epsilon: float = EPSILON) -> "Bm25Stats":
+        """The host-exact part of the index build: ``avgdl`` and ``idf`` exactly as rank_bm25 / bm25s derive them
+        from the counted arrays (``math.log`` per term, a sequential float64 sum in first-seen term order).
+        ``first_pos[t]``: corpus position of term t's first occurrence (only its ORDER matters)."""
+        n = n_docs
+        avgdl = total_tokens / n
         df_host = df.cpu().numpy()
         present = np.nonzero(df_host)[0]
         idf = np.zeros(vocab, dtype=np.float64)
@@ -76,9 +118,7 @@ class Bm25Stats:
                             dtype=np.float64)
             idf[present] = vals
             if present.size:
-                first_pos = torch.full((vocab,), total, dtype=torch.int64, device=dev)
-                first_pos.scatter_reduce_(0, tok, torch.arange(total, device=dev, dtype=torch.int64), reduce="amin")
-                order = torch.argsort(first_pos[torch.as_tensor(present, device=dev)], stable=True).cpu().numpy()
+                order = np.argsort(np.asarray(first_pos)[present].astype(np.uint64), kind="stable")
                 seq = np.cumsum(vals[order])          # np.cumsum is a plain left-to-right float64 sum
                 average_idf = float(seq[-1]) / present.size
                 neg = present[vals < 0]
@@ -89,7 +129,7 @@ class Bm25Stats:
             idf[present] = vals.astype(np.float64)
         else:
             raise ValueError("bm25_type must be 0 (BM25Okapi) or 1 (bm25s)")
-        return Bm25Stats(n_docs=n, vocab=vocab, bm25_type=bm25_type, avgdl=avgdl, doc_len=lens.to(torch.int32),
+        return Bm25Stats(n_docs=n, vocab=vocab, bm25_type=bm25_type, avgdl=avgdl, doc_len=doc_len.to(torch.int32),
                          df=df, idf=idf, indptr=indptr, post_doc=post_doc, post_tf=post_tf,
                          average_idf=average_idf)
 
@@ -115,8 +155,10 @@ def _load_arrays(path: str):
         raise ValueError(f"{path}: index format {meta.get('format_version')} != {INDEX_FORMAT_VERSION}")
 
     def get(name):
-        a = np.load(os.path.join(path, name + ".npy"), mmap_mode="r")     # start-up is an mmap, not a re-tokenise
-        t = torch.from_numpy(np.ascontiguousarray(a))
+        # start-up is an mmap, not a re-tokenise: a private copy-on-write mapping of the .npy payload; the pages go
+        # from the page cache straight into the H2D copy (no intermediate host array)
+        a = np.load(os.path.join(path, name + ".npy"), mmap_mode="c")
+        t = torch.from_numpy(a)
         return t.view(torch.bfloat16) if name in meta.get("bf16", []) else t
     return meta, get
 
@@ -144,18 +186,24 @@ class Bm25Index:
         self.score_dtype = torch.float64 if stats.bm25_type == 0 else torch.float32
         self.device = device
         with torch.cuda.device(device):
-            post_doc = stats.post_doc.to(device)
-            post_tf = stats.post_tf.to(device)
-            indptr = stats.indptr.to(device)
+            post_doc = stats.post_doc.to(device).contiguous()
+            post_tf = stats.post_tf.to(device).contiguous()
+            indptr = stats.indptr.to(device).contiguous()
             if doc_lo != 0 or doc_hi != stats.n_docs:
-                keep = (post_doc >= doc_lo) & (post_doc < doc_hi)
-                term_of = torch.repeat_interleave(torch.arange(stats.vocab, device=device),
-                                                  (indptr[1:] - indptr[:-1]))
-                df_local = torch.bincount(term_of[keep], minlength=stats.vocab)
-                indptr = torch.zeros(stats.vocab + 1, dtype=torch.int64, device=device)
-                torch.cumsum(df_local, 0, out=indptr[1:])
-                post_doc = (post_doc[keep] - doc_lo).to(torch.int32)
-                post_tf = post_tf[keep]
+                # a row shard's postings are a contiguous sub-segment of every term's (document-sorted) list
+                first = torch.empty(stats.vocab, dtype=torch.int64, device=device)
+                df_local = torch.empty(stats.vocab, dtype=torch.int64, device=device)
+                ind_local = torch.empty(stats.vocab + 1, dtype=torch.int64, device=device)
+                _lib.check(L.ezr_bm25_shard_count(_lib.ptr(indptr), _lib.ptr(post_doc), stats.vocab, doc_lo, doc_hi,
+                                                  _lib.ptr(first), _lib.ptr(df_local), _lib.ptr(ind_local),
+                                                  _lib.stream_ptr()), "ezr_bm25_shard_count")
+                n_local = int(ind_local[-1])
+                doc_l = torch.empty(n_local, dtype=torch.int32, device=device)
+                tf_l = torch.empty(n_local, dtype=torch.int32, device=device)
+                _lib.check(L.ezr_bm25_shard_copy(_lib.ptr(first), _lib.ptr(ind_local), _lib.ptr(post_doc),
+                                                 _lib.ptr(post_tf), stats.vocab, doc_lo, _lib.ptr(doc_l), _lib.ptr(tf_l),
+                                                 _lib.stream_ptr()), "ezr_bm25_shard_copy")
+                indptr, post_doc, post_tf = ind_local, doc_l, tf_l
             self.indptr = indptr.contiguous()
             self.post_doc = post_doc.contiguous()
             self.n_postings = int(self.post_doc.numel())

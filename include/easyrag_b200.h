@@ -94,6 +94,32 @@ int ezr_bm25_weights(const int64_t* indptr, const int32_t* post_doc, const int32
 int ezr_bm25_range_index(const int64_t* indptr, const int32_t* post_doc, int32_t vocab, int32_t range_size,
                          int32_t n_ranges, uint32_t* out_range_off, void* stream);
 
+/* ---- index construction (replaces the dict building of BM25Retriever.__init__, retrievers.py:98-118) ----
+ * Corpus = int32 term ids tokens[n_tokens] + int64 doc_ptr[n_docs+1] (device).  Two phases because the number of
+ * postings is only known after counting:
+ *   count: df[vocab], indptr[vocab+1] (int64), first_pos[vocab] (uint64 corpus position of each term's first
+ *          occurrence, ~0 = absent: rank_bm25 sums idf in first-seen term order) + the workspace for phase two.
+ *          Documents longer than 8192 tokens sort in the global scratch long_keys (long_docs[n_long] document indices,
+ *          long_off[n_long] key offsets, sum(next_pow2(len)) uint64 keys); NULL / 0 when there are none.
+ *          *status_host = 0, or 1 + the index of a document holding a token id outside [0, vocab).  Synchronises.
+ *   fill : post_doc / post_tf [indptr[vocab]], term-major, ascending document id inside a term (no sort: documents
+ *          are placed block by block in order).
+ * ezr_bm25_shard_*: postings of documents [doc_lo, doc_hi) of a built index (ids rebased to doc_lo). */
+int ezr_bm25_build_block(void);
+size_t ezr_bm25_build_workspace(int64_t n_docs, int64_t n_tokens, int32_t vocab);
+int ezr_bm25_build_count(const int32_t* tokens, const int64_t* doc_ptr, int64_t n_docs, int64_t n_tokens, int32_t vocab,
+                         int32_t max_doc_len, int64_t* out_df, int64_t* out_indptr, uint64_t* out_first_pos,
+                         const int32_t* long_docs, const int64_t* long_off, uint64_t* long_keys, int32_t n_long,
+                         void* workspace, size_t workspace_bytes, int32_t* status_host, void* stream);
+int ezr_bm25_build_fill(const int64_t* doc_ptr, int64_t n_docs, int64_t n_tokens, int32_t vocab, const int64_t* indptr,
+                        int32_t* out_post_doc, int32_t* out_post_tf, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int ezr_bm25_shard_count(const int64_t* indptr, const int32_t* post_doc, int32_t vocab, int32_t doc_lo, int32_t doc_hi,
+                         int64_t* out_first, int64_t* out_df_local, int64_t* out_indptr_local, void* stream);
+int ezr_bm25_shard_copy(const int64_t* first, const int64_t* indptr_local, const int32_t* post_doc,
+                        const int32_t* post_tf, int32_t vocab, int32_t doc_lo, int32_t* out_post_doc,
+                        int32_t* out_post_tf, void* stream);
+
 /* Packed postings for the candidate pass of ezr_bm25_topk: out_pk[p] = (post_doc[p] mod range_size) << W |
  * ceil(post_w[p] * 2^e), W = 32 - log2(range_size), e chosen from the largest weight so that every field fits
  * (returned in *out_scale_log2).  Rounding up makes the integer sums upper bounds of the float64 scores; the

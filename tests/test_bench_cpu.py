@@ -6,6 +6,8 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
+from _host_counts import stats_from_host_counts
+
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
@@ -22,7 +24,7 @@ def test_cpu_reference_arm_matches_oracle():
     queries = synth.make_queries(corpus, nq, 4)
     vec = synth.make_dense_corpus(n, dim, 5)
     qvec = synth.make_dense_queries(vec, nq, 6)
-    data = dict(stats=Bm25Stats.from_tokens(corpus.tokens, corpus.doc_ptr, vocab), queries=queries, vec=vec, qvec=qvec)
+    data = dict(stats=stats_from_host_counts(corpus.tokens, corpus.doc_ptr, vocab), queries=queries, vec=vec, qvec=qvec)
     ref = bench.CpuReference(data, SimpleNamespace(k=k))
     got = ref.run(0, nq)
     model = obm.OkapiCSR(corpus.doc_lists(), vocab)
@@ -69,7 +71,7 @@ def test_parity_full_size_accepts_the_oracle_and_rejects_a_wrong_list():
     queries = synth.make_queries(corpus, nq, 14)
     vec = synth.make_dense_corpus(n, dim, 15)
     qvec = synth.make_dense_queries(vec, nq, 16)
-    data = dict(stats=Bm25Stats.from_tokens(corpus.tokens, corpus.doc_ptr, vocab), queries=queries, vec=vec, qvec=qvec)
+    data = dict(stats=stats_from_host_counts(corpus.tokens, corpus.doc_ptr, vocab), queries=queries, vec=vec, qvec=qvec)
     ref = bench.CpuReference(data, SimpleNamespace(k=k))
     f, s, d = _fake_gpu_lists(ref, nq, k)
     res = bench.parity_full_size(ref, nq, f, s, d, k)

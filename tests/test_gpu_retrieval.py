@@ -548,6 +548,62 @@ def test_fusion_over_any_number_of_lists_bit_exact(n_lists, width, k_out):
             assert g_sc[q, :g_cnt[q]].tobytes() == ref_s.tobytes()
 
 
+# ------------------------------------------------------- index build on the GPU ----
+def _assert_counts_equal(st, tokens, ptr, vocab):
+    from _host_counts import host_counts
+    c = host_counts(tokens, ptr, vocab)
+    assert np.array_equal(st.df.cpu().numpy(), c["df"])
+    assert np.array_equal(st.indptr.cpu().numpy(), c["indptr"])
+    assert np.array_equal(st.post_doc.cpu().numpy(), c["post_doc"])          # term-major, documents ascending
+    assert np.array_equal(st.post_tf.cpu().numpy(), c["post_tf"])
+    assert np.array_equal(st.doc_len.cpu().numpy(), c["doc_len"])
+
+
+@pytest.mark.parametrize("n,vocab,mean_len,max_len", [(3000, 700, 40, 200), (20000, 5000, 300, 800), (9000, 64, 12, 40),
+                                                       (1, 10, 5, 9)])
+def test_index_build_kernels_match_the_host_counting(n, vocab, mean_len, max_len):
+    """csrc/bm25_build.cu (per-document sort, block-ordered placement) against the numpy restatement of
+    retrievers.py:98-118: df, indptr, postings in (term, document) order, tf, document lengths -- and the idf values
+    that depend on the first-seen term order (sequential float64 sum)."""
+    from _host_counts import stats_from_host_counts
+    corpus = synth.make_sparse_corpus(n, vocab, 900 + n, mean_len=mean_len, min_len=0, max_len=max_len)
+    st = Bm25Stats.from_tokens(corpus.tokens, corpus.doc_ptr, vocab)
+    assert st.post_doc.is_cuda
+    _assert_counts_equal(st, corpus.tokens, corpus.doc_ptr, vocab)
+    ref = stats_from_host_counts(corpus.tokens, corpus.doc_ptr, vocab)
+    assert st.avgdl == ref.avgdl and st.average_idf == ref.average_idf and st.idf.tobytes() == ref.idf.tobytes()
+
+
+def test_index_build_long_documents_empty_documents_and_bad_tokens():
+    g = torch.Generator().manual_seed(3)
+    lens = [0, 5, 9000, 0, 8192, 8193, 20000, 1, 300, 0]           # around the shared-memory sort capacity (8192)
+    vocab = 1500
+    tokens = torch.randint(0, vocab, (sum(lens),), generator=g, dtype=torch.int32)
+    ptr = torch.tensor(np.cumsum([0] + lens), dtype=torch.int64)
+    st = Bm25Stats.from_tokens(tokens, ptr, vocab)
+    _assert_counts_equal(st, tokens, ptr, vocab)
+    bad = tokens.clone()
+    bad[9100] = vocab                                                # inside document 2
+    with pytest.raises(ValueError, match="document 2"):
+        Bm25Stats.from_tokens(bad, ptr, vocab)
+
+
+def test_index_shard_slice_kernels_equal_a_filter_of_the_global_postings(c1):
+    st = c1["stats"]
+    n = st.n_docs
+    for lo, hi in ((0, n), (0, n // 3), (n // 3, 2 * n // 3 + 5), (n - 7, n), (5, 5)):
+        ix = Bm25Index(st, device=DEV, doc_lo=lo, doc_hi=hi, packed=False) if hi > lo else None
+        pd, tf, ind = st.post_doc.cpu().numpy(), st.post_tf.cpu().numpy(), st.indptr.cpu().numpy()
+        term_of = np.repeat(np.arange(st.vocab), np.diff(ind))
+        keep = (pd >= lo) & (pd < hi)
+        if ix is None:
+            continue
+        assert np.array_equal(ix.post_doc.cpu().numpy(), pd[keep] - lo)
+        want_ptr = np.zeros(st.vocab + 1, np.int64)
+        np.cumsum(np.bincount(term_of[keep], minlength=st.vocab), out=want_ptr[1:])
+        assert np.array_equal(ix.indptr.cpu().numpy(), want_ptr)
+
+
 # ------------------------------------------------------- hybrid, one GPU ----
 def test_hybrid_dense_bm25_rrf_matches_oracle(c1):
     n, dim, k = c1["stats"].n_docs, 256, 10

@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import torch
 
+from _host_counts import stats_from_host_counts
+
 from oracle import bm25 as obm
 from easyrag_b200 import synth, _lib
 from easyrag_b200.index import Bm25Stats
@@ -48,12 +50,16 @@ def test_product_fails_loudly_without_cuda(lib_built):
     a = [NodeWithScore(TextNode("x"), 1.0)]
     with pytest.raises(_lib.EzrError):
         HybridRetriever.reciprocal_rank_fusion([a, a])
+    # the index build counts on the GPU only: no CPU implementation to fall back to
+    c = synth.make_sparse_corpus(20, 30, 1, mean_len=5, min_len=1, max_len=9)
+    with pytest.raises(_lib.EzrError):
+        Bm25Stats.from_tokens(c.tokens, c.doc_ptr, c.vocab)
 
 
 @pytest.mark.parametrize("bm25_type", [0, 1])
 def test_bm25_stats_match_oracle(bm25_type):
     c = synth.make_sparse_corpus(500, 400, 11, mean_len=30, min_len=0, max_len=90)
-    st = Bm25Stats.from_tokens(c.tokens, c.doc_ptr, c.vocab, bm25_type=bm25_type)
+    st = stats_from_host_counts(c.tokens, c.doc_ptr, c.vocab, bm25_type=bm25_type)
     docs = c.doc_lists()
     if bm25_type == 0:
         o = obm.OkapiCSR(docs, c.vocab)
@@ -71,7 +77,7 @@ def test_bm25_stats_match_oracle(bm25_type):
 
 def test_bm25_stats_empty_corpus_raises_like_reference():
     with pytest.raises(ZeroDivisionError):
-        Bm25Stats.from_tokens(torch.zeros(0, dtype=torch.int32), torch.zeros(1, dtype=torch.int64), 4)
+        stats_from_host_counts(torch.zeros(0, dtype=torch.int32), torch.zeros(1, dtype=torch.int64), 4)
 
 
 def test_shard_bounds_cover_exactly():
