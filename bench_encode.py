@@ -62,7 +62,8 @@ def make_batches(lens: torch.Tensor, batch: int, vocab: int, dev, seed: int):
 
 
 def encode_block(dev, arch: str = "bert", chunks: int = 100_000, queries: int = 1_000, batch: int = 512, layers: int = 12,
-                 dim: int = 768, steps: int = 3, rank: int = 0, world: int = 1, parity_seqs: int = 6) -> dict:
+                 dim: int = 768, steps: int = 3, rank: int = 0, world: int = 1, parity_seqs: int = 6,
+                 len_min: int = 64, len_max: int = 512) -> dict:
     """The measured block; every rank calls it, every rank returns the same dict (times are the max over ranks)."""
     import torch.distributed as dist
     from easyrag_b200 import _lib, batched
@@ -72,7 +73,7 @@ def encode_block(dev, arch: str = "bert", chunks: int = 100_000, queries: int = 
     L = _lib.lib()
     cfg, state, model = build_model(arch, layers, dim, dev)
     g = torch.Generator().manual_seed(SEED)
-    lens_all = torch.randint(64, 513, (chunks,), generator=g)
+    lens_all = torch.randint(len_min, len_max + 1, (chunks,), generator=g)
     qlens = torch.randint(8, 49, (queries,), generator=g)
     lo, hi = shard_bounds(chunks, world, rank)
     lens = lens_all[lo:hi]
@@ -146,7 +147,7 @@ def encode_block(dev, arch: str = "bert", chunks: int = 100_000, queries: int = 
     tokens_all = int(lens_all.sum())
     return {
         "arch": arch, "layers": layers, "dim": dim, "chunks": chunks, "tokens": tokens_all, "batch_sequences": batch,
-        "chunk_len": "U[64,512]", "query_len": "U[8,48]", "n_gpus": world,
+        "chunk_len": f"U[{len_min},{len_max}]", "query_len": "U[8,48]", "n_gpus": world,
         "encode_s": ms_corpus * 1e-3, "chunks_per_s": chunks / (ms_corpus * 1e-3),
         "tokens_per_s": tokens_all / (ms_corpus * 1e-3),
         "model_tflops_per_gpu": flops_local / (ms_corpus * 1e-3) / 1e12,
@@ -196,6 +197,8 @@ def main(from_bench=None):
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--enc-dim", type=int, default=768)
     ap.add_argument("--enc-steps", type=int, default=3)
+    ap.add_argument("--len-min", type=int, default=64)
+    ap.add_argument("--len-max", type=int, default=512)
     args = ap.parse_known_args()[0]
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,7 +210,7 @@ def main(from_bench=None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     blk = encode_block(dev, args.arch, args.chunks, args.enc_queries, args.batch, args.layers, args.enc_dim,
-                       args.enc_steps, rank, world)
+                       args.enc_steps, rank, world, len_min=args.len_min, len_max=args.len_max)
     if rank == 0:
         if from_bench is not None:
             line = {"metric": "chunks/sec GTE-base-shaped 768-d encode (configs[1])", "value": blk["chunks_per_s"],

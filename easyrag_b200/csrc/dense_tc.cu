@@ -55,6 +55,8 @@ struct TcParams {
     const int32_t* q_group;
     float* part_s;        // [n_queries][n_slices][k]
     int32_t* part_id;
+    int32_t* bound;       // TS variant: [n_queries] float bits (0 = none) of a proven lower bound of each query's final
+                          // k-th best score, raised by every finished unit; later units of the query start from it
     int n_slices;
     int n_qblocks;        // TS variant: units = n_slices x n_qblocks, walked by persistent CTAs
     int kps;              // TS variant: k-chunks (TMA boxes) per pipeline stage: 1, 2 or 4
@@ -444,7 +446,15 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             int ti[KT];
 #pragma unroll
             for (int j = 0; j < KT; ++j) { ts[j] = -INFINITY; ti[j] = -1; }
-            float thr = -INFINITY;
+            // Seed: k documents with a score >= seed are already known for this query (published by units that
+            // finished earlier, possibly on other SMs), so nothing below it can reach the final top-k; equal scores
+            // stay in (ties are decided by id in the merge).  Without a seed the list warms up from -inf in every unit.
+            float seed = -INFINITY;
+            if (active) {
+                const int b = *reinterpret_cast<const volatile int32_t*>(p.bound + qg);
+                if (b > 0) seed = __int_as_float(b);
+            }
+            float thr = seed;
 
             for (int t = 0; t < n_tiles; ++t, ++it) {
                 const int as = it % TS_ACC;
@@ -508,12 +518,14 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                 cv = b ? fs : cv;
                                 ci = b ? is : ci;
                             }
-                            thr = ts[KT - 1];
+                            thr = fmaxf(ts[KT - 1], seed);
                         }
                     }
                 }
                 }   // sub
             }
+            if (active && ti[k - 1] >= 0 && ts[k - 1] > 0.f)
+                atomicMax(p.bound + qg, __float_as_int(ts[k - 1]));      // positive floats order like their bit patterns
             if (active) {
                 const int64_t o = (((int64_t)qg * p.n_slices + slice) * 2 + half) * k;
 #pragma unroll
@@ -615,7 +627,7 @@ size_t dense_tc_workspace(int64_t n_rows, int dim, int n_queries, int k) {
     if (dim % TC_KC != 0 || dim > TS_MAXD || k > TC_KMAX || n_rows < 1) return 0;
     const int slices = tc_slices(n_rows);
     const size_t n = (size_t)n_queries * slices * k * 2;      // TS variant: two lists per (query, split)
-    return align_up(n * 4, 256) * 2;
+    return align_up(n * 4, 256) * 2 + align_up((size_t)n_queries * 4, 256);      // + the per-query score bounds
 }
 
 int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t ldc, const __nv_bfloat16* queries,
@@ -672,6 +684,8 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     const size_t n_part = (size_t)n_queries * p.n_slices * k * lists;
     p.part_s = reinterpret_cast<float*>(ws);
     p.part_id = reinterpret_cast<int32_t*>((char*)ws + align_up(n_part * 4, 256));
+    p.bound = reinterpret_cast<int32_t*>((char*)ws + need - align_up((size_t)n_queries * 4, 256));
+    if (ts) EZR_CUDA(cudaMemsetAsync(p.bound, 0, (size_t)n_queries * 4, st));
 
     CUtensorMap map_q, map_c;
     int rc = encode_tmap_2d_bf16(&map_q, queries, (uint64_t)dim, (uint64_t)n_queries, (uint64_t)ldq, TC_KC, TC_M);
