@@ -240,6 +240,24 @@ int ezr_fuse_lists(int32_t rrf, int32_t n_lists, const int32_t* const* ids_host,
                    int32_t canon_base, int32_t K, int32_t k_out, int32_t* out_ids, double* out_scores,
                    int32_t* out_counts, void* stream);
 
+/* ------------------------------------------------- reranker hand-off ---
+ * The coarse ranker's fused top-k -> the token sequences LLMRerank scores (rerankers.py:196-293 get_inputs /
+ * get_inputs_v2_5, sliced 32 at a time by _postprocess_nodes :309-322), built on the device.  Pair p = q*k + r is
+ * candidate r of query q: [bos] + query[: 3/4 max_length] + sep + passage (the pair truncated to max_length, the
+ * passage gives way) + sep + prompt.  Queries ("A: ..." ids, q_ptr/q_tok) and passages ("B: ..." ids of every chunk,
+ * tokenised once at index time, p_ptr/p_tok) are device CSR arrays.  Output is packed: ids[T], cu[P+1]; pairs past a
+ * query's count are empty.  plan: lengths, their scan (int64) and get_inputs_v2_5's query_lengths; *total_host = T
+ * (synchronises).  fill: the tokens + an int32 copy of cu (the cu_seqlens format of the encoder kernels). */
+int ezr_rerank_pack_plan(const int32_t* cand_ids, const int32_t* cand_cnt, int32_t n_queries, int32_t k, int32_t k_stride,
+                         int32_t id_base, const int32_t* q_ptr, const int64_t* p_ptr, int32_t n_sep, int32_t n_prompt,
+                         int32_t max_length, int64_t* out_len, int64_t* out_cu, int32_t* out_query_len,
+                         int64_t* total_host, void* stream);
+int ezr_rerank_pack_fill(const int32_t* cand_ids, const int32_t* cand_cnt, int32_t n_queries, int32_t k, int32_t k_stride,
+                         int32_t id_base, const int32_t* q_ptr, const int32_t* q_tok, const int64_t* p_ptr,
+                         const int32_t* p_tok, const int32_t* sep, int32_t n_sep, const int32_t* prompt, int32_t n_prompt,
+                         int32_t bos, int32_t max_length, const int64_t* cu, int32_t* out_ids, int32_t* out_cu32,
+                         void* stream);
+
 /* ------------------------------------------------------------ encoder ---
  * Building blocks of the chunk/query embedding forward pass (GTEEmbedding._embed, gte_embeddings.py:59-72 ->
  * Qwen2Model.forward, modeling_qwen.py:956-1116; HuggingFaceEmbedding._embed, hf_embeddings.py:112-123 ->

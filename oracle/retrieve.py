@@ -192,3 +192,24 @@ def dense_topk(corpus: np.ndarray, queries: np.ndarray, k: int,
         ids[i, :order.size] = order
         sc[i, :order.size] = s[order]
     return ids, sc
+
+
+def rerank_inputs(query_ids: Sequence[int], passages: Sequence[Sequence[int]], sep: Sequence[int], prompt: Sequence[int],
+                  bos: int, max_length: int = 1024):
+    """``LLMRerank.get_inputs`` / ``get_inputs_v2_5`` (rerankers.py:196-293) on token ids, before padding.
+
+    ``query_ids`` = tokenizer("A: " + query) and ``passages[i]`` = tokenizer("B: " + passage), add_special_tokens=False
+    (what the reference computes at :221-226 / :266-275; their own truncations max_length*3//4 and max_length are
+    applied here).  ``prepare_for_model(first, second, truncation='only_second', max_length=max_length)`` keeps
+    ``first`` whole and cuts ``second`` from its end.  Returns (list of id lists, query_lengths, prompt_lengths).
+    """
+    q = list(query_ids)[: max_length * 3 // 4]
+    items, qlens, plens = [], [], []
+    for p in passages:
+        first = [bos] + q
+        second = list(sep) + list(p)[:max_length]
+        second = second[: max(max_length - len(first), 0)]
+        items.append(first + second + list(sep) + list(prompt))
+        qlens.append(len(first) + len(sep))
+        plens.append(len(sep) + len(prompt))
+    return items, qlens, plens

@@ -274,3 +274,39 @@ def test_fusion_classmethods_on_the_class(world):
     ref = ort.fusion([to_o(l) for l in (a, b, c)], topk=15)
     got = HybridRetriever.fusion([a, b, c], topk=15)
     assert [int(g.node.node_id.split("-")[1]) for g in got] == [o.node.idx for o in ref]
+
+
+def test_rerank_packer_builds_the_reference_inputs_on_the_device(lib_built):
+    """rerankers.py:196-293 (get_inputs / get_inputs_v2_5) + the 32-pair slices of :309-322, from fused device ids."""
+    from easyrag_b200 import handoff
+    rng = np.random.default_rng(9)
+    n_docs, nq, k, max_length = 400, 7, 40, 64
+    passages = [rng.integers(5, 1000, rng.integers(0, 120)).tolist() for _ in range(n_docs)]      # some longer than max_length
+    sep, prompt, bos = [13], rng.integers(5, 1000, 9).tolist(), 1
+    packer = handoff.RerankPacker(passages, sep, prompt, bos, max_length=max_length)
+    queries = [rng.integers(5, 1000, rng.integers(1, 70)).tolist() for _ in range(nq)]            # some beyond 3/4 max_length
+    q_ptr = torch.tensor(np.cumsum([0] + [len(q) for q in queries]), dtype=torch.int32)
+    q_tok = torch.tensor([t for q in queries for t in q], dtype=torch.int32)
+    cnt = rng.integers(0, k + 1, nq).astype(np.int32)
+    cnt[0], cnt[1] = k, 0
+    ids = np.full((nq, k), -1, np.int32)
+    for q in range(nq):
+        ids[q, :cnt[q]] = rng.choice(n_docs, cnt[q], replace=False)
+    out = packer.pack(torch.from_numpy(ids).cuda(), torch.from_numpy(cnt).cuda(), q_ptr, q_tok)
+    cu, tok, qlen = out.cu.cpu().numpy(), out.ids.cpu().numpy(), out.query_len.cpu().numpy()
+    assert cu[0] == 0 and cu[-1] == tok.size and out.prompt_len == len(sep) + len(prompt)
+    for q in range(nq):
+        want, want_ql, want_pl = ort.rerank_inputs(queries[q], [passages[d] for d in ids[q, :cnt[q]]], sep, prompt, bos,
+                                                   max_length)
+        assert all(p == out.prompt_len for p in want_pl)
+        for r in range(k):
+            p = q * k + r
+            got = tok[cu[p]:cu[p + 1]].tolist()
+            if r < cnt[q]:
+                assert got == want[r], (q, r)
+                assert qlen[p] == want_ql[r] and len(got) <= max_length + len(sep) + len(prompt)
+            else:
+                assert got == [] and qlen[p] == 0
+    # slices in the reference's order: per query, 32 pairs at a time
+    sl = list(out.slices(32))
+    assert sl[:2] == [(0, 0, 32), (0, 32, 40)] and len(sl) == nq * 2 and sl[-1] == (nq - 1, (nq - 1) * k + 32, nq * k)

@@ -163,6 +163,12 @@ def test_rerank_handoff_slices_like_the_reference():
     import pytest
     with pytest.raises(ValueError):
         list(handoff.rerank_batches(nodes, "q", batch_size=0))
+    # the oracle restatement of get_inputs (rerankers.py:253-293) that the device packer is tested against
+    from oracle import retrieve as ort
+    items, ql, pl = ort.rerank_inputs([7, 8, 9], [[20, 21], list(range(100, 200))], sep=[13], prompt=[50, 51], bos=1,
+                                      max_length=16)
+    assert items[0] == [1, 7, 8, 9, 13, 20, 21, 13, 50, 51] and ql == [5, 5] and pl == [3, 3]
+    assert items[1] == [1, 7, 8, 9, 13] + list(range(100, 111)) + [13, 50, 51]       # pair cut to 16, passage gives way
 
 
 def test_ctypes_struct_layout_matches_the_c_header(tmp_path):
