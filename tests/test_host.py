@@ -171,6 +171,18 @@ def test_rerank_handoff_slices_like_the_reference():
     assert items[1] == [1, 7, 8, 9, 13] + list(range(100, 111)) + [13, 50, 51]       # pair cut to 16, passage gives way
 
 
+def test_integration_md_struct_matches_the_binding():
+    """The ctypes sample a maintainer would copy from INTEGRATION.md lists exactly the fields of the real binding
+    (a struct that is 8 bytes short makes the library read a garbage pointer: ADVICE round 1)."""
+    text = (ROOT / "INTEGRATION.md").read_text()
+    block = text[text.index("class ezr_bm25_index(C.Structure):"):]
+    block = block[:block.index("lib.ezr_bm25_topk.restype")]
+    doc_fields = re.findall(r'\("([a-z_0-9]+)",\s*C\.(c_[a-z0-9_]+)\)', block)
+    real = _lib.Bm25IndexStruct._fields_
+    assert [n for n, _ in doc_fields] == [n for n, _ in real]
+    assert all(getattr(ctypes, t) is rt for (_, t), (_, rt) in zip(doc_fields, real))      # c_int32 is an alias of c_int
+
+
 def test_ctypes_struct_layout_matches_the_c_header(tmp_path):
     # ezr_bm25_index crosses the boundary by pointer: the ctypes mirror must have the C compiler's layout.
     import ctypes

@@ -31,6 +31,23 @@ def test_okapi_known_answer_csr():
     assert np.allclose(got, k["scores"], atol=1e-8)
 
 
+def test_bm25s_lucene_hand_computed_known_answers():
+    """bm25s is absent offline; these vectors are computed by hand from its documented Lucene formula (kat.json says
+    how).  They pin the oracle's idf / tfc formula, the duplicate-token rule (np.add.at per query token) and the
+    float32 storage; what stays UNPINNED is anything the bm25s package does beyond that formula."""
+    k = KAT["bm25s_lucene"]
+    corpus = [d.split(" ") for d in k["corpus"]]
+    vocab = {}
+    docs = [np.array([vocab.setdefault(w, len(vocab)) for w in d]) for d in corpus]
+    m = obm.Bm25sLucene(docs, len(vocab), k1=k["k1"], b=k["b"])
+    assert abs(float(m.idf32[vocab["windy"]]) - k["idf_df1"]) <= 1e-7 * k["idf_df1"] * 2
+    assert abs(float(m.idf32[vocab["is"]]) - k["idf_df2"]) <= 1e-7 * k["idf_df2"] * 2
+    for q, want in k["queries"].items():
+        got = m.get_scores([vocab.get(w, -1) for w in q.split(" ")])
+        assert got.dtype == np.float32
+        assert np.allclose(got, want, rtol=k["rel_tol"], atol=0), (q, got, want)
+
+
 def _small_corpus(n=400, vocab=300, seed=3):
     c = synth.make_sparse_corpus(n, vocab, seed, mean_len=40, min_len=0, max_len=120)
     q = synth.make_queries(c, 25, seed + 1, min_terms=1, max_terms=9)
