@@ -4,16 +4,20 @@
 // handled by an additive mask :1037-1040) and BERT self-attention behind SentenceTransformer.encode
 // (hf_embeddings.py:118-123).  Sequences are packed, so the mask reduces to "keys beyond this sequence".
 //
-// One CTA = 128 query rows of one (sequence, head); two CTAs share an SM (256 TMEM columns and <= 96 KB of shared
-// memory each), so one CTA's softmax overlaps the other's MMAs.
-//   warp 0      TMA producer: Q tile once, then K / V tiles of 128 keys (one 2-D tensor map over the packed
+// Work item = 128 query rows of one (sequence, head).  A small plan kernel lists the (sequence, query block) pairs
+// that exist; PERSISTENT CTAs (two per SM: 256 TMEM columns and <= 96 KB of shared memory each, so one CTA's softmax
+// overlaps the other's MMAs) walk the items round-robin, query blocks of one (sequence, head) next to each other so
+// that concurrently running CTAs share its K / V tiles through L2.  Barriers, tensor memory and the tensor-map
+// prefetch are set up once per CTA, and the TMA producer runs ahead into the next item.
+//   warp 0      TMA producer: Q tile per item, K / V tiles of 128 keys (one 2-D tensor map over the packed
 //               [tokens, (H + 2 KV) hd] matrix serves Q, K and V; 128B swizzle; rows past the matrix are zero-filled)
 //   warp 1      tcgen05.mma issuer:  S = Q K^T   (SS form, both operands K-major in shared memory, N = keys of the tile)
 //                                    O += P V    (TS form: P is read from TENSOR MEMORY, V is the MN-major B operand
 //                                                 straight from its row-major TMA tile -- no transpose anywhere)
-//   warps 2-9   softmax: two warps per TMEM lane quadrant, a thread owns one query row and 64 of the 128 key columns:
-//               row max (pair exchange through shared memory), exp2 with the 1/sqrt(d) scale folded in, probabilities
-//               written back as packed bf16 over the S columns they came from (tcgen05.st), running sum in fp32.
+//   warps 2-9   softmax: two warps per TMEM lane quadrant, a thread owns one query row and 64 of the 128 key columns,
+//               read ONCE from tensor memory into registers: row max (pair exchange through shared memory), exp2 with
+//               the 1/sqrt(d) scale folded in, probabilities written back as packed bf16 over the S columns they came
+//               from (tcgen05.st), running sum in fp32; at the end of an item O / sum -> bf16 -> global.
 // TMEM columns: [0,128) S (fp32) aliased by P (bf16 pairs: keys 0-63 -> columns 0-31, keys 64-127 -> columns 64-95),
 // [128, 128+hd) O.  The running maximum is lazy: O is rescaled in tensor memory (tcgen05.ld / multiply / tcgen05.st)
 // only when a row's maximum grows by more than 2^8; otherwise the stale maximum stays (p <= 256 is harmless in
@@ -23,7 +27,7 @@
 
 namespace ezr {
 
-constexpr int AT_M = 128;                 // query rows per CTA (UMMA M, one TMEM lane each)
+constexpr int AT_M = 128;                 // query rows per work item (UMMA M, one TMEM lane each)
 constexpr int AT_N = 128;                 // keys per tile (UMMA N of S = Q K^T)
 constexpr int AT_THREADS = 320;           // TMA warp, MMA warp, 8 softmax warps
 constexpr int AT_BOX_BYTES = 128 * 64 * 2;   // one TMA box: 128 rows x 64 bf16
@@ -32,16 +36,54 @@ constexpr int AT_O_COL = 128;
 constexpr float AT_RESCALE_LOG2 = 8.0f;   // rescale O only when the row maximum grows by more than 2^8
 
 struct AttnBarriers {
-    uint64_t q_full;
+    uint64_t q_full, q_empty;
     uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
     uint64_t s_full, p_full, o_full;
     uint32_t tmem_base;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// plan[i] = (sequence << 8) | query block, for every 128-row query block that exists; plan_n[0] = their number.
+// One CTA; sequences in order, so the query blocks of a sequence are adjacent.
+__global__ void __launch_bounds__(256)
+attn_plan_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict__ plan, int32_t* __restrict__ plan_n) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_seq; b0 += 256) {
+        const int b = b0 + tid;
+        const int nqb = b < n_seq ? (cu[b + 1] - cu[b] + AT_M - 1) / AT_M : 0;
+        int inc = nqb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        const int first = before + inc - nqb;
+        for (int j = 0; j < nqb; ++j) plan[first + j] = (b << 8) | j;
+        __syncthreads();
+        if (tid == 255) s_base = before + inc;
+        __syncthreads();
+    }
+    if (tid == 0) plan_n[0] = s_base;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restrict__ cu, int n_heads, int n_kv_heads,
-               float scale_log2, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restrict__ cu, const int32_t* __restrict__ plan,
+               const int32_t* __restrict__ plan_n, int n_heads, int n_kv_heads, float scale_log2,
+               __nv_bfloat16* __restrict__ out, int64_t ldo) {
     constexpr int CH = HD / 64;                          // 64-column TMA boxes per tile
     constexpr int TILE_BYTES = CH * AT_BOX_BYTES;        // one Q / K / V tile
     constexpr int STAGES = HD == 64 ? 2 : 1;             // K/V ring depth (K and V have their own barriers)
@@ -53,19 +95,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
     AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_v + STAGES * TILE_BYTES);
     __shared__ float s_xch[2][AT_M];                     // pair exchange: row maxima, then row sums
 
-    const int qb = blockIdx.x, b = blockIdx.y, h = blockIdx.z;
-    const int lo = cu[b];
-    const int len = cu[b + 1] - lo;
-    const int q0 = qb * AT_M;
-    if (q0 >= len) return;                               // block-uniform
-    const int kvh = h / (n_heads / n_kv_heads);
-    const int col_q = h * HD, col_k = (n_heads + kvh) * HD, col_v = (n_heads + n_kv_heads + kvh) * HD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_kt = (len + AT_N - 1) / AT_N;
+    const int n_pairs = plan_n[0];
+    const int n_work = n_pairs * n_heads;                // work w: head = w / n_pairs, pair = w % n_pairs
+    const int kv_group = n_heads / n_kv_heads;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map);
         ptx::mbar_init(&bars->q_full, 1);
+        ptx::mbar_init(&bars->q_empty, 1);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&bars->k_full[i], 1);
             ptx::mbar_init(&bars->k_empty[i], 1);
@@ -85,64 +123,83 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---------------- TMA producer ----------------
-            ptx::mbar_expect_tx(&bars->q_full, TILE_BYTES);
-            for (int c = 0; c < CH; ++c)
-                ptx::tma_load_2d(smem_q + c * AT_BOX_BYTES, &map, &bars->q_full, col_q + c * 64, lo + q0);
-            for (int j = 0; j < n_kt; ++j) {
-                const int s = j % STAGES;
-                const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-                const int row = lo + j * AT_N;
-                ptx::mbar_wait(&bars->k_empty[s], ph ^ 1);
-                ptx::mbar_expect_tx(&bars->k_full[s], TILE_BYTES);
+            // ---------------- TMA producer: runs ahead of the consumers, across work items ----------------
+            int jt = 0;                                   // K/V tiles issued so far (ring position)
+            int it = 0;                                   // items started
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+                const int h = w / n_pairs, pe = plan[w % n_pairs];
+                const int b = pe >> 8, q0 = (pe & 0xff) * AT_M;
+                const int lo = cu[b], len = cu[b + 1] - lo;
+                const int kvh = h / kv_group;
+                const int col_q = h * HD, col_k = (n_heads + kvh) * HD, col_v = (n_heads + n_kv_heads + kvh) * HD;
+                const int n_kt = (len + AT_N - 1) / AT_N;
+                ptx::mbar_wait(&bars->q_empty, ((uint32_t)it & 1u) ^ 1u);      // the previous item's QK^T MMAs are done
+                ptx::mbar_expect_tx(&bars->q_full, TILE_BYTES);
                 for (int c = 0; c < CH; ++c)
-                    ptx::tma_load_2d(smem_k + s * TILE_BYTES + c * AT_BOX_BYTES, &map, &bars->k_full[s], col_k + c * 64, row);
-                ptx::mbar_wait(&bars->v_empty[s], ph ^ 1);
-                ptx::mbar_expect_tx(&bars->v_full[s], TILE_BYTES);
-                for (int c = 0; c < CH; ++c)
-                    ptx::tma_load_2d(smem_v + s * TILE_BYTES + c * AT_BOX_BYTES, &map, &bars->v_full[s], col_v + c * 64, row);
+                    ptx::tma_load_2d(smem_q + c * AT_BOX_BYTES, &map, &bars->q_full, col_q + c * 64, lo + q0);
+                for (int j = 0; j < n_kt; ++j, ++jt) {
+                    const int s = jt % STAGES;
+                    const uint32_t ph = (uint32_t)(jt / STAGES) & 1u;
+                    const int row = lo + j * AT_N;
+                    ptx::mbar_wait(&bars->k_empty[s], ph ^ 1);
+                    ptx::mbar_expect_tx(&bars->k_full[s], TILE_BYTES);
+                    for (int c = 0; c < CH; ++c)
+                        ptx::tma_load_2d(smem_k + s * TILE_BYTES + c * AT_BOX_BYTES, &map, &bars->k_full[s], col_k + c * 64, row);
+                    ptx::mbar_wait(&bars->v_empty[s], ph ^ 1);
+                    ptx::mbar_expect_tx(&bars->v_full[s], TILE_BYTES);
+                    for (int c = 0; c < CH; ++c)
+                        ptx::tma_load_2d(smem_v + s * TILE_BYTES + c * AT_BOX_BYTES, &map, &bars->v_full[s], col_v + c * 64, row);
+                }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
+        // ---------------- MMA issuer (warp-uniform loops, one elected lane issues) ----------------
         constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(AT_M, HD) | ptx::kIdescBMajorMN;
         const uint32_t q_addr = ptx::smem_u32(smem_q);
         const uint32_t tm_s = tmem_base, tm_o = tmem_base + AT_O_COL;
-        ptx::mbar_wait(&bars->q_full, 0);
-        for (int j = 0; j < n_kt; ++j) {
-            const int s = j % STAGES;
-            const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-            const int valid = len - j * AT_N;
-            const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);        // keys of this tile, multiple of 16
-            const uint32_t k_addr = ptx::smem_u32(smem_k + s * TILE_BYTES);
-            const uint32_t v_addr = ptx::smem_u32(smem_v + s * TILE_BYTES);
-            ptx::mbar_wait(&bars->k_full[s], ph);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                const uint32_t idesc_qk = ptx::make_idesc_bf16(AT_M, n_j);
+        int jt = 0, it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int pe = plan[w % n_pairs];
+            const int b = pe >> 8;
+            const int len = cu[b + 1] - cu[b];
+            const int n_kt = (len + AT_N - 1) / AT_N;
+            ptx::mbar_wait(&bars->q_full, (uint32_t)it & 1u);
+            for (int j = 0; j < n_kt; ++j, ++jt) {
+                const int s = jt % STAGES;
+                const uint32_t ph = (uint32_t)(jt / STAGES) & 1u;
+                const int valid = len - j * AT_N;
+                const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);     // keys of this tile, multiple of 16
+                const uint32_t k_addr = ptx::smem_u32(smem_k + s * TILE_BYTES);
+                const uint32_t v_addr = ptx::smem_u32(smem_v + s * TILE_BYTES);
+                ptx::mbar_wait(&bars->k_full[s], ph);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t idesc_qk = ptx::make_idesc_bf16(AT_M, n_j);
 #pragma unroll
-                for (int kk = 0; kk < HD / 16; ++kk) {
-                    const uint32_t off = (uint32_t)((kk >> 2) * AT_BOX_BYTES + (kk & 3) * 32);
-                    ptx::umma_f16_ss(tm_s, ptx::make_desc_sw128(q_addr + off), ptx::make_desc_sw128(k_addr + off), idesc_qk,
-                                     (uint32_t)(kk != 0));
+                    for (int kk = 0; kk < HD / 16; ++kk) {
+                        const uint32_t off = (uint32_t)((kk >> 2) * AT_BOX_BYTES + (kk & 3) * 32);
+                        ptx::umma_f16_ss(tm_s, ptx::make_desc_sw128(q_addr + off), ptx::make_desc_sw128(k_addr + off),
+                                         idesc_qk, (uint32_t)(kk != 0));
+                    }
+                    ptx::umma_commit(&bars->k_empty[s]);
+                    if (j == n_kt - 1) ptx::umma_commit(&bars->q_empty);          // the Q tile may be overwritten
+                    ptx::umma_commit(&bars->s_full);
                 }
-                ptx::umma_commit(&bars->k_empty[s]);
-                ptx::umma_commit(&bars->s_full);
-            }
-            __syncwarp();
-            ptx::mbar_wait(&bars->p_full, (uint32_t)j & 1u);                    // probabilities are in tensor memory
-            ptx::mbar_wait(&bars->v_full[s], ph);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                for (int i = 0; i < n_j / 16; ++i) {
-                    const uint32_t a_tmem = tm_s + (uint32_t)(i < 4 ? 8 * i : 64 + 8 * (i - 4));
-                    ptx::umma_f16_ts(tm_o, a_tmem, ptx::make_desc_sw128_mn(v_addr + (uint32_t)i * 2048u, AT_BOX_BYTES), idesc_pv,
-                                     (uint32_t)((j | i) != 0));
+                __syncwarp();
+                ptx::mbar_wait(&bars->p_full, (uint32_t)jt & 1u);                 // probabilities are in tensor memory
+                ptx::mbar_wait(&bars->v_full[s], ph);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    for (int i = 0; i < n_j / 16; ++i) {
+                        const uint32_t a_tmem = tm_s + (uint32_t)(i < 4 ? 8 * i : 64 + 8 * (i - 4));
+                        ptx::umma_f16_ts(tm_o, a_tmem, ptx::make_desc_sw128_mn(v_addr + (uint32_t)i * 2048u, AT_BOX_BYTES),
+                                         idesc_pv, (uint32_t)((j | i) != 0));
+                    }
+                    ptx::umma_commit(&bars->v_empty[s]);
+                    if (j == n_kt - 1) ptx::umma_commit(&bars->o_full);
                 }
-                ptx::umma_commit(&bars->v_empty[s]);
-                if (j == n_kt - 1) ptx::umma_commit(&bars->o_full);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ---------------- softmax + epilogue: 8 warps, two per TMEM lane quadrant ----------------
@@ -152,101 +209,121 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t s_col = (uint32_t)(half * 64);
         const uint32_t o_col = (uint32_t)(AT_O_COL + half * (HD / 2));
-        float m_run = -INFINITY, l_part = 0.f;
-        for (int j = 0; j < n_kt; ++j) {
-            const int valid = len - j * AT_N;
-            const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);
-            ptx::mbar_wait(&bars->s_full, (uint32_t)j & 1u);   // also: every earlier O += P V has retired
-            ptx::tc_fence_after();
-            // pass 1: maximum of the row over this warp's columns
-            float mx = -INFINITY;
+        int jt = 0, it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const int h = w / n_pairs, pe = plan[w % n_pairs];
+            const int b = pe >> 8, q0 = (pe & 0xff) * AT_M;
+            const int lo = cu[b], len = cu[b + 1] - lo;
+            const int n_kt = (len + AT_N - 1) / AT_N;
+            float m_run = -INFINITY, l_part = 0.f;
+            for (int j = 0; j < n_kt; ++j, ++jt) {
+                const int valid = len - j * AT_N;
+                const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);
+                const bool two = (int)s_col + 32 < n_j;            // this warp's second 32-column chunk exists
+                const bool any = (int)s_col < n_j;                 // ... its first one (warp-uniform)
+                ptx::mbar_wait(&bars->s_full, (uint32_t)jt & 1u);  // also: every earlier O += P V has retired
+                ptx::tc_fence_after();
+                // the warp's 64 S values, read once (columns past n_j hold stale data: masked below, never used)
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld_32x32(lane_addr + s_col, r0);
+                ptx::tmem_ld_32x32(lane_addr + s_col + 32, r1);
+                ptx::tmem_ld_wait();
+                float mx = -INFINITY;
+                if (valid < AT_N) {                                // last tile of the sequence: mask the keys past it
+                    const int lim = valid - (int)s_col;            // columns of this warp's slice that are real keys
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int col0 = (int)s_col + c * 32;
-                if (col0 < n_j) {                              // warp-uniform
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32(lane_addr + (uint32_t)col0, r);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, col0 + i < valid ? __uint_as_float(r[i]) : -INFINITY);
+                    for (int i = 0; i < 32; ++i) {
+                        r0[i] = i < lim ? r0[i] : 0xff800000u;     // -inf: exp2 gives 0
+                        r1[i] = 32 + i < lim ? r1[i] : 0xff800000u;
+                    }
                 }
-            }
-            s_xch[half][row] = mx;
-            ptx::named_bar_sync(1 + quad, 64);
-            mx = fmaxf(mx, s_xch[half ^ 1][row]);
-            float m_new = fmaxf(m_run, mx);
-            const bool grow = (m_new - m_run) * scale_log2 > AT_RESCALE_LOG2;   // true on the first tile (m_run = -inf)
-            if (!grow) m_new = m_run;
-            const float alpha = exp2f((m_run - m_new) * scale_log2);            // 1 when the maximum is kept
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {
-                // rare: bring this warp's half of the O columns to the new maximum
 #pragma unroll
-                for (int c = 0; c < HD / 64; ++c) {
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32(lane_addr + o_col + c * 32, r);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                    ptx::tmem_st_32x32(lane_addr + o_col + c * 32, r);
-                }
-            }
-            l_part *= alpha;
-            m_run = m_new;
-            const float mb = m_new * scale_log2;
-            // pass 2: probabilities, packed to bf16 over the S columns they came from
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int col0 = (int)s_col + c * 32;
-                if (col0 < n_j) {
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32(lane_addr + (uint32_t)col0, r);
-                    ptx::tmem_ld_wait();
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+                s_xch[half][row] = mx;
+                ptx::named_bar_sync(1 + quad, 64);
+                mx = fmaxf(mx, s_xch[half ^ 1][row]);
+                float m_new = fmaxf(m_run, mx);
+                const bool grow = (m_new - m_run) * scale_log2 > AT_RESCALE_LOG2;   // true on the first tile (m_run = -inf)
+                if (!grow) m_new = m_run;
+                const float alpha = ex2_approx((m_run - m_new) * scale_log2);       // 1 when the maximum is kept
+                const bool rescale = j > 0 && __any_sync(0xffffffffu, grow);
+                l_part *= alpha;
+                m_run = m_new;
+                const float mb = m_new * scale_log2;
+                if (any) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const float p0 = col0 + i < valid ? exp2f(fmaf(__uint_as_float(r[i]), scale_log2, -mb)) : 0.f;
-                        const float p1 = col0 + i + 1 < valid ? exp2f(fmaf(__uint_as_float(r[i + 1]), scale_log2, -mb)) : 0.f;
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(r0[i]), scale_log2, -mb));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(r0[i + 1]), scale_log2, -mb));
                         l_part += p0 + p1;
                         __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
                         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&v);
                     }
-                    ptx::tmem_st_32x16(lane_addr + s_col + (uint32_t)(c * 16), pk);
+                    ptx::tmem_st_32x16(lane_addr + s_col, pk);
+                }
+                if (two) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(r1[i]), scale_log2, -mb));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(r1[i + 1]), scale_log2, -mb));
+                        l_part += p0 + p1;
+                        __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&v);
+                    }
+                    ptx::tmem_st_32x16(lane_addr + s_col + 16, pk);
+                }
+                if (rescale) {
+                    // rare: bring this warp's half of the O columns to the new maximum (after the S registers are dead)
+#pragma unroll
+                    for (int c = 0; c < HD / 64; ++c) {
+                        uint32_t r[32];
+                        ptx::tmem_ld_32x32(lane_addr + o_col + c * 32, r);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        ptx::tmem_st_32x32(lane_addr + o_col + c * 32, r);
+                    }
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars->p_full);
+            }
+            // epilogue of the item: O / row sum -> bf16 -> global
+            s_xch[half][row] = l_part;
+            ptx::named_bar_sync(1 + quad, 64);
+            const float inv = 1.0f / (l_part + s_xch[half ^ 1][row]);
+            ptx::mbar_wait(&bars->o_full, (uint32_t)it & 1u);
+            ptx::tc_fence_after();
+            const bool row_ok = q0 + row < len;
+            __nv_bfloat16* orow = out + (int64_t)(lo + q0 + row) * ldo + h * HD + half * (HD / 2);
+#pragma unroll
+            for (int c = 0; c < HD / 64; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(lane_addr + o_col + c * 32, r);
+                ptx::tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 pk;
+                        __nv_bfloat162 v;
+                        v = __floats2bfloat162_rn(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+                        pk.x = *reinterpret_cast<uint32_t*>(&v);
+                        v = __floats2bfloat162_rn(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+                        pk.y = *reinterpret_cast<uint32_t*>(&v);
+                        v = __floats2bfloat162_rn(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+                        pk.z = *reinterpret_cast<uint32_t*>(&v);
+                        v = __floats2bfloat162_rn(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+                        pk.w = *reinterpret_cast<uint32_t*>(&v);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + i) = pk;
+                    }
                 }
             }
-            ptx::tmem_st_wait();
+            // the pair's s_xch slots and this warp's O columns are reused by the next item: its first exchange is
+            // ordered behind these reads by the named barrier above / the p_full handshake
             ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bars->p_full);
-        }
-        // epilogue: O / row sum -> bf16 -> global
-        s_xch[half][row] = l_part;
-        ptx::named_bar_sync(1 + quad, 64);
-        const float inv = 1.0f / (l_part + s_xch[half ^ 1][row]);
-        ptx::mbar_wait(&bars->o_full, 0);
-        ptx::tc_fence_after();
-        const bool row_ok = q0 + row < len;
-        __nv_bfloat16* orow = out + (int64_t)(lo + q0 + row) * ldo + h * HD + half * (HD / 2);
-#pragma unroll
-        for (int c = 0; c < HD / 64; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(lane_addr + o_col + c * 32, r);
-            ptx::tmem_ld_wait();
-            if (row_ok) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 pk;
-                    __nv_bfloat162 v;
-                    v = __floats2bfloat162_rn(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-                    pk.x = *reinterpret_cast<uint32_t*>(&v);
-                    v = __floats2bfloat162_rn(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
-                    pk.y = *reinterpret_cast<uint32_t*>(&v);
-                    v = __floats2bfloat162_rn(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
-                    pk.z = *reinterpret_cast<uint32_t*>(&v);
-                    v = __floats2bfloat162_rn(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
-                    pk.w = *reinterpret_cast<uint32_t*>(&v);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + i) = pk;
-                }
-            }
         }
     }
 
@@ -265,6 +342,10 @@ int attn_bidir_legacy(const void* qkv, int64_t ld, const int32_t* cu_seqlens, in
 static int g_attn_kernel = 0;     // ezr_attn_set_kernel: 0 = tcgen05 (default), 1 = legacy mma.sync kernel (cross-checks)
 static thread_local const char* g_attn_last = "none";
 
+// plan buffer (query-block list) of the calling thread's device, grown on demand; (n_seq * 256 + 1) ints at most
+static thread_local int32_t* g_plan = nullptr;
+static thread_local size_t g_plan_cap = 0;
+
 template <int HD>
 static int attn_tc_launch(const CUtensorMap& map, const int32_t* cu, int n_seq, int max_len, int n_heads, int n_kv_heads,
                           float scale_log2, __nv_bfloat16* out, int64_t ldo, cudaStream_t st) {
@@ -277,9 +358,24 @@ static int attn_tc_launch(const CUtensorMap& map, const int32_t* cu, int n_seq, 
                                       cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
-    dim3 grid((max_len + AT_M - 1) / AT_M, n_seq, n_heads);
+    const int max_qb = (max_len + AT_M - 1) / AT_M;
+    EZR_CHECK_ARG(max_qb <= 256, "attn: sequences longer than %d tokens are not supported", 256 * AT_M);
+    const size_t need = (size_t)n_seq * max_qb + 1;
+    if (need > g_plan_cap) {                              // first call / larger batch: grow (synchronises once)
+        if (g_plan) EZR_CUDA(cudaFree(g_plan));
+        g_plan = nullptr;
+        g_plan_cap = 0;
+        EZR_CUDA(cudaMalloc(&g_plan, need * 2 * sizeof(int32_t)));
+        g_plan_cap = need * 2;
+    }
+    int32_t* plan_n = g_plan;
+    int32_t* plan = g_plan + 1;
     ProfScope prof(EZR_PROF_ENC_ATTN, st);
-    attn_tc_kernel<HD><<<grid, AT_THREADS, smem, st>>>(map, cu, n_heads, n_kv_heads, scale_log2, out, ldo);
+    attn_plan_kernel<<<1, 256, 0, st>>>(cu, n_seq, plan, plan_n);
+    EZR_LAUNCH_CHECK();
+    const long long upper = (long long)n_seq * max_qb * n_heads;      // work items at most
+    const int grid = (int)(upper < 2ll * sm_count() ? upper : 2ll * sm_count());
+    attn_tc_kernel<HD><<<grid, AT_THREADS, smem, st>>>(map, cu, plan, plan_n, n_heads, n_kv_heads, scale_log2, out, ldo);
     EZR_LAUNCH_CHECK();
     return EZR_OK;
 }

@@ -583,8 +583,8 @@ def test_index_build_long_documents_empty_documents_and_bad_tokens():
     st = Bm25Stats.from_tokens(tokens, ptr, vocab)
     _assert_counts_equal(st, tokens, ptr, vocab)
     bad = tokens.clone()
-    bad[9100] = vocab                                                # inside document 2
-    with pytest.raises(ValueError, match="document 2"):
+    bad[9100] = vocab                                                # inside document 4 (tokens 9005..17196)
+    with pytest.raises(ValueError, match="document 4"):
         Bm25Stats.from_tokens(bad, ptr, vocab)
 
 
