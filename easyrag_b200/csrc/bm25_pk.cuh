@@ -33,6 +33,7 @@
 // candidate pass gets 14% faster but candidates multiply (their partial lower bounds tighten B more slowly) and the
 // rescoring eats the gain several times over, so ezr_bm25_set_skipping is OFF by default.
 #pragma once
+#include <type_traits>
 
 namespace ezr {
 
@@ -155,10 +156,6 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     const int rbase = r * kBmRange;
     const uint32_t* __restrict__ pk = c.post_pk;
     const int want = p.q_group ? p.q_group[q] : -1;
-    if (tid == kPkThreads - 1) {
-        s_b = *reinterpret_cast<const volatile int32_t*>(c.thr_q + q);
-        s_cnt = 0;
-    }
     // lane j of every warp: posting segment of token tb + j in this range
     auto load_seg = [&](int tb, int& beg, int& len) {
         beg = 0; len = 0;
@@ -172,8 +169,29 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
             }
         }
     };
-    int beg, len;
-    load_seg(0, beg, len);
+    // Set-up of the (query, range): ONE warp resolves the bound, the (optional) skipped tokens and the first 32 token
+    // segments (three dependent loads each) and leaves them in shared memory, while the other warps clear the
+    // accumulators; every warp then picks its lane's segment up with three shared-memory loads.  (Done by all eight
+    // warps redundantly this was ~45% of the instructions of an average CTA: profiles/README.md, round 2.)
+    __shared__ int s_beg[32], s_len[32], s_ne;
+    if (warp == kPkWarps - 1) {
+        int b0 = 0;
+        if (lane == 0) b0 = *reinterpret_cast<const volatile int32_t*>(c.thr_q + q);
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        int beg0, len0;
+        load_seg(0, beg0, len0);
+        // tokens bm25_bound_kernel declared non-essential for this query (valid for every later, higher bound): their
+        // postings are not read, their largest possible contribution NE is taken off the crossing threshold instead
+        const uint32_t nm = (b0 > 0 && c.term_max) ? __ldg(c.ne_mask + q) : 0u;
+        if ((nm >> lane) & 1u) len0 = 0;                // first token batch only (the mask covers tokens 0..31)
+        s_beg[lane] = beg0;
+        s_len[lane] = len0;
+        if (lane == 0) {
+            s_b = b0;
+            s_cnt = 0;
+            s_ne = nm ? __ldg(c.ne_sum + q) : 0;
+        }
+    }
     {
         uint4* a4 = reinterpret_cast<uint4*>(acc);
 #pragma unroll
@@ -182,13 +200,10 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     }
     __syncthreads();
 
+    int beg = s_beg[lane], len = s_len[lane];
     const int bound = s_b;                               // B: lower bound of S * (k-th best exact score), 0 = none yet
     const bool track = bound > 0;
-    // tokens bm25_bound_kernel declared non-essential for this query (valid for every later, higher bound): their
-    // postings are not read, their largest possible contribution NE is taken off the crossing threshold instead
-    const uint32_t ne_mask = (track && c.term_max) ? __ldg(c.ne_mask + q) : 0u;
-    const int ne = ne_mask ? __ldg(c.ne_sum + q) : 0;
-    if ((ne_mask >> lane) & 1u) len = 0;                 // first token batch only (the mask covers tokens 0..31)
+    const int ne = s_ne;
     // crossing test in one unsigned compare: old < tq <= old + wq  <=>  tq - 1 - old < wq  (wraps to a huge value
     // when old >= tq; without a bound tq1 = 2^32-1: ~old is never below a packed weight)
     const uint32_t tq1 = track ? (uint32_t)max(bound - 1 - ne, 1) - 1u : 0xffffffffu;
@@ -236,29 +251,40 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
             const int jp = __shfl_sync(0xffffffffu, pre, j);
             const int o0 = (g - jp) * kPkPiece + lane;
             const uint32_t* src = pk + jb + o0;
-            uint32_t x[kPkUnroll];
+            // 32-posting slots this piece really has (warp-uniform).  Most segments of a (query, range) are short
+            // (a rare term has a handful of postings in 8192 documents), so the work item comes in three sizes --
+            // 1, 4 or kPkUnroll slots -- behind a warp-uniform branch: a short segment executes one load + one atomic
+            // instead of kPkUnroll predicated-off copies of them.
+            const int n_u = (jl - (g - jp) * kPkPiece + 31) >> 5;
+            auto run = [&](auto tag) {
+                constexpr int NU = decltype(tag)::value;
+                uint32_t x[NU];
 #pragma unroll
-            for (int u = 0; u < kPkUnroll; ++u) x[u] = (o0 + u * 32 < jl) ? __ldg(src + u * 32) : 0u;
+                for (int u = 0; u < NU; ++u) x[u] = (o0 + u * 32 < jl) ? __ldg(src + u * 32) : 0u;
 #if EZR_BM25_PK_VOTE_EACH    // A/B switch: one warp vote per posting slot (the first version)
 #pragma unroll
-            for (int u = 0; u < kPkUnroll; ++u) {
-                const bool crossed = apply(x[u]);
-                if (__any_sync(0xffffffffu, crossed)) {  // warp-uniform branch; almost never taken
-                    if (crossed) push(x[u]);
+                for (int u = 0; u < NU; ++u) {
+                    const bool crossed = apply(x[u]);
+                    if (__any_sync(0xffffffffu, crossed)) {  // warp-uniform branch; almost never taken
+                        if (crossed) push(x[u]);
+                    }
                 }
-            }
 #else
-            // one vote per work item: crossings are collected in a bit mask; the (rare) push path re-reads its
-            // posting instead of keeping all loaded words live across the vote
-            unsigned crossed = 0u;
+                // one vote per work item: crossings are collected in a bit mask; the (rare) push path re-reads its
+                // posting instead of keeping all loaded words live across the vote
+                unsigned crossed = 0u;
 #pragma unroll
-            for (int u = 0; u < kPkUnroll; ++u) crossed |= (apply(x[u]) ? 1u : 0u) << u;
-            if (__any_sync(0xffffffffu, crossed != 0u)) {
+                for (int u = 0; u < NU; ++u) crossed |= (apply(x[u]) ? 1u : 0u) << u;
+                if (__any_sync(0xffffffffu, crossed != 0u)) {
 #pragma unroll 1
-                for (int u = 0; u < kPkUnroll; ++u)
-                    if ((crossed >> u) & 1u) push(__ldg(src + u * 32));
-            }
+                    for (int u = 0; u < NU; ++u)
+                        if ((crossed >> u) & 1u) push(__ldg(src + u * 32));
+                }
 #endif
+            };
+            if (n_u <= 1) run(std::integral_constant<int, 1>{});
+            else if (n_u <= 4 && kPkUnroll > 4) run(std::integral_constant<int, 4>{});
+            else run(std::integral_constant<int, kPkUnroll>{});
         }
     }
     __syncthreads();                                     // every contribution of this (query, range) is in acc

@@ -93,7 +93,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
     unsigned char* smem_k = smem_q + TILE_BYTES;
     unsigned char* smem_v = smem_k + STAGES * TILE_BYTES;
     AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_v + STAGES * TILE_BYTES);
-    __shared__ float s_xch[2][AT_M];                     // pair exchange: row maxima, then row sums
+    __shared__ float s_xch[2][AT_M];                     // pair exchange of the row maxima (every tile)
+    __shared__ float s_sum[2][AT_M];                     // ... and of the row sums (once per item): separate slots, so a
+                                                         // warp that runs ahead into the next item cannot overwrite what
+                                                         // its partner has not read yet
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pairs = plan_n[0];
@@ -292,9 +295,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
                 if (lane == 0) ptx::mbar_arrive(&bars->p_full);
             }
             // epilogue of the item: O / row sum -> bf16 -> global
-            s_xch[half][row] = l_part;
+            s_sum[half][row] = l_part;
             ptx::named_bar_sync(1 + quad, 64);
-            const float inv = 1.0f / (l_part + s_xch[half ^ 1][row]);
+            const float inv = 1.0f / (l_part + s_sum[half ^ 1][row]);
             ptx::mbar_wait(&bars->o_full, (uint32_t)it & 1u);
             ptx::tc_fence_after();
             const bool row_ok = q0 + row < len;
@@ -321,8 +324,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
                     }
                 }
             }
-            // the pair's s_xch slots and this warp's O columns are reused by the next item: its first exchange is
-            // ordered behind these reads by the named barrier above / the p_full handshake
+            // this warp's O columns are rewritten by the next item's first O = P V, which is issued only after this
+            // warp's next p_full arrival
             ptx::tc_fence_before();
         }
     }
@@ -345,6 +348,7 @@ static thread_local const char* g_attn_last = "none";
 // plan buffer (query-block list) of the calling thread's device, grown on demand; (n_seq * 256 + 1) ints at most
 static thread_local int32_t* g_plan = nullptr;
 static thread_local size_t g_plan_cap = 0;
+static thread_local int g_plan_dev = -1;
 
 template <int HD>
 static int attn_tc_launch(const CUtensorMap& map, const int32_t* cu, int n_seq, int max_len, int n_heads, int n_kv_heads,
@@ -361,8 +365,11 @@ static int attn_tc_launch(const CUtensorMap& map, const int32_t* cu, int n_seq, 
     const int max_qb = (max_len + AT_M - 1) / AT_M;
     EZR_CHECK_ARG(max_qb <= 256, "attn: sequences longer than %d tokens are not supported", 256 * AT_M);
     const size_t need = (size_t)n_seq * max_qb + 1;
-    if (need > g_plan_cap) {                              // first call / larger batch: grow (synchronises once)
-        if (g_plan) EZR_CUDA(cudaFree(g_plan));
+    int dev = 0;
+    EZR_CUDA(cudaGetDevice(&dev));
+    if (need > g_plan_cap || dev != g_plan_dev) {         // first call / larger batch / other device: (re)allocate
+        if (g_plan && dev == g_plan_dev) EZR_CUDA(cudaFree(g_plan));
+        g_plan_dev = dev;
         g_plan = nullptr;
         g_plan_cap = 0;
         EZR_CUDA(cudaMalloc(&g_plan, need * 2 * sizeof(int32_t)));
