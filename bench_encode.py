@@ -177,14 +177,24 @@ def oracle_parity(arch, cfg, state, model, batch, n_seq: int) -> dict:
     got = model.embed_packed(sub)[1].cpu()
     ids = batch.ids[:total].cpu().tolist()
     seqs = [ids[int(cu[i]):int(cu[i + 1])] for i in range(n_seq)]
+    import torch.nn.functional as F
     if arch == "bert":
         ref = oenc.bert_embed(state, cfg, seqs, pooling="cls")
+        ref_bf16 = oenc.bert_embed(state, cfg, seqs, pooling="cls", dtype=torch.bfloat16)
     else:
         iid, mask = oenc.pad_left(seqs)
         ref = oenc.gte_embed(state, cfg, iid, mask)
-    diff = float(((got @ got.T) - (ref @ ref.T)).abs().max())
-    return {"sequences": n_seq, "max_abs_cosine_diff_vs_fp32_oracle": diff, "tol": 1e-3, "ok": diff <= 1e-3,
-            "min_self_cosine": float((got * ref).sum(1).min())}
+        ref_bf16 = oenc.gte_embed(state, cfg, iid, mask, torch.bfloat16)
+    ref_bf16 = F.normalize(ref_bf16.float(), dim=1)
+    got = F.normalize(got, dim=1)
+    # the bar of tests/test_gpu_encoder.py: every embedding within 1e-3 (cosine) of the fp32 oracle's, and the pairwise
+    # cosine scores (what a retriever sees) within 1e-3 of the fp32 scores beyond the floor ANY bf16 evaluation of
+    # these weights has (the oracle itself run in bf16 on the CPU)
+    self_cos = float((got * ref).sum(1).min())
+    err = float(((got @ got.T) - (ref @ ref.T)).abs().max())
+    floor = float(((ref_bf16 @ ref_bf16.T) - (ref @ ref.T)).abs().max())
+    return {"sequences": n_seq, "min_cosine_to_fp32_oracle": self_cos, "pairwise_cosine_max_abs_err": err,
+            "bf16_oracle_floor": floor, "tol": 1e-3, "ok": bool(self_cos >= 1 - 1e-3 and err <= floor + 1e-3)}
 
 
 def main(from_bench=None):

@@ -109,8 +109,11 @@ def pad_right(seqs, pad_id=0):
     return ids, mask
 
 
-def bert_embed(state, cfg, seqs, pooling: str = "cls", normalize: bool = True, device="cpu") -> torch.Tensor:
-    """transformers.BertModel (fp32, eager) + pooling + F.normalize -> float32 [B, d]."""
+def bert_embed(state, cfg, seqs, pooling: str = "cls", normalize: bool = True, device="cpu",
+               dtype=torch.float32) -> torch.Tensor:
+    """transformers.BertModel (eager; fp32 = what SentenceTransformer.encode runs, hf_embeddings.py:80-92 passes no
+    dtype) + pooling + F.normalize -> float32 [B, d].  ``dtype=torch.bfloat16`` evaluates the same model in bf16: its
+    distance from the fp32 result is the noise floor of ANY bf16 evaluation of these weights."""
     from transformers import BertConfig as HFBertConfig, BertModel
     hf = HFBertConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_hidden_layers,
                       num_attention_heads=cfg.num_attention_heads, intermediate_size=cfg.intermediate_size,
@@ -119,10 +122,10 @@ def bert_embed(state, cfg, seqs, pooling: str = "cls", normalize: bool = True, d
     model = BertModel(hf, add_pooling_layer=False).eval()
     missing, unexpected = model.load_state_dict({k: v.float() for k, v in state.items()}, strict=False)
     assert not [m for m in missing if "position_ids" not in m], missing
-    model = model.to(device)
+    model = model.to(device=device, dtype=dtype)
     ids, mask = pad_right(seqs)
     with torch.no_grad():
-        h = model(input_ids=ids.to(device), attention_mask=mask.to(device)).last_hidden_state
+        h = model(input_ids=ids.to(device), attention_mask=mask.to(device)).last_hidden_state.float()
     m = mask.to(device).unsqueeze(-1).float()
     if pooling == "cls":
         e = h[:, 0]
