@@ -70,7 +70,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (parity still runs)")
     ap.add_argument("--parity-queries", type=int, default=256,
                     help="queries compared with the CPU oracle over the full corpus after timing (0 = off)")
-    ap.add_argument("--dense-kernel", type=int, default=0, help="0 auto, 1 simt, 2 tcgen05 SS, 3 tcgen05 TS")
+    ap.add_argument("--dense-kernel", type=int, default=0,
+                    help="0 auto, 1 simt, 2 tcgen05 SS, 3 tcgen05 TS (N=64), 4 TS (N=128), 5 TS128 in cluster pairs (multicast)")
     ap.add_argument("--overlap", type=int, default=1, help="1 (default): dense and BM25 routes on two streams")
     ap.add_argument("--cal-steps", type=int, default=5, help="non-overlapped calibration steps for per-kernel times")
     ap.add_argument("--self-check", type=int, default=64,

@@ -145,8 +145,9 @@ using namespace ezr;
 extern "C" {
 
 int ezr_dense_set_kernel(int32_t which) {
-    EZR_CHECK_ARG(which >= 0 && which <= 4,
-                  "dense_set_kernel: 0 auto, 1 simt, 2 tcgen05 (SS), 3 tcgen05 (TS, N=64), 4 tcgen05 (TS, N=128)");
+    EZR_CHECK_ARG(which >= 0 && which <= 5,
+                  "dense_set_kernel: 0 auto, 1 simt, 2 tcgen05 (SS), 3 tcgen05 (TS, N=64), 4 tcgen05 (TS, N=128), "
+                  "5 tcgen05 (TS, N=128, cluster pairs with multicast corpus tiles)");
     g_force_kernel = which;
     return EZR_OK;
 }
@@ -197,12 +198,14 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
         return EZR_ERR_UNSUPPORTED;
     }
     if (tc_ok && g_force_kernel != 1) {
-        int variant = g_force_kernel == 4 ? 2 : g_force_kernel == 3 ? 1 : (g_force_kernel == 2 ? 0 : g_default_variant);
+        // 0 = SS, 1 = TS with 64-row tiles, 2 = TS with 128-row tiles, 3 = TS128 in cluster pairs (multicast corpus tiles)
+        int variant = g_force_kernel == 5 ? 3 : g_force_kernel == 4 ? 2 : g_force_kernel == 3 ? 1
+                      : (g_force_kernel == 2 ? 0 : g_default_variant);
         if (dim > 768 && variant == 0) {
             set_error("dense_topk: the SS tcgen05 kernel supports dim <= 768 (got %d)", dim);
             return EZR_ERR_UNSUPPORTED;
         }
-        g_last_kernel = variant == 2 ? "tcgen05-ts128" : variant == 1 ? "tcgen05-ts" : "tcgen05";
+        g_last_kernel = variant == 3 ? "tcgen05-ts128-mc2" : variant == 2 ? "tcgen05-ts128" : variant == 1 ? "tcgen05-ts" : "tcgen05";
         return dense_tc_topk(c, n_rows, dim, ld_corpus, q, n_queries, ld_queries, k, doc_group, q_group, id_base,
                              out_scores, out_ids, out_counts, workspace, workspace_bytes, st, variant);
     }

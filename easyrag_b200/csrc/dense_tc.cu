@@ -259,7 +259,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // operand from tensor memory at 64 B/clk (4 KB per 128x16 slab = 64 cycles per MMA, measured: a pipeline run
 // with the TMA loads removed still takes 64 cycles per N=64 MMA, twice its 32-cycle floor), so only N >= 128
 // keeps the tensor pipe busy: one MMA then covers 128 corpus rows in the same 64 cycles.
-template <bool FILTER, int KT, int TN>
+// CL = 2: CTAs run in cluster pairs on the same corpus split with two neighbouring query blocks; each CTA loads HALF of
+// every corpus tile and TMA-multicasts it into both CTAs' rings (map_c then has boxes of TN / 2 rows), so a pair
+// pulls each tile from L2 once instead of twice.  The stage hand-over is the only other change: a ring stage is free
+// when BOTH CTAs' MMAs have released it (tcgen05.commit multicast), because the peer's multicast writes into it.
+template <bool FILTER, int KT, int TN, int CL>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                 const TcParams p) {
@@ -277,7 +281,11 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_units = p.n_slices * p.n_qblocks;
+    // work unit = (corpus split, group of CL neighbouring query blocks); this CTA owns query block group * CL + rank
+    const int rank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+    const int worker = blockIdx.x / CL, n_workers = gridDim.x / CL;
+    const int qb_groups = (p.n_qblocks + CL - 1) / CL;
+    const int n_units = p.n_slices * qb_groups;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_c);
@@ -287,7 +295,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ptx::mbar_init(&bars->ahi_empty, 1);
         for (int i = 0; i < p.n_stages; ++i) {
             ptx::mbar_init(&bars->b_full[i], 1);
-            ptx::mbar_init(&bars->b_empty[i], 1);
+            ptx::mbar_init(&bars->b_empty[i], CL);
         }
         for (int i = 0; i < TS_ACC; ++i) {
             ptx::mbar_init(&bars->acc_full[i], 1);
@@ -298,6 +306,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (warp == 1) ptx::tmem_alloc<512>(&bars->tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
+    if (CL > 1) ptx::cluster_sync();     // the peer's barriers exist before anything is multicast into this CTA
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -307,14 +316,14 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             int ui = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-                const int slice = u / p.n_qblocks;
+            for (int u = worker; u < n_units; u += n_workers, ++ui) {
+                const int slice = u / qb_groups;
                 const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
                 const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
                 const int n_tiles = (int)((row_end - row_begin + TN - 1) / TN);
                 if (kc_sm > 0) {
                     // tail of the query block (columns >= 768) -> shared memory, once the previous unit's MMAs are done
-                    const int q0 = (u % p.n_qblocks) * TC_M;
+                    const int q0 = ((u % qb_groups) * CL + rank) * TC_M;
                     ptx::mbar_wait(&bars->ahi_empty, ((uint32_t)ui & 1u) ^ 1u);
                     ptx::mbar_expect_tx(&bars->ahi_full, (uint32_t)kc_sm * TC_A_CHUNK_BYTES);
                     for (int j = 0; j < kc_sm; ++j)
@@ -332,9 +341,15 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         }
                         ptx::mbar_expect_tx(&bars->b_full[stage], (uint32_t)(p.kps * B_CHUNK_BYTES));
                         unsigned char* dst = smem_b + (size_t)stage * (size_t)(p.kps * B_CHUNK_BYTES);
-                        for (int j = 0; j < p.kps; ++j)
-                            ptx::tma_load_2d(dst + (size_t)j * B_CHUNK_BYTES, &map_c, &bars->b_full[stage],
-                                             (kc + j) * TC_KC, row0);
+                        for (int j = 0; j < p.kps; ++j) {
+                            if (CL == 1)
+                                ptx::tma_load_2d(dst + (size_t)j * B_CHUNK_BYTES, &map_c, &bars->b_full[stage],
+                                                 (kc + j) * TC_KC, row0);
+                            else     // this CTA's rows [rank * TN / 2, +TN / 2) of the tile, into both CTAs
+                                ptx::tma_load_2d_mcast(dst + (size_t)j * B_CHUNK_BYTES + (size_t)rank * (B_CHUNK_BYTES / CL),
+                                                       &map_c, &bars->b_full[stage], (kc + j) * TC_KC,
+                                                       row0 + rank * (TN / CL), (uint16_t)0x3);
+                        }
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -351,8 +366,8 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t phase = 0;
         int it = 0;           // tiles issued by this CTA so far (accumulator stage / phase)
         int ui = 0;           // units started (phase of a_full / ahi_full)
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-            const int slice = u / p.n_qblocks;
+        for (int u = worker; u < n_units; u += n_workers, ++ui) {
+            const int slice = u / qb_groups;
             const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
             const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
             const int n_tiles = (int)((row_end - row_begin + TN - 1) / TN);
@@ -392,7 +407,8 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                 }
                             }
                         }
-                        ptx::umma_commit(&bars->b_empty[stage]);
+                        if (CL == 1) ptx::umma_commit(&bars->b_empty[stage]);
+                        else ptx::umma_commit_mcast(&bars->b_empty[stage], (uint16_t)0x3);   // frees the stage in both CTAs
                         if (kc + p.kps >= p.kchunks) {
                             ptx::umma_commit(&bars->acc_full[as]);
                             if (kc_sm > 0 && t == n_tiles - 1) ptx::umma_commit(&bars->ahi_empty);   // unit done with A_hi
@@ -413,9 +429,9 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int m = quad * 32 + lane;
         const int k = p.k;
         int it = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int slice = u / p.n_qblocks;
-            const int q0 = (u % p.n_qblocks) * TC_M;
+        for (int u = worker; u < n_units; u += n_workers) {
+            const int slice = u / qb_groups;
+            const int q0 = ((u % qb_groups) * CL + rank) * TC_M;
             const int64_t row_begin = (int64_t)slice * p.rows_per_slice;
             const int64_t row_end = min(p.n_rows, row_begin + p.rows_per_slice);
             const int n_tiles = (int)((row_end - row_begin + TN - 1) / TN);
@@ -541,6 +557,7 @@ dense_ts_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CL > 1) ptx::cluster_sync();     // no CTA leaves while its peer may still multicast into it / arrive on its barriers
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
@@ -646,9 +663,12 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     p.n_rows = n_rows;
     p.n_qblocks = (n_queries + TC_M - 1) / TC_M;
     const bool ts = variant >= 1;
+    const int cl = variant == 3 ? 2 : 1;                        // variant 3: TS128 in cluster pairs (multicast corpus tiles)
+    if (variant == 3) variant = 2;
     const int tn = variant == 2 ? 128 : TC_N;                   // corpus rows per tile (UMMA N)
     const int tmem_kc = variant == 2 ? 8 : TS_TMEM_KC;          // k-chunks of the query block in tensor memory
-    p.n_slices = ts ? ts_choose_splits(p.n_qblocks, n_rows, dim, sm_count(), tn) : tc_slices(n_rows);
+    const int qb_groups = (p.n_qblocks + cl - 1) / cl;          // work units per corpus split
+    p.n_slices = ts ? ts_choose_splits(qb_groups, n_rows, dim, sm_count() / cl, tn) : tc_slices(n_rows);
     p.rows_per_slice = tc_rows_per_slice(n_rows, p.n_slices, tn);
     // with the rounded-up slice size the last slices may be empty: shrink to the non-empty ones
     p.n_slices = (int)((n_rows + p.rows_per_slice - 1) / p.rows_per_slice);
@@ -690,26 +710,30 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     CUtensorMap map_q, map_c;
     int rc = encode_tmap_2d_bf16(&map_q, queries, (uint64_t)dim, (uint64_t)n_queries, (uint64_t)ldq, TC_KC, TC_M);
     if (rc) return rc;
-    rc = encode_tmap_2d_bf16(&map_c, corpus, (uint64_t)dim, (uint64_t)n_rows, (uint64_t)ldc, TC_KC, (uint32_t)tn);
+    rc = encode_tmap_2d_bf16(&map_c, corpus, (uint64_t)dim, (uint64_t)n_rows, (uint64_t)ldc, TC_KC, (uint32_t)(tn / cl));
     if (rc) return rc;
 
     const bool filter = (q_group != nullptr);
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const TcParams);
-    static const kern_t table[3][2][4] = {
+    static const kern_t table[4][2][4] = {
         {{dense_tc_kernel<false, 4>, dense_tc_kernel<false, 8>, dense_tc_kernel<false, 12>, dense_tc_kernel<false, 16>},
          {dense_tc_kernel<true, 4>, dense_tc_kernel<true, 8>, dense_tc_kernel<true, 12>, dense_tc_kernel<true, 16>}},
-        {{dense_ts_kernel<false, 4, 64>, dense_ts_kernel<false, 8, 64>, dense_ts_kernel<false, 12, 64>,
-          dense_ts_kernel<false, 16, 64>},
-         {dense_ts_kernel<true, 4, 64>, dense_ts_kernel<true, 8, 64>, dense_ts_kernel<true, 12, 64>,
-          dense_ts_kernel<true, 16, 64>}},
-        {{dense_ts_kernel<false, 4, 128>, dense_ts_kernel<false, 8, 128>, dense_ts_kernel<false, 12, 128>,
-          dense_ts_kernel<false, 16, 128>},
-         {dense_ts_kernel<true, 4, 128>, dense_ts_kernel<true, 8, 128>, dense_ts_kernel<true, 12, 128>,
-          dense_ts_kernel<true, 16, 128>}}};
+        {{dense_ts_kernel<false, 4, 64, 1>, dense_ts_kernel<false, 8, 64, 1>, dense_ts_kernel<false, 12, 64, 1>,
+          dense_ts_kernel<false, 16, 64, 1>},
+         {dense_ts_kernel<true, 4, 64, 1>, dense_ts_kernel<true, 8, 64, 1>, dense_ts_kernel<true, 12, 64, 1>,
+          dense_ts_kernel<true, 16, 64, 1>}},
+        {{dense_ts_kernel<false, 4, 128, 1>, dense_ts_kernel<false, 8, 128, 1>, dense_ts_kernel<false, 12, 128, 1>,
+          dense_ts_kernel<false, 16, 128, 1>},
+         {dense_ts_kernel<true, 4, 128, 1>, dense_ts_kernel<true, 8, 128, 1>, dense_ts_kernel<true, 12, 128, 1>,
+          dense_ts_kernel<true, 16, 128, 1>}},
+        {{dense_ts_kernel<false, 4, 128, 2>, dense_ts_kernel<false, 8, 128, 2>, dense_ts_kernel<false, 12, 128, 2>,
+          dense_ts_kernel<false, 16, 128, 2>},
+         {dense_ts_kernel<true, 4, 128, 2>, dense_ts_kernel<true, 8, 128, 2>, dense_ts_kernel<true, 12, 128, 2>,
+          dense_ts_kernel<true, 16, 128, 2>}}};
     const int kt = (k + 3) / 4 - 1;
-    const int vi = variant;
+    const int vi = cl == 2 ? 3 : variant;
     kern_t kern = table[vi][filter ? 1 : 0][kt];
-    static bool attr_done[3][2][4] = {};
+    static bool attr_done[4][2][4] = {};
     if (!attr_done[vi][filter ? 1 : 0][kt]) {
         EZR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
         // always configure the SM for the largest shared-memory carveout: with a capped ring the rest of the
@@ -719,12 +743,29 @@ int dense_tc_topk(const __nv_bfloat16* corpus, int64_t n_rows, int dim, int64_t 
     }
     dim3 grid(p.n_slices, p.n_qblocks);
     if (ts) {
-        const int units = p.n_slices * p.n_qblocks;
-        grid = dim3(units < sm_count() ? units : sm_count(), 1);
+        const int units = p.n_slices * qb_groups;
+        const int workers = units < sm_count() / cl ? units : sm_count() / cl;
+        grid = dim3(workers * cl, 1);
     }
     {
         ProfScope prof(EZR_PROF_DENSE_TC, st);
-        kern<<<grid, ts ? TS_THREADS : TC_THREADS, smem, st>>>(map_q, map_c, p);
+        if (cl == 1) {
+            kern<<<grid, ts ? TS_THREADS : TC_THREADS, smem, st>>>(map_q, map_c, p);
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid;
+            cfg.blockDim = dim3(TS_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            EZR_CUDA(cudaLaunchKernelEx(&cfg, kern, map_q, map_c, p));
+        }
     }
     EZR_LAUNCH_CHECK();
     const int n_cand = p.n_slices * k * lists;

@@ -7,6 +7,14 @@
 // cuBLAS calls behind the reference's projections: Qwen2 q/k/v/o and SwiGLU MLP (modeling_qwen.py:261-263,
 // 319,186) and the BERT-shaped encoder's dense layers behind SentenceTransformer.encode (hf_embeddings.py:118-123).
 //
+// The GEMMs of this encoder are L2 -> SM bandwidth bound, not tensor bound: a 128 x 256 tile pulls 48 KB of operands per
+// 64-wide k-chunk (87 FLOP / byte) and 148 SMs doing that need ~2x what the L2 delivers (measured: 0.42-0.45 of the
+// tensor peak whatever the epilogue).  So CTAs run in CLUSTER PAIRS on the same W tile (two M tiles, one N tile): each
+// CTA loads its own A tile and HALF of the W tile and TMA-multicasts that half into both CTAs' shared memory, 32 KB
+// instead of 48 KB from L2 per CTA and k-chunk (131 FLOP / byte).  The MMAs stay single-CTA (cta_group::1); only the
+// stage hand-over changes: a stage is free when BOTH CTAs' MMAs have released it (tcgen05.commit multicast to both
+// CTAs' empty barriers), because the peer's multicast writes into it.
+//
 // Persistent, warp-specialised: warp 0 = TMA producer (4-stage ring of 128x64 A and 256x64 W tiles),
 // warp 1 = tcgen05.mma issuer (128x256x16, fp32 accumulate into one of two 256-column TMEM stages; the 128x256
 // tile halves L2->SM operand traffic per flop versus 128x128, which measured L2-bound), warps 2-5 = epilogue (tcgen05.ld, one output row per thread, bias / GELU / SwiGLU / residual in
@@ -22,6 +30,7 @@ constexpr int G_ACC = 2;
 constexpr int G_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int G_A_BYTES = GM * GK * 2;   // 16 KB
 constexpr int G_B_BYTES = GN * GK * 2;   // 32 KB
+constexpr int G_CLUSTER = 2;             // CTAs sharing a W tile
 
 enum { EPI_NONE = 0, EPI_GELU = 1, EPI_SWIGLU = 2 };
 
@@ -73,7 +82,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int EPI>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const GemmParams p) {
+               const GemmParams p) {          // map_w: boxes of GN / 2 rows (one CTA's half of the W tile)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_a = smem;
@@ -82,19 +91,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     __shared__ float s_bias[8][GN];          // per epilogue warp: bias of its column half (x2 rows for SwiGLU)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = p.tiles_m * p.tiles_n;
+    // work = super-tiles of (two M tiles) x (one N tile), walked by cluster pairs; this CTA owns M tile 2 * sm + rank
+    const int rank = (int)ptx::cluster_ctarank();
+    const int pair = blockIdx.x / G_CLUSTER, n_pairs = gridDim.x / G_CLUSTER;
+    const int super_m = (p.tiles_m + 1) / 2;
+    const int n_tiles = super_m * p.tiles_n;
     const int kchunks = p.K / GK;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_w);
-        for (int i = 0; i < G_STAGES; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); }
+        for (int i = 0; i < G_STAGES; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], G_CLUSTER); }
         for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], 8); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc<G_ACC * GN>(&bars->tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();                 // the peer's barriers exist before anything is multicast into this CTA
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -102,16 +116,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int tm = t % p.tiles_m, tn = t / p.tiles_m;
+            for (int t = pair; t < n_tiles; t += n_pairs) {
+                const int tm = (t % super_m) * 2 + rank, tn = t / super_m;
                 for (int kc = 0; kc < kchunks; kc += p.kps) {
-                    ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+                    ptx::mbar_wait(&bars->empty[stage], phase ^ 1);          // released by BOTH CTAs of the pair
                     ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(p.kps * (G_A_BYTES + G_B_BYTES)));
                     for (int j = 0; j < p.kps; ++j) {
                         ptx::tma_load_2d(smem_a + (size_t)(stage * p.kps + j) * G_A_BYTES, &map_a, &bars->full[stage],
                                          (kc + j) * GK, tm * GM);
-                        ptx::tma_load_2d_hint(smem_b + (size_t)(stage * p.kps + j) * G_B_BYTES, &map_w,
-                                              &bars->full[stage], (kc + j) * GK, tn * GN, ptx::kEvictLast);
+                        // this CTA's half of the W tile, into both CTAs (rows [rank * 128, +128) of the 256-row tile)
+                        ptx::tma_load_2d_mcast(smem_b + (size_t)(stage * p.kps + j) * G_B_BYTES + (size_t)rank * (G_B_BYTES / 2),
+                                               &map_w, &bars->full[stage], (kc + j) * GK, tn * GN + rank * (GN / 2),
+                                               (uint16_t)0x3);
                     }
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
@@ -125,7 +141,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
             const int as = it % G_ACC;
             const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
             ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
@@ -144,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                              b_desc + (uint64_t)(j * (G_B_BYTES >> 4) + k4 * 2), idesc,
                                              (uint32_t)((kc | j | k4) != 0));
                     }
-                    ptx::umma_commit(&bars->empty[stage]);
+                    ptx::umma_commit_mcast(&bars->empty[stage], (uint16_t)0x3);   // frees the stage in both CTAs
                     if (kc + p.kps >= kchunks) ptx::umma_commit(&bars->acc_full[as]);
                 }
                 __syncwarp();
@@ -162,8 +178,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float* sb = s_bias[warp - 2];                                           // this warp's bias slice
         const int n_out = (EPI == EPI_SWIGLU) ? p.N / 2 : p.N;
         int it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const int tm = t % p.tiles_m, tn = t / p.tiles_m;
+        for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
+            const int tm = (t % super_m) * 2 + rank, tn = t / super_m;
             const int as = it % G_ACC;
             const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
             const int row = tm * GM + quad * 32 + lane;
@@ -276,6 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();                 // no CTA leaves while its peer may still multicast into it / arrive on its barriers
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<G_ACC * GN>(tmem_base);
@@ -301,7 +318,7 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     CUtensorMap map_a, map_w;
     int rc = encode_tmap_2d_bf16(&map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GK, GM);
     if (rc) return rc;
-    rc = encode_tmap_2d_bf16(&map_w, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GK, GN);
+    rc = encode_tmap_2d_bf16(&map_w, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GK, GN / G_CLUSTER);
     if (rc) return rc;
     const size_t smem = 1024 + (size_t)G_STAGES * (G_A_BYTES + G_B_BYTES) + sizeof(GemmBarriers) + 64;
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const GemmParams);
@@ -311,11 +328,24 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
         EZR_CUDA(cudaFuncSetAttribute(table[epi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[epi] = true;
     }
-    const int n_tiles = p.tiles_m * p.tiles_n;
-    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    const int n_super = ((p.tiles_m + 1) / 2) * p.tiles_n;           // (two M tiles) x (one N tile) per cluster pair
+    int pairs = sm_count() / G_CLUSTER;
+    if (n_super < pairs) pairs = n_super;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pairs * G_CLUSTER));
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     {
         ProfScope prof(EZR_PROF_ENC_GEMM, st);
-        table[epi]<<<grid, G_THREADS, smem, st>>>(map_a, map_w, p);
+        EZR_CUDA(cudaLaunchKernelEx(&cfg, table[epi], map_a, map_w, p));
     }
     EZR_LAUNCH_CHECK();
     return EZR_OK;

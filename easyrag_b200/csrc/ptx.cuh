@@ -82,6 +82,17 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* map
           "l"(policy)
         : "memory");
 }
+// 2-D tile load MULTICAST to the CTAs of the cluster named in cta_mask: the tile lands at the same shared-memory
+// offset in every destination CTA and completes on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1,
+                                                  uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0),
+          "r"(c1)
+        : "memory");
+}
 // 2-D tile store (smem -> global), bulk-group completion
 __device__ __forceinline__ void tma_store_2d(const void* map, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -139,6 +150,22 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+// same, arriving on the mbarrier at this offset in EVERY CTA of the cluster named in cta_mask (a shared-memory stage
+// that peer CTAs fill by TMA multicast is free only when every consumer has released it)
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // K-major operand tile in shared memory, 128-byte swizzle (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B).

@@ -198,10 +198,12 @@ int ezr_normalize_rows(const void* x, int32_t x_is_f32, int64_t ldx, int64_t n_r
                        int64_t ldo, void* stream);
 /* 0 = pick automatically, 1 = force the generic SIMT kernel, 2 = force tcgen05 with the query block in shared
  * memory (SS), 3 = force tcgen05 with the query block in tensor memory (TS) and 64-row corpus tiles, 4 = TS with
- * 128-row corpus tiles (the automatic choice); 2/3/4 error if the shape is unsupported */
+ * 128-row corpus tiles (the automatic choice), 5 = 4 run in cluster pairs (two neighbouring query blocks on the same
+ * corpus split; each CTA loads half of every corpus tile and TMA-multicasts it to both); 2-5 error if the shape is
+ * unsupported */
 int ezr_dense_set_kernel(int32_t which);
 /* name of the kernel the last ezr_dense_topk call on this thread launched
- * ("tcgen05" / "tcgen05-ts" / "tcgen05-ts128" / "simt") */
+ * ("tcgen05" / "tcgen05-ts" / "tcgen05-ts128" / "tcgen05-ts128-mc2" / "simt") */
 const char* ezr_dense_last_kernel(void);
 
 /* Cap the TMA ring of the tcgen05 kernels at `stages` stages (0 = use all shared memory, the default).  A capped

@@ -382,8 +382,9 @@ def _check_dense(res, c, qv, k, allowed=None, exact=False, id_base=0):
             assert m[got].all()
 
 
-# 1 = generic SIMT, 2 = tcgen05 (queries in smem), 3 = tcgen05 (queries in TMEM, 64-row tiles), 4 = same, 128-row tiles
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
+# 1 = generic SIMT, 2 = tcgen05 (queries in smem), 3 = tcgen05 (queries in TMEM, 64-row tiles), 4 = same, 128-row tiles,
+# 5 = 4 in cluster pairs (each CTA loads half of every corpus tile and TMA-multicasts it to both)
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("n,d,q,k", [(5000, 128, 130, 10), (777, 768, 3, 5), (64, 64, 1, 16), (20_000, 768, 257, 10),
                                      (100, 256, 5, 12)])
 def test_dense_exact_integer_inputs(kernel, n, d, q, k):
@@ -392,10 +393,23 @@ def test_dense_exact_integer_inputs(kernel, n, d, q, k):
     _lib.check(L.ezr_dense_set_kernel(kernel))
     try:
         res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), k)
-        assert L.ezr_dense_last_kernel() == {1: b"simt", 2: b"tcgen05", 3: b"tcgen05-ts", 4: b"tcgen05-ts128"}[kernel]
+        assert L.ezr_dense_last_kernel() == {1: b"simt", 2: b"tcgen05", 3: b"tcgen05-ts", 4: b"tcgen05-ts128",
+                                             5: b"tcgen05-ts128-mc2"}[kernel]
     finally:
         L.ezr_dense_set_kernel(0)
     _check_dense(res, c, qv, k, exact=True)
+
+
+def test_dense_wide_dims_cluster_pair_kernel():
+    c, qv = _dense_case(70_000, 1024, 300, 270, integer=True)      # odd number of query blocks (3), 1024-d, several splits
+    L = _lib.lib()
+    _lib.check(L.ezr_dense_set_kernel(5))
+    try:
+        res = batched.dense_topk(DenseIndex(c, device=DEV), qv.to(DEV), 10)
+        assert L.ezr_dense_last_kernel() == b"tcgen05-ts128-mc2"
+    finally:
+        L.ezr_dense_set_kernel(0)
+    _check_dense(res, c, qv, 10, exact=True)
 
 
 @pytest.mark.parametrize("n,d,q,k", [(3000, 1024, 130, 10), (2500, 832, 5, 8), (70_000, 1024, 300, 10)])
@@ -422,7 +436,7 @@ def test_dense_wide_dims_use_hybrid_tmem_smem_queries(n, d, q, k):
         L.ezr_dense_set_kernel(0)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
 def test_dense_unit_vectors_within_tolerance(kernel):
     c, qv = _dense_case(30_000, 768, 200, 7)
     L = _lib.lib()
@@ -434,7 +448,7 @@ def test_dense_unit_vectors_within_tolerance(kernel):
     _check_dense(res, c, qv, 10)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
 def test_dense_dir_filter_and_id_base(kernel):
     c, qv = _dense_case(9000, 256, 70, 11, integer=True)
     groups = synth.make_groups(9000, 4, 12)
