@@ -5,20 +5,25 @@
 // (hf_embeddings.py:118-123).  Sequences are packed, so the mask reduces to "keys beyond this sequence".
 //
 // Work item = 128 query rows of one (sequence, head).  A small plan kernel lists the (sequence, query block) pairs
-// that exist; PERSISTENT CTAs (two per SM: 256 TMEM columns and <= 96 KB of shared memory each, so one CTA's softmax
-// overlaps the other's MMAs) walk the items round-robin, query blocks of one (sequence, head) next to each other so
-// that concurrently running CTAs share its K / V tiles through L2.  Barriers, tensor memory and the tensor-map
-// prefetch are set up once per CTA, and the TMA producer runs ahead into the next item.
-//   warp 0      TMA producer: Q tile per item, K / V tiles of 128 keys (one 2-D tensor map over the packed
-//               [tokens, (H + 2 KV) hd] matrix serves Q, K and V; 128B swizzle; rows past the matrix are zero-filled)
+// that exist; PERSISTENT CTAs (two per SM: 256 TMEM columns and <= 96 KB of shared memory each) walk the items
+// round-robin, query blocks of one (sequence, head) next to each other so that concurrently running CTAs share its
+// K / V tiles through L2.  Barriers, tensor memory and the tensor-map prefetch are set up once per CTA, and the TMA
+// producer runs ahead into the next item.
+//   warp 0      TMA producer: Q tile per item, K / V tiles of 64 keys (one packed [tokens, (H + 2 KV) hd] matrix serves
+//               Q, K and V through two tensor maps -- 128-row and 64-row boxes; 128B swizzle; rows past the matrix are
+//               zero-filled)
 //   warp 1      tcgen05.mma issuer:  S = Q K^T   (SS form, both operands K-major in shared memory, N = keys of the tile)
 //                                    O += P V    (TS form: P is read from TENSOR MEMORY, V is the MN-major B operand
 //                                                 straight from its row-major TMA tile -- no transpose anywhere)
-//   warps 2-9   softmax: two warps per TMEM lane quadrant, a thread owns one query row and 64 of the 128 key columns,
-//               read ONCE from tensor memory into registers: row max (pair exchange through shared memory), exp2 with
-//               the 1/sqrt(d) scale folded in, probabilities written back as packed bf16 over the S columns they came
-//               from (tcgen05.st), running sum in fp32; at the end of an item O / sum -> bf16 -> global.
-// TMEM columns: [0,128) S (fp32) aliased by P (bf16 pairs: keys 0-63 -> columns 0-31, keys 64-127 -> columns 64-95),
+//               S is DOUBLE BUFFERED: S_{j+1} = Q K_{j+1}^T is issued before the probabilities of tile j are waited for,
+//               so the softmax warps never wait for a QK^T and the tensor pipe works under the softmax.
+//   warps 2-5   softmax: one warp per TMEM lane quadrant, a thread owns one query row and all 64 key columns of a
+//               tile, read ONCE from tensor memory into registers: row max, exp2 with the 1/sqrt(d) scale folded in,
+//               probabilities written back as packed bf16 over the S columns they came from (tcgen05.st), running sum
+//               in fp32; at the end of an item O / sum -> bf16 -> global.  No cross-warp exchange anywhere.
+// The kernel is bound by the softmax arithmetic (one MUFU.EX2 per score: 16 per clock and SM), not by the tensor
+// pipe: ncu, profiles/README.md round 2.
+// TMEM columns: [0,64) / [64,128) the two S buffers (fp32), each aliased by its P (bf16 pairs, 32 columns),
 // [128, 128+hd) O.  The running maximum is lazy: O is rescaled in tensor memory (tcgen05.ld / multiply / tcgen05.st)
 // only when a row's maximum grows by more than 2^8; otherwise the stale maximum stays (p <= 256 is harmless in
 // bf16 / fp32) -- the final division by the row sum makes both choices the same function.
@@ -28,9 +33,10 @@
 namespace ezr {
 
 constexpr int AT_M = 128;                 // query rows per work item (UMMA M, one TMEM lane each)
-constexpr int AT_N = 128;                 // keys per tile (UMMA N of S = Q K^T)
-constexpr int AT_THREADS = 320;           // TMA warp, MMA warp, 8 softmax warps
-constexpr int AT_BOX_BYTES = 128 * 64 * 2;   // one TMA box: 128 rows x 64 bf16
+constexpr int AT_N = 64;                  // keys per tile (UMMA N of S = Q K^T)
+constexpr int AT_THREADS = 192;           // TMA warp, MMA warp, 4 softmax warps
+constexpr int AT_BOX_BYTES = 128 * 64 * 2;   // one Q TMA box: 128 rows x 64 bf16
+constexpr int AT_KV_BOX_BYTES = AT_N * 64 * 2;   // one K / V TMA box: 64 rows x 64 bf16
 constexpr int AT_TMEM_COLS = 256;
 constexpr int AT_O_COL = 128;
 constexpr float AT_RESCALE_LOG2 = 8.0f;   // rescale O only when the row maximum grows by more than 2^8
@@ -38,7 +44,7 @@ constexpr float AT_RESCALE_LOG2 = 8.0f;   // rescale O only when the row maximum
 struct AttnBarriers {
     uint64_t q_full, q_empty;
     uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-    uint64_t s_full, p_full, o_full;
+    uint64_t s_full[2], p_full[2], o_full;
     uint32_t tmem_base;
 };
 
@@ -81,22 +87,19 @@ attn_plan_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict_
 
 template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restrict__ cu, const int32_t* __restrict__ plan,
-               const int32_t* __restrict__ plan_n, int n_heads, int n_kv_heads, float scale_log2,
-               __nv_bfloat16* __restrict__ out, int64_t ldo) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+               const int32_t* __restrict__ cu, const int32_t* __restrict__ plan, const int32_t* __restrict__ plan_n,
+               int n_heads, int n_kv_heads, float scale_log2, __nv_bfloat16* __restrict__ out, int64_t ldo) {
     constexpr int CH = HD / 64;                          // 64-column TMA boxes per tile
-    constexpr int TILE_BYTES = CH * AT_BOX_BYTES;        // one Q / K / V tile
-    constexpr int STAGES = HD == 64 ? 2 : 1;             // K/V ring depth (K and V have their own barriers)
+    constexpr int Q_BYTES = CH * AT_BOX_BYTES;           // the Q tile
+    constexpr int KV_BYTES = CH * AT_KV_BOX_BYTES;       // one K / V tile
+    constexpr int STAGES = 2;                            // K and V rings (own barriers each)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_q = smem;
-    unsigned char* smem_k = smem_q + TILE_BYTES;
-    unsigned char* smem_v = smem_k + STAGES * TILE_BYTES;
-    AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_v + STAGES * TILE_BYTES);
-    __shared__ float s_xch[2][AT_M];                     // pair exchange of the row maxima (every tile)
-    __shared__ float s_sum[2][AT_M];                     // ... and of the row sums (once per item): separate slots, so a
-                                                         // warp that runs ahead into the next item cannot overwrite what
-                                                         // its partner has not read yet
+    unsigned char* smem_k = smem_q + Q_BYTES;
+    unsigned char* smem_v = smem_k + STAGES * KV_BYTES;
+    AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_v + STAGES * KV_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pairs = plan_n[0];
@@ -104,7 +107,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
     const int kv_group = n_heads / n_kv_heads;
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&map);
+        ptx::prefetch_tensormap(&map_q);
+        ptx::prefetch_tensormap(&map_kv);
         ptx::mbar_init(&bars->q_full, 1);
         ptx::mbar_init(&bars->q_empty, 1);
         for (int i = 0; i < 2; ++i) {
@@ -112,9 +116,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
             ptx::mbar_init(&bars->k_empty[i], 1);
             ptx::mbar_init(&bars->v_full[i], 1);
             ptx::mbar_init(&bars->v_empty[i], 1);
+            ptx::mbar_init(&bars->s_full[i], 1);
+            ptx::mbar_init(&bars->p_full[i], 4);
         }
-        ptx::mbar_init(&bars->s_full, 1);
-        ptx::mbar_init(&bars->p_full, 8);
         ptx::mbar_init(&bars->o_full, 1);
         ptx::fence_barrier_init();
     }
@@ -137,21 +141,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
                 const int col_q = h * HD, col_k = (n_heads + kvh) * HD, col_v = (n_heads + n_kv_heads + kvh) * HD;
                 const int n_kt = (len + AT_N - 1) / AT_N;
                 ptx::mbar_wait(&bars->q_empty, ((uint32_t)it & 1u) ^ 1u);      // the previous item's QK^T MMAs are done
-                ptx::mbar_expect_tx(&bars->q_full, TILE_BYTES);
+                ptx::mbar_expect_tx(&bars->q_full, Q_BYTES);
                 for (int c = 0; c < CH; ++c)
-                    ptx::tma_load_2d(smem_q + c * AT_BOX_BYTES, &map, &bars->q_full, col_q + c * 64, lo + q0);
+                    ptx::tma_load_2d(smem_q + c * AT_BOX_BYTES, &map_q, &bars->q_full, col_q + c * 64, lo + q0);
                 for (int j = 0; j < n_kt; ++j, ++jt) {
                     const int s = jt % STAGES;
                     const uint32_t ph = (uint32_t)(jt / STAGES) & 1u;
                     const int row = lo + j * AT_N;
                     ptx::mbar_wait(&bars->k_empty[s], ph ^ 1);
-                    ptx::mbar_expect_tx(&bars->k_full[s], TILE_BYTES);
+                    ptx::mbar_expect_tx(&bars->k_full[s], KV_BYTES);
                     for (int c = 0; c < CH; ++c)
-                        ptx::tma_load_2d(smem_k + s * TILE_BYTES + c * AT_BOX_BYTES, &map, &bars->k_full[s], col_k + c * 64, row);
+                        ptx::tma_load_2d(smem_k + s * KV_BYTES + c * AT_KV_BOX_BYTES, &map_kv, &bars->k_full[s], col_k + c * 64, row);
                     ptx::mbar_wait(&bars->v_empty[s], ph ^ 1);
-                    ptx::mbar_expect_tx(&bars->v_full[s], TILE_BYTES);
+                    ptx::mbar_expect_tx(&bars->v_full[s], KV_BYTES);
                     for (int c = 0; c < CH; ++c)
-                        ptx::tma_load_2d(smem_v + s * TILE_BYTES + c * AT_BOX_BYTES, &map, &bars->v_full[s], col_v + c * 64, row);
+                        ptx::tma_load_2d(smem_v + s * KV_BYTES + c * AT_KV_BOX_BYTES, &map_kv, &bars->v_full[s], col_v + c * 64, row);
                 }
             }
         }
@@ -159,7 +163,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
         // ---------------- MMA issuer (warp-uniform loops, one elected lane issues) ----------------
         constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(AT_M, HD) | ptx::kIdescBMajorMN;
         const uint32_t q_addr = ptx::smem_u32(smem_q);
-        const uint32_t tm_s = tmem_base, tm_o = tmem_base + AT_O_COL;
+        const uint32_t tm_o = tmem_base + AT_O_COL;
+        // S_j = Q K_j^T into S buffer (jt & 1); jt counts this CTA's tiles across items
+        auto issue_qk = [&](int jt, int valid, bool last) {
+            const int s = jt % STAGES;
+            const uint32_t ph = (uint32_t)(jt / STAGES) & 1u;
+            const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);         // keys of this tile, multiple of 16
+            const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_BYTES);
+            ptx::mbar_wait(&bars->k_full[s], ph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t idesc_qk = ptx::make_idesc_bf16(AT_M, n_j);
+                const uint32_t tm_s = tmem_base + (uint32_t)((jt & 1) * AT_N);
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk) {
+                    const uint32_t qoff = (uint32_t)((kk >> 2) * AT_BOX_BYTES + (kk & 3) * 32);
+                    const uint32_t koff = (uint32_t)((kk >> 2) * AT_KV_BOX_BYTES + (kk & 3) * 32);
+                    ptx::umma_f16_ss(tm_s, ptx::make_desc_sw128(q_addr + qoff), ptx::make_desc_sw128(k_addr + koff),
+                                     idesc_qk, (uint32_t)(kk != 0));
+                }
+                ptx::umma_commit(&bars->k_empty[s]);
+                if (last) ptx::umma_commit(&bars->q_empty);                      // the Q tile may be overwritten
+                ptx::umma_commit(&bars->s_full[jt & 1]);
+            }
+            __syncwarp();
+        };
         int jt = 0, it = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
             const int pe = plan[w % n_pairs];
@@ -167,37 +195,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
             const int len = cu[b + 1] - cu[b];
             const int n_kt = (len + AT_N - 1) / AT_N;
             ptx::mbar_wait(&bars->q_full, (uint32_t)it & 1u);
+            issue_qk(jt, len, n_kt == 1);
             for (int j = 0; j < n_kt; ++j, ++jt) {
+                // the next tile's scores first: they do not depend on this tile's softmax (other S buffer)
+                if (j + 1 < n_kt) issue_qk(jt + 1, len - (j + 1) * AT_N, j + 2 == n_kt);
                 const int s = jt % STAGES;
                 const uint32_t ph = (uint32_t)(jt / STAGES) & 1u;
                 const int valid = len - j * AT_N;
-                const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);     // keys of this tile, multiple of 16
-                const uint32_t k_addr = ptx::smem_u32(smem_k + s * TILE_BYTES);
-                const uint32_t v_addr = ptx::smem_u32(smem_v + s * TILE_BYTES);
-                ptx::mbar_wait(&bars->k_full[s], ph);
-                ptx::tc_fence_after();
-                if (ptx::elect_one()) {
-                    const uint32_t idesc_qk = ptx::make_idesc_bf16(AT_M, n_j);
-#pragma unroll
-                    for (int kk = 0; kk < HD / 16; ++kk) {
-                        const uint32_t off = (uint32_t)((kk >> 2) * AT_BOX_BYTES + (kk & 3) * 32);
-                        ptx::umma_f16_ss(tm_s, ptx::make_desc_sw128(q_addr + off), ptx::make_desc_sw128(k_addr + off),
-                                         idesc_qk, (uint32_t)(kk != 0));
-                    }
-                    ptx::umma_commit(&bars->k_empty[s]);
-                    if (j == n_kt - 1) ptx::umma_commit(&bars->q_empty);          // the Q tile may be overwritten
-                    ptx::umma_commit(&bars->s_full);
-                }
-                __syncwarp();
-                ptx::mbar_wait(&bars->p_full, (uint32_t)jt & 1u);                 // probabilities are in tensor memory
+                const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);
+                const uint32_t v_addr = ptx::smem_u32(smem_v + s * KV_BYTES);
+                ptx::mbar_wait(&bars->p_full[jt & 1], (uint32_t)(jt >> 1) & 1u);   // probabilities are in tensor memory
                 ptx::mbar_wait(&bars->v_full[s], ph);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    for (int i = 0; i < n_j / 16; ++i) {
-                        const uint32_t a_tmem = tm_s + (uint32_t)(i < 4 ? 8 * i : 64 + 8 * (i - 4));
-                        ptx::umma_f16_ts(tm_o, a_tmem, ptx::make_desc_sw128_mn(v_addr + (uint32_t)i * 2048u, AT_BOX_BYTES),
-                                         idesc_pv, (uint32_t)((j | i) != 0));
-                    }
+                    const uint32_t tm_p = tmem_base + (uint32_t)((jt & 1) * AT_N);
+                    for (int i = 0; i < n_j / 16; ++i)
+                        ptx::umma_f16_ts(tm_o, tm_p + (uint32_t)(8 * i),
+                                         ptx::make_desc_sw128_mn(v_addr + (uint32_t)i * 2048u, AT_KV_BOX_BYTES), idesc_pv,
+                                         (uint32_t)((j | i) != 0));
                     ptx::umma_commit(&bars->v_empty[s]);
                     if (j == n_kt - 1) ptx::umma_commit(&bars->o_full);
                 }
@@ -205,82 +220,70 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
             }
         }
     } else {
-        // ---------------- softmax + epilogue: 8 warps, two per TMEM lane quadrant ----------------
+        // ---------------- softmax + epilogue: 4 warps, one per TMEM lane quadrant ----------------
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;                      // key columns [64 half, 64 half + 64) of every tile
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint32_t s_col = (uint32_t)(half * 64);
-        const uint32_t o_col = (uint32_t)(AT_O_COL + half * (HD / 2));
+        const uint32_t o_col = (uint32_t)AT_O_COL;
         int jt = 0, it = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
             const int h = w / n_pairs, pe = plan[w % n_pairs];
             const int b = pe >> 8, q0 = (pe & 0xff) * AT_M;
             const int lo = cu[b], len = cu[b + 1] - lo;
             const int n_kt = (len + AT_N - 1) / AT_N;
-            float m_run = -INFINITY, l_part = 0.f;
+            float m_run = -INFINITY, l_run = 0.f;
             for (int j = 0; j < n_kt; ++j, ++jt) {
                 const int valid = len - j * AT_N;
-                const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);
-                const bool two = (int)s_col + 32 < n_j;            // this warp's second 32-column chunk exists
-                const bool any = (int)s_col < n_j;                 // ... its first one (warp-uniform)
-                ptx::mbar_wait(&bars->s_full, (uint32_t)jt & 1u);  // also: every earlier O += P V has retired
+                const uint32_t s_addr = lane_addr + (uint32_t)((jt & 1) * AT_N);
+                ptx::mbar_wait(&bars->s_full[jt & 1], (uint32_t)(jt >> 1) & 1u);   // also: every earlier O += P V retired
                 ptx::tc_fence_after();
-                // the warp's 64 S values, read once (columns past n_j hold stale data: masked below, never used)
+                // the row's 64 scores, read once (columns past the tile's keys hold stale data: masked, never used)
                 uint32_t r0[32], r1[32];
-                ptx::tmem_ld_32x32(lane_addr + s_col, r0);
-                ptx::tmem_ld_32x32(lane_addr + s_col + 32, r1);
+                ptx::tmem_ld_32x32(s_addr, r0);
+                ptx::tmem_ld_32x32(s_addr + 32, r1);
                 ptx::tmem_ld_wait();
-                float mx = -INFINITY;
                 if (valid < AT_N) {                                // last tile of the sequence: mask the keys past it
-                    const int lim = valid - (int)s_col;            // columns of this warp's slice that are real keys
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        r0[i] = i < lim ? r0[i] : 0xff800000u;     // -inf: exp2 gives 0
-                        r1[i] = 32 + i < lim ? r1[i] : 0xff800000u;
+                        r0[i] = i < valid ? r0[i] : 0xff800000u;   // -inf: exp2 gives 0
+                        r1[i] = 32 + i < valid ? r1[i] : 0xff800000u;
                     }
                 }
+                float mx = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-                s_xch[half][row] = mx;
-                ptx::named_bar_sync(1 + quad, 64);
-                mx = fmaxf(mx, s_xch[half ^ 1][row]);
                 float m_new = fmaxf(m_run, mx);
                 const bool grow = (m_new - m_run) * scale_log2 > AT_RESCALE_LOG2;   // true on the first tile (m_run = -inf)
                 if (!grow) m_new = m_run;
                 const float alpha = ex2_approx((m_run - m_new) * scale_log2);       // 1 when the maximum is kept
                 const bool rescale = j > 0 && __any_sync(0xffffffffu, grow);
-                l_part *= alpha;
+                l_run *= alpha;
                 m_run = m_new;
                 const float mb = m_new * scale_log2;
-                if (any) {
-                    uint32_t pk[16];
+                // probabilities, packed in place: pair (2i, 2i+1) -> 32-bit column i (reads run ahead of the writes)
+                float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(r0[i]), scale_log2, -mb));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(r0[i + 1]), scale_log2, -mb));
-                        l_part += p0 + p1;
-                        __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&v);
-                    }
-                    ptx::tmem_st_32x16(lane_addr + s_col, pk);
+                for (int i = 0; i < 16; ++i) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * i]), scale_log2, -mb));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * i + 1]), scale_log2, -mb));
+                    l0 += p0; l1 += p1;
+                    __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
+                    r0[i] = *reinterpret_cast<uint32_t*>(&v);
                 }
-                if (two) {
-                    uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(r1[i]), scale_log2, -mb));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(r1[i + 1]), scale_log2, -mb));
-                        l_part += p0 + p1;
-                        __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&v);
-                    }
-                    ptx::tmem_st_32x16(lane_addr + s_col + 16, pk);
+                for (int i = 0; i < 16; ++i) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(r1[2 * i]), scale_log2, -mb));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(r1[2 * i + 1]), scale_log2, -mb));
+                    l0 += p0; l1 += p1;
+                    __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
+                    r0[16 + i] = *reinterpret_cast<uint32_t*>(&v);
                 }
+                l_run += l0 + l1;
+                ptx::tmem_st_32x32(s_addr, r0);                    // P over the first 32 columns of this S buffer
                 if (rescale) {
-                    // rare: bring this warp's half of the O columns to the new maximum (after the S registers are dead)
+                    // rare: bring the O columns to the new maximum (after the S registers are dead)
 #pragma unroll
-                    for (int c = 0; c < HD / 64; ++c) {
+                    for (int c = 0; c < HD / 32; ++c) {
                         uint32_t r[32];
                         ptx::tmem_ld_32x32(lane_addr + o_col + c * 32, r);
                         ptx::tmem_ld_wait();
@@ -292,18 +295,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&bars->p_full);
+                if (lane == 0) ptx::mbar_arrive(&bars->p_full[jt & 1]);
             }
             // epilogue of the item: O / row sum -> bf16 -> global
-            s_sum[half][row] = l_part;
-            ptx::named_bar_sync(1 + quad, 64);
-            const float inv = 1.0f / (l_part + s_sum[half ^ 1][row]);
+            const float inv = 1.0f / l_run;
             ptx::mbar_wait(&bars->o_full, (uint32_t)it & 1u);
             ptx::tc_fence_after();
             const bool row_ok = q0 + row < len;
-            __nv_bfloat16* orow = out + (int64_t)(lo + q0 + row) * ldo + h * HD + half * (HD / 2);
+            __nv_bfloat16* orow = out + (int64_t)(lo + q0 + row) * ldo + h * HD;
 #pragma unroll
-            for (int c = 0; c < HD / 64; ++c) {
+            for (int c = 0; c < HD / 32; ++c) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(lane_addr + o_col + c * 32, r);
                 ptx::tmem_ld_wait();
@@ -324,8 +325,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map, const int32_t* __restric
                     }
                 }
             }
-            // this warp's O columns are rewritten by the next item's first O = P V, which is issued only after this
-            // warp's next p_full arrival
+            // the O columns are rewritten by the next item's first O = P V, which is issued only after this warp's
+            // next p_full arrival
             ptx::tc_fence_before();
         }
     }
@@ -351,10 +352,9 @@ static thread_local size_t g_plan_cap = 0;
 static thread_local int g_plan_dev = -1;
 
 template <int HD>
-static int attn_tc_launch(const CUtensorMap& map, const int32_t* cu, int n_seq, int max_len, int n_heads, int n_kv_heads,
-                          float scale_log2, __nv_bfloat16* out, int64_t ldo, cudaStream_t st) {
-    constexpr int stages = HD == 64 ? 2 : 1;
-    const size_t smem = 1024 + (size_t)(1 + 2 * stages) * (HD / 64) * AT_BOX_BYTES + sizeof(AttnBarriers) + 64;
+static int attn_tc_launch(const CUtensorMap& map_q, const CUtensorMap& map_kv, const int32_t* cu, int n_seq, int max_len,
+                          int n_heads, int n_kv_heads, float scale_log2, __nv_bfloat16* out, int64_t ldo, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)(HD / 64) * (AT_BOX_BYTES + 4 * AT_KV_BOX_BYTES) + sizeof(AttnBarriers) + 64;
     static bool attr_done = false;
     if (!attr_done) {
         EZR_CUDA(cudaFuncSetAttribute(attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -382,7 +382,8 @@ static int attn_tc_launch(const CUtensorMap& map, const int32_t* cu, int n_seq, 
     EZR_LAUNCH_CHECK();
     const long long upper = (long long)n_seq * max_qb * n_heads;      // work items at most
     const int grid = (int)(upper < 2ll * sm_count() ? upper : 2ll * sm_count());
-    attn_tc_kernel<HD><<<grid, AT_THREADS, smem, st>>>(map, cu, plan, plan_n, n_heads, n_kv_heads, scale_log2, out, ldo);
+    attn_tc_kernel<HD><<<grid, AT_THREADS, smem, st>>>(map_q, map_kv, cu, plan, plan_n, n_heads, n_kv_heads, scale_log2, out,
+                                                       ldo);
     EZR_LAUNCH_CHECK();
     return EZR_OK;
 }
@@ -417,13 +418,15 @@ extern "C" int ezr_attn_bidir(const void* qkv, int64_t n_tokens, int64_t ld, con
                                  ldo, st);
     }
     g_attn_last = "tcgen05";
-    CUtensorMap map;
-    int rc = encode_tmap_2d_bf16(&map, qkv, (uint64_t)(n_heads + 2 * n_kv_heads) * head_dim, (uint64_t)n_tokens,
-                                 (uint64_t)ld, 64, 128);
+    CUtensorMap map_q, map_kv;
+    const uint64_t width = (uint64_t)(n_heads + 2 * n_kv_heads) * head_dim;
+    int rc = encode_tmap_2d_bf16(&map_q, qkv, width, (uint64_t)n_tokens, (uint64_t)ld, 64, AT_M);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&map_kv, qkv, width, (uint64_t)n_tokens, (uint64_t)ld, 64, AT_N);
     if (rc) return rc;
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    return head_dim == 64 ? attn_tc_launch<64>(map, cu_seqlens, n_seq, max_len, n_heads, n_kv_heads, scale_log2,
-                                               (__nv_bfloat16*)out, ldo, st)
-                          : attn_tc_launch<128>(map, cu_seqlens, n_seq, max_len, n_heads, n_kv_heads, scale_log2,
-                                                (__nv_bfloat16*)out, ldo, st);
+    return head_dim == 64 ? attn_tc_launch<64>(map_q, map_kv, cu_seqlens, n_seq, max_len, n_heads, n_kv_heads,
+                                               scale_log2, (__nv_bfloat16*)out, ldo, st)
+                          : attn_tc_launch<128>(map_q, map_kv, cu_seqlens, n_seq, max_len, n_heads, n_kv_heads,
+                                                scale_log2, (__nv_bfloat16*)out, ldo, st);
 }
