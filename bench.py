@@ -635,9 +635,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": n_warm, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16 dense / f64 bm25", "data": "synthetic",
-        "config": {"workload": f"configs[2]: dense+BM25 dual-route + RRF top-{k}, {args.rows} x {args.dim} chunks, "
-                               f"{args.queries} queries/step"
-                               + (f", row-sharded over {world} GPUs (configs[3])" if world > 1 else ""),
+        "config": {"workload": (f"configs[4] shape: {args.rows} x {args.dim} chunks (BGE-large width) + BM25 + RRF top-{k}, "
+                                f"batch-{args.queries} queries"
+                                if args.rows >= 4_000_000 and args.dim == 1024 else
+                                f"configs[2]: dense+BM25 dual-route + RRF top-{k}, {args.rows} x {args.dim} chunks, "
+                                f"{args.queries} queries/step")
+                               + (f", row-sharded over {world} GPUs" + (" (configs[3])" if args.rows < 4_000_000 else "")
+                                  if world > 1 else ""),
                    "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "queries_per_step": args.queries,
                    "k": k, "rrf_K": 60, "tokens": data["n_tokens"], "postings_local": postings_local,
                    "queries_per_corpus_pass": min(args.queries, 128), "routes_overlapped": overlap,

@@ -27,11 +27,11 @@
 // bound B exists, bm25_bound_kernel marks as NON-ESSENTIAL the tokens with the smallest gm whose sum NE stays
 // below kPkNeNum/kPkNeDen of B - 1.  The candidate pass does not read their postings at all: with
 // Q = Q_ess + Q_ne and Q_ne <= NE, a document with Q >= B - 1 has Q_ess >= B - 1 - NE, so that becomes the
-// crossing threshold.  Candidates then carry L = Q_ess (a lower bound of Q: still valid for raising B) and
-// U = L + NE (an upper bound: what pruning must use).  The high-df terms have the smallest weights and the
-// longest lists; phase 2 looks every token up anyway, so exactness is untouched.  Measured (profiles/r02i_*): the
-// candidate pass gets 14% faster but candidates multiply (their partial lower bounds tighten B more slowly) and the
-// rescoring eats the gain several times over, so ezr_bm25_set_skipping is OFF by default.
+// crossing threshold.  The high-df terms have the smallest weights and the longest lists.  Round 1 pushed those
+// relaxed crossers as candidates with partial bounds (L = Q_ess, U = L + NE): the candidate pass got 14% faster but
+// candidates multiplied and the rescoring ate the gain (profiles/r02i_*).  Round 2 COMPLETES the relaxed crossers
+// inside the candidate kernel (binary search of each skipped token's postings for just those documents) and then
+// applies the exact test, so the candidate set and the bounds are those of a full pass (L = U = Q).
 #pragma once
 #include <type_traits>
 
@@ -173,7 +173,7 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     // segments (three dependent loads each) and leaves them in shared memory, while the other warps clear the
     // accumulators; every warp then picks its lane's segment up with three shared-memory loads.  (Done by all eight
     // warps redundantly this was ~45% of the instructions of an average CTA: profiles/README.md, round 2.)
-    __shared__ int s_beg[32], s_len[32], s_ne;
+    __shared__ int s_beg[32], s_len[32], s_ne, s_nm;
     if (warp == kPkWarps - 1) {
         int b0 = 0;
         if (lane == 0) b0 = *reinterpret_cast<const volatile int32_t*>(c.thr_q + q);
@@ -190,6 +190,7 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
             s_b = b0;
             s_cnt = 0;
             s_ne = nm ? __ldg(c.ne_sum + q) : 0;
+            s_nm = (int)nm;
         }
     }
     {
@@ -345,14 +346,43 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
         if (tid == 0) c.ovf[q] = 1;
         return;
     }
+    // Skipped (non-essential) tokens: the documents above crossed the RELAXED threshold B - 1 - NE on their essential
+    // tokens alone.  Complete their sums here -- one thread per (document, skipped token) binary-searches the token's
+    // packed postings of this range -- so that the test below is the exact one (Q >= B - 1) and the candidates carry
+    // their full integer score: the candidate set and the bound updates are then exactly those of a pass that read
+    // every posting, and only the handful of near-candidates pays for the long lists.
+    const uint32_t nm = (uint32_t)s_nm;
+    if (nm != 0u) {                                      // block-uniform
+        for (int idx = tid; idx < n * 32; idx += kPkThreads) {
+            const int tk = idx & 31;
+            if (!((nm >> tk) & 1u) || tk >= m) continue;
+            const int t = p.q_terms[qs + tk];
+            if (t < 0 || t >= p.vocab) continue;
+            const uint32_t dl = (uint32_t)s_wi[idx >> 5];
+            const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
+            const int base = (int)__ldg(p.indptr + t);
+            int lo = base + (int)__ldg(ro), hi = base + (int)__ldg(ro + 1);
+            const int end = hi;
+            while (lo < hi) {                            // lower_bound on the document bits (ascending inside a term)
+                const int mid = lo + ((hi - lo) >> 1);
+                if ((__ldg(pk + mid) >> kPkWBits) < dl) lo = mid + 1; else hi = mid;
+            }
+            if (lo < end) {
+                const uint32_t x = __ldg(pk + lo);
+                if ((x >> kPkWBits) == dl) atomicAdd(&acc[dl], x & kPkWMask);
+            }
+        }
+        __syncthreads();
+    }
     for (int i = tid; i < n; i += kPkThreads) {
         const int dl = s_wi[i];
         const uint32_t mine = acc[dl];
+        if (nm != 0u && (int)mine < bound - 1) continue;  // crossed only the relaxed threshold
         const int slot = atomicAdd(c.cand_cnt + q, 1);
         if (slot < kPkListCap) {
             c.cand_ids[(int64_t)q * kPkListCap + slot] = rbase + dl;
             c.cand_q[(int64_t)q * kPkListCap + slot] = (int)mine;
-            c.cand_u[(int64_t)q * kPkListCap + slot] = (int)mine + ne;
+            c.cand_u[(int64_t)q * kPkListCap + slot] = (int)mine;       // full sums: lower and upper bound coincide
         } else {
             c.ovf[q] = 1;
         }
