@@ -15,6 +15,10 @@
 // stage hand-over changes: a stage is free when BOTH CTAs' MMAs have released it (tcgen05.commit multicast to both
 // CTAs' empty barriers), because the peer's multicast writes into it.
 //
+// Tile order: N tiles fastest.  The activations of a 147k-token batch (226 MB at K = 768, 905 MB at K = 3072) do not fit
+// the L2, the weights (a few MB) do: with M fastest every N tile re-streamed all of A from HBM (9x for the QKV
+// projection); with N fastest the CTAs in flight cover ~16 M tiles x all N tiles, so an A tile is fetched from HBM once.
+//
 // Persistent, warp-specialised: warp 0 = TMA producer (4-stage ring of 128x64 A and 256x64 W tiles),
 // warp 1 = tcgen05.mma issuer (128x256x16, fp32 accumulate into one of two 256-column TMEM stages; the 128x256
 // tile halves L2->SM operand traffic per flop versus 128x128, which measured L2-bound), warps 2-5 = epilogue (tcgen05.ld, one output row per thread, bias / GELU / SwiGLU / residual in
@@ -117,7 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int t = pair; t < n_tiles; t += n_pairs) {
-                const int tm = (t % super_m) * 2 + rank, tn = t / super_m;
+                const int tn = t % p.tiles_n, tm = (t / p.tiles_n) * 2 + rank;     // N tiles fastest: see the header
                 for (int kc = 0; kc < kchunks; kc += p.kps) {
                     ptx::mbar_wait(&bars->empty[stage], phase ^ 1);          // released by BOTH CTAs of the pair
                     ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(p.kps * (G_A_BYTES + G_B_BYTES)));
@@ -179,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int n_out = (EPI == EPI_SWIGLU) ? p.N / 2 : p.N;
         int it = 0;
         for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
-            const int tm = (t % super_m) * 2 + rank, tn = t / super_m;
+            const int tn = t % p.tiles_n, tm = (t / p.tiles_n) * 2 + rank;     // N tiles fastest: see the header
             const int as = it % G_ACC;
             const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
             const int row = tm * GM + quad * 32 + lane;
