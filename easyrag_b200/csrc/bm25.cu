@@ -638,6 +638,7 @@ static bool pk_usable(const ezr_bm25_index* ix, int k) {
 struct PkWorkspace {
     int32_t *thr_key, *thr_q, *cand_cnt, *ovf, *ne_sum, *ovf_n, *ovf_list, *cand_ids, *cand_q, *cand_u;
     uint32_t* ne_mask;
+    int2* plan;
     size_t zero_bytes, total;
 };
 
@@ -662,6 +663,8 @@ static PkWorkspace pk_carve(void* base, int n_queries) {
     off += align_up(q * kPkListCap * 4, 256);
     w.cand_u = reinterpret_cast<int32_t*>(b + off);
     off += align_up(q * kPkListCap * 4, 256);
+    w.plan = reinterpret_cast<int2*>(b + off);
+    off += align_up(q * kPkMaxChunk * kPkPlanTok * sizeof(int2), 256);
     w.total = off;
     return w;
 }
@@ -678,7 +681,7 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
     PkParams c;
     c.post_pk = ix->post_pk; c.thr_q = w.thr_q; c.cand_cnt = w.cand_cnt; c.cand_ids = w.cand_ids; c.cand_q = w.cand_q; c.cand_u = w.cand_u; c.ovf = w.ovf;
     c.term_max = g_bm25_skip ? ix->term_max : nullptr; c.ne_mask = w.ne_mask; c.ne_sum = w.ne_sum;
-    c.ovf_n = w.ovf_n; c.ovf_list = w.ovf_list;
+    c.ovf_n = w.ovf_n; c.ovf_list = w.ovf_list; c.plan = w.plan;
     const size_t smem = (size_t)(kBmRange + 32) * 4;
     static bool attr_done = false;
     if (!attr_done) {
@@ -695,7 +698,11 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
         int r0 = 0, span = 4;
         while (r0 < ix->n_ranges) {
             int len = ix->n_ranges - r0 < span ? ix->n_ranges - r0 : span;
-            if (ix->n_ranges - (r0 + len) < span / 2) len = ix->n_ranges - r0;      // no tiny last chunk
+            if (span < kPkMaxChunk && ix->n_ranges - (r0 + len) < span / 2) len = ix->n_ranges - r0;   // no tiny last chunk
+            if (len > kPkMaxChunk) len = kPkMaxChunk;                                 // the plan table holds this many
+            const int64_t n_plan = (int64_t)n_queries * len * kPkPlanTok;
+            bm25_plan_kernel<<<(unsigned)((n_plan + 255) / 256), 256, 0, st>>>(p, r0, len, n_queries, w.plan);
+            EZR_LAUNCH_CHECK();
             bm25_cand_kernel<<<dim3(n_queries, len), kPkThreads, smem, st>>>(p, c, r0);
             EZR_LAUNCH_CHECK();
             r0 += len;
@@ -703,7 +710,7 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
                 bm25_bound_kernel<<<n_queries, kBdThreads, 0, st>>>(p, c);
                 EZR_LAUNCH_CHECK();
             }
-            if (r0 > 4) span *= 2;
+            if (r0 > 4 && span < kPkMaxChunk) span *= 2;
         }
     }
     {

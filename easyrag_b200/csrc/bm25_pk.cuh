@@ -44,6 +44,8 @@ constexpr int kPkWBits = 32 - kPkDocBits;                 // 19 bits of weight f
 constexpr uint32_t kPkWMask = (1u << kPkWBits) - 1u;
 constexpr int kPkMaxTerms = 1 << (31 - kPkWBits);         // packed weights are < 2^(WBits-1): sums stay below 2^30
 constexpr int kPkLocalCap = 512;                          // candidates one (query, range) CTA can hold
+constexpr int kPkPlanTok = 16;                            // tokens per query resolved by the plan kernel (the rest in-kernel)
+constexpr int kPkMaxChunk = 32;                           // document ranges per candidate launch (size of the plan table)
 #ifndef EZR_BM25_CAND_CAP
 #define EZR_BM25_CAND_CAP 1024
 #endif
@@ -86,6 +88,7 @@ struct PkParams {
     int32_t* ovf;              // [Q] zeroed per call: 1 = hand the query to the ordered kernel
     int32_t* ovf_n;            // [1] zeroed per call
     int32_t* ovf_list;         // [Q]
+    int2* plan;                // [Q][ranges of the chunk][kPkPlanTok] (first posting, postings) of token j in that range
 };
 
 // ---- index build: largest weight (as bits; non-negative doubles order like their bit patterns) + validity ----
@@ -129,6 +132,32 @@ __global__ void bm25_term_max_kernel(const int64_t* __restrict__ indptr, const u
     if (lane == 0) out[t] = mx;
 }
 
+// ---- per (query, range, token): where the token's postings of that range start and how many there are ----
+// Resolved ONCE per candidate launch by fully parallel threads (token -> term -> range table -> offsets is a chain of
+// three dependent loads); bm25_cand_kernel then starts from one coalesced 8-byte load per lane instead of walking that
+// chain inside every (query, range) CTA while seven of its eight warps wait at a barrier (ncu, round 2: 55% of the
+// candidate pass's warp samples sat at barriers).
+__global__ void bm25_plan_kernel(const Bm25Params p, int r_begin, int n_r, int n_queries, int2* __restrict__ plan) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_queries * n_r * kPkPlanTok) return;
+    const int tk = (int)(i % kPkPlanTok);
+    const int rr = (int)((i / kPkPlanTok) % n_r);
+    const int q = (int)(i / ((int64_t)kPkPlanTok * n_r));
+    const int qs = p.q_ptr[q];
+    const int m = p.q_ptr[q + 1] - qs;
+    int2 e = make_int2(0, 0);
+    if (tk < m) {
+        const int t = p.q_terms[qs + tk];
+        if (t >= 0 && t < p.vocab) {
+            const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + (r_begin + rr);
+            const uint32_t o0 = __ldg(ro), o1 = __ldg(ro + 1);
+            e.x = (int)__ldg(p.indptr + t) + (int)o0;
+            e.y = (int)(o1 - o0);
+        }
+    }
+    plan[i] = e;
+}
+
 // ---- phase 1 ----
 // One CTA per (query, document range).  Work is dealt to warps in pieces of kPkPiece postings (256 by default) over
 // ALL terms of the query (a warp's lanes each hold one term's segment; ballot + shuffles map a piece number to its
@@ -169,29 +198,25 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
             }
         }
     };
-    // Set-up of the (query, range): ONE warp resolves the bound, the (optional) skipped tokens and the first 32 token
-    // segments (three dependent loads each) and leaves them in shared memory, while the other warps clear the
-    // accumulators; every warp then picks its lane's segment up with three shared-memory loads.  (Done by all eight
-    // warps redundantly this was ~45% of the instructions of an average CTA: profiles/README.md, round 2.)
-    __shared__ int s_beg[32], s_len[32], s_ne, s_nm;
-    if (warp == kPkWarps - 1) {
-        int b0 = 0;
-        if (lane == 0) b0 = *reinterpret_cast<const volatile int32_t*>(c.thr_q + q);
-        b0 = __shfl_sync(0xffffffffu, b0, 0);
-        int beg0, len0;
-        load_seg(0, beg0, len0);
+    // Set-up of the (query, range): the first kPkPlanTok token segments come from the plan table (one coalesced
+    // 8-byte load per lane, no dependent chain), later tokens (queries longer than kPkPlanTok) are resolved here.
+    __shared__ int s_ne, s_nm;
+    int beg = 0, len = 0;
+    if (lane < kPkPlanTok) {
+        const int2 e = __ldg(c.plan + ((int64_t)q * gridDim.y + blockIdx.y) * kPkPlanTok + lane);
+        beg = e.x; len = e.y;
+    } else if (lane < m) {
+        load_seg(0, beg, len);
+    }
+    if (tid == kPkThreads - 1) {
+        const int b0 = *reinterpret_cast<const volatile int32_t*>(c.thr_q + q);
         // tokens bm25_bound_kernel declared non-essential for this query (valid for every later, higher bound): their
         // postings are not read, their largest possible contribution NE is taken off the crossing threshold instead
         const uint32_t nm = (b0 > 0 && c.term_max) ? __ldg(c.ne_mask + q) : 0u;
-        if ((nm >> lane) & 1u) len0 = 0;                // first token batch only (the mask covers tokens 0..31)
-        s_beg[lane] = beg0;
-        s_len[lane] = len0;
-        if (lane == 0) {
-            s_b = b0;
-            s_cnt = 0;
-            s_ne = nm ? __ldg(c.ne_sum + q) : 0;
-            s_nm = (int)nm;
-        }
+        s_b = b0;
+        s_cnt = 0;
+        s_ne = nm ? __ldg(c.ne_sum + q) : 0;
+        s_nm = (int)nm;
     }
     {
         uint4* a4 = reinterpret_cast<uint4*>(acc);
@@ -201,7 +226,7 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     }
     __syncthreads();
 
-    int beg = s_beg[lane], len = s_len[lane];
+    if (((uint32_t)s_nm >> lane) & 1u) len = 0;           // skipped tokens: first token batch only (the mask covers 0..31)
     const int bound = s_b;                               // B: lower bound of S * (k-th best exact score), 0 = none yet
     const bool track = bound > 0;
     const int ne = s_ne;

@@ -201,6 +201,10 @@ int ezr_dense_topk(const void* corpus_bf16, int64_t n_rows, int32_t dim, int64_t
         // 0 = SS, 1 = TS with 64-row tiles, 2 = TS with 128-row tiles, 3 = TS128 in cluster pairs (multicast corpus tiles)
         int variant = g_force_kernel == 5 ? 3 : g_force_kernel == 4 ? 2 : g_force_kernel == 3 ? 1
                       : (g_force_kernel == 2 ? 0 : g_default_variant);
+        // auto: with the whole shared memory for the ring and enough query blocks to pair up, the cluster-pair form
+        // (each corpus tile pulled from L2 once per pair) measured 10% faster (10.2 vs 11.2 ms per 10k-query launch,
+        // profiles/R2e_bench_k5_seq.json); with a capped ring (routes overlapped) the two forms measured the same
+        if (g_force_kernel == 0 && g_dense_stage_cap == 0 && n_queries >= 8 * 128) variant = 3;
         if (dim > 768 && variant == 0) {
             set_error("dense_topk: the SS tcgen05 kernel supports dim <= 768 (got %d)", dim);
             return EZR_ERR_UNSUPPORTED;
