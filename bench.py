@@ -77,6 +77,7 @@ def parse():
     ap.add_argument("--self-check", type=int, default=64,
                     help="after timing: first N queries through both BM25 kernel paths at full size, compared bit for bit")
     ap.add_argument("--bm25-skip", type=int, default=0, help="1: candidate pass skips non-essential terms (A/B)")
+    ap.add_argument("--bm25-plan", type=int, default=1, help="0: candidate CTAs resolve their posting segments themselves (A/B)")
     ap.add_argument("--dense-probe", type=int, default=0, help="measurement probe of the dense kernel (results invalid)")
     ap.add_argument("--dense-stages", type=int, default=-1,
                     help="cap of the dense kernel's TMA ring (0 = all smem; -1 = 3 with --overlap 1, else 0)")
@@ -369,6 +370,7 @@ def run_ours(args):
     _lib.check(L.ezr_dense_set_stage_cap(stage_cap))
     _lib.check(L.ezr_dense_set_probe(args.dense_probe))
     _lib.check(L.ezr_bm25_set_skipping(args.bm25_skip))
+    _lib.check(L.ezr_bm25_set_plan(args.bm25_plan))
 
     data = make_data(args, dev)
     lo, hi = ezdist.shard_bounds(args.rows, world, rank, align=64)
@@ -464,6 +466,21 @@ def run_ours(args):
     ms_cal, _ = timed(step_cal, max(args.cal_steps, 1))
     prof = read_prof()
     dense_kernel_name = L.ezr_dense_last_kernel().decode()
+    # the one collective on its own (scaling_terms.all_gather_ms): the exchange record of a step, 10 launches
+    ag_ms, rec_bytes = None, None
+    if sharded is not None:
+        st_ = sharded._buffers(args.queries, k, sparse.score_dtype)
+        rec_bytes = int(st_["layout"].nbytes)
+        dist.all_gather_into_tensor(st_["gathered"], st_["record"])
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        ea.record()
+        for _ in range(10):
+            dist.all_gather_into_tensor(st_["gathered"], st_["record"])
+        eb.record()
+        torch.cuda.synchronize()
+        ag_ms = ea.elapsed_time(eb) / 10
     # ---- timed region 1: device-resident inputs, product path
     _lib.check(L.ezr_profile_reset())
     launches0 = L.ezr_launch_count()
@@ -628,7 +645,8 @@ def run_ours(args):
         "dense_TFLOPs": kernels.get("dense_tc", {}).get("TFLOPs"), "dense_ms": kernels.get("dense_tc", {}).get("avg_ms"),
         "bm25_cand_ms": kernels.get("bm25_cand", {}).get("avg_ms"),
         "fixed_ms": seq_ms - sum(kernels[n_]["avg_ms"] for n_ in kernels),
-        "sequential_step_ms": seq_ms, "overlapped_step_ms": step_ms,
+        "sequential_step_ms": seq_ms, "overlapped_step_ms": step_ms, "all_gather_ms": ag_ms,
+        "record_bytes_per_rank": rec_bytes,
         "note": "fixed_ms = one-stream step minus dense and candidate kernels (rescore, merges, fusion, all-gather, gaps); "
                 "compare the terms across N: imbalance -> 1.0 is balanced, dense_TFLOPs falling = shorter units per CTA"}
     line = {

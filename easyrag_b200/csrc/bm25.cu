@@ -630,6 +630,7 @@ static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int
 // lower bounds and the running bound tightens more slowly.  Kept (and parity-tested) as the starting point for a
 // version that refines the bounds between chunks.
 static int g_bm25_skip = 0;
+static int g_bm25_plan = 1;     // ezr_bm25_set_plan: 1 = per-launch plan table (default), 0 = resolve segments inside the CTAs
 
 static bool pk_usable(const ezr_bm25_index* ix, int k) {
     return kPkEnabled && ix->post_pk != nullptr && ix->monotone && ix->score_type == EZR_F64 && k <= 32;
@@ -681,7 +682,7 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
     PkParams c;
     c.post_pk = ix->post_pk; c.thr_q = w.thr_q; c.cand_cnt = w.cand_cnt; c.cand_ids = w.cand_ids; c.cand_q = w.cand_q; c.cand_u = w.cand_u; c.ovf = w.ovf;
     c.term_max = g_bm25_skip ? ix->term_max : nullptr; c.ne_mask = w.ne_mask; c.ne_sum = w.ne_sum;
-    c.ovf_n = w.ovf_n; c.ovf_list = w.ovf_list; c.plan = w.plan;
+    c.ovf_n = w.ovf_n; c.ovf_list = w.ovf_list; c.plan = g_bm25_plan ? w.plan : nullptr;
     const size_t smem = (size_t)(kBmRange + 32) * 4;
     static bool attr_done = false;
     if (!attr_done) {
@@ -701,8 +702,10 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
             if (span < kPkMaxChunk && ix->n_ranges - (r0 + len) < span / 2) len = ix->n_ranges - r0;   // no tiny last chunk
             if (len > kPkMaxChunk) len = kPkMaxChunk;                                 // the plan table holds this many
             const int64_t n_plan = (int64_t)n_queries * len * kPkPlanTok;
-            bm25_plan_kernel<<<(unsigned)((n_plan + 255) / 256), 256, 0, st>>>(p, r0, len, n_queries, w.plan);
-            EZR_LAUNCH_CHECK();
+            if (g_bm25_plan) {
+                bm25_plan_kernel<<<(unsigned)((n_plan + 255) / 256), 256, 0, st>>>(p, r0, len, n_queries, w.plan);
+                EZR_LAUNCH_CHECK();
+            }
             bm25_cand_kernel<<<dim3(n_queries, len), kPkThreads, smem, st>>>(p, c, r0);
             EZR_LAUNCH_CHECK();
             r0 += len;
@@ -827,6 +830,11 @@ int ezr_bm25_term_max(const int64_t* indptr, const uint32_t* post_pk, int32_t vo
 
 int ezr_bm25_set_skipping(int32_t on) {
     g_bm25_skip = on != 0;
+    return EZR_OK;
+}
+
+int ezr_bm25_set_plan(int32_t on) {
+    g_bm25_plan = on != 0;
     return EZR_OK;
 }
 

@@ -202,11 +202,11 @@ bm25_cand_kernel(const Bm25Params p, const PkParams c, const int r_begin) {
     // 8-byte load per lane, no dependent chain), later tokens (queries longer than kPkPlanTok) are resolved here.
     __shared__ int s_ne, s_nm;
     int beg = 0, len = 0;
-    if (lane < kPkPlanTok) {
+    if (c.plan != nullptr && lane < kPkPlanTok) {
         const int2 e = __ldg(c.plan + ((int64_t)q * gridDim.y + blockIdx.y) * kPkPlanTok + lane);
         beg = e.x; len = e.y;
     } else if (lane < m) {
-        load_seg(0, beg, len);
+        load_seg(0, beg, len);                           // tokens past the plan table (or no plan: A/B switch)
     }
     if (tid == kPkThreads - 1) {
         const int b0 = *reinterpret_cast<const volatile int32_t*>(c.thr_q + q);

@@ -7,13 +7,14 @@
 // cuBLAS calls behind the reference's projections: Qwen2 q/k/v/o and SwiGLU MLP (modeling_qwen.py:261-263,
 // 319,186) and the BERT-shaped encoder's dense layers behind SentenceTransformer.encode (hf_embeddings.py:118-123).
 //
-// The GEMMs of this encoder are L2 -> SM bandwidth bound, not tensor bound: a 128 x 256 tile pulls 48 KB of operands per
-// 64-wide k-chunk (87 FLOP / byte) and 148 SMs doing that need ~2x what the L2 delivers (measured: 0.42-0.45 of the
-// tensor peak whatever the epilogue).  So CTAs run in CLUSTER PAIRS on the same W tile (two M tiles, one N tile): each
-// CTA loads its own A tile and HALF of the W tile and TMA-multicasts that half into both CTAs' shared memory, 32 KB
-// instead of 48 KB from L2 per CTA and k-chunk (131 FLOP / byte).  The MMAs stay single-CTA (cta_group::1); only the
-// stage hand-over changes: a stage is free when BOTH CTAs' MMAs have released it (tcgen05.commit multicast to both
-// CTAs' empty barriers), because the peer's multicast writes into it.
+// CTA PAIRS (cta_group::2).  A single-CTA tcgen05.mma 128 x 256 x 16 reads A (4 KB) and B (8 KB) from shared memory every
+// 128 cycles while TMA refills the same 12 KB: 192 B/clk against the 128 B/clk a shared memory delivers, i.e. a ceiling
+// of two thirds of the tensor peak (measured in round 2: tensor pipe 65% active at best, 1130 TFLOP/s on the
+// friendliest shape).  In pair mode one instruction spans the two CTAs of a cluster pair (M = 256, N = 256): each CTA
+// keeps its own 128 rows of A and only its HALF of the W tile (128 of the 256 rows) in shared memory -- 8 KB per 128
+// cycles -- and each CTA's tensor memory receives its 128 rows of the result.  The leader CTA (cluster rank 0) issues
+// the MMAs; both CTAs run their own TMA producer (own A tile + own W half, bytes counted on the leader's barrier) and
+// their own epilogue (remote arrive on the leader's accumulator-free barrier).
 //
 // Tile order: N tiles fastest.  The activations of a 147k-token batch (226 MB at K = 768, 905 MB at K = 3072) do not fit
 // the L2, the weights (a few MB) do: with M fastest every N tile re-streamed all of A from HBM (9x for the QKV
@@ -29,12 +30,12 @@
 namespace ezr {
 
 constexpr int GM = 128, GN = 256, GK = 64;
-constexpr int G_STAGES = 4;
+constexpr int G_STAGES = 6;
 constexpr int G_ACC = 2;
 constexpr int G_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int G_A_BYTES = GM * GK * 2;   // 16 KB
-constexpr int G_B_BYTES = GN * GK * 2;   // 32 KB
-constexpr int G_CLUSTER = 2;             // CTAs sharing a W tile
+constexpr int G_B_BYTES = (GN / 2) * GK * 2;   // 16 KB: this CTA's half of the 256-row W tile
+constexpr int G_CLUSTER = 2;             // CTAs of a pair
 
 enum { EPI_NONE = 0, EPI_GELU = 1, EPI_SWIGLU = 2 };
 
@@ -86,7 +87,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int EPI>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const GemmParams p) {          // map_w: boxes of GN / 2 rows (one CTA's half of the W tile)
+               const GemmParams p) {          // map_w: boxes of GN / 2 rows (this CTA's half of the W tile)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_a = smem;
@@ -105,14 +106,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_w);
-        for (int i = 0; i < G_STAGES; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], G_CLUSTER); }
-        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], 8); }
+        for (int i = 0; i < G_STAGES; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); }
+        // acc_empty is only waited on in the leader: 8 epilogue warps of each CTA of the pair arrive there
+        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], 8 * G_CLUSTER); }
         ptx::fence_barrier_init();
     }
-    if (warp == 1) ptx::tmem_alloc<G_ACC * GN>(&bars->tmem_base);
+    if (warp == 1) ptx::tmem_alloc_pair<G_ACC * GN>(&bars->tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync();                 // the peer's barriers exist before anything is multicast into this CTA
+    ptx::cluster_sync();                 // the peer's barriers exist before anything arrives on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -123,32 +125,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int t = pair; t < n_tiles; t += n_pairs) {
                 const int tn = t % p.tiles_n, tm = (t / p.tiles_n) * 2 + rank;     // N tiles fastest: see the header
                 for (int kc = 0; kc < kchunks; kc += p.kps) {
-                    ptx::mbar_wait(&bars->empty[stage], phase ^ 1);          // released by BOTH CTAs of the pair
-                    ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(p.kps * (G_A_BYTES + G_B_BYTES)));
+                    ptx::mbar_wait(&bars->empty[stage], phase ^ 1);          // the pair's MMAs have released the stage
+                    // the leader's barrier counts the bytes of BOTH CTAs (own A tile + own W half each)
+                    if (rank == 0)
+                        ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(p.kps * G_CLUSTER * (G_A_BYTES + G_B_BYTES)));
                     for (int j = 0; j < p.kps; ++j) {
-                        ptx::tma_load_2d(smem_a + (size_t)(stage * p.kps + j) * G_A_BYTES, &map_a, &bars->full[stage],
-                                         (kc + j) * GK, tm * GM);
-                        // this CTA's half of the W tile, into both CTAs (rows [rank * 128, +128) of the 256-row tile)
-                        ptx::tma_load_2d_mcast(smem_b + (size_t)(stage * p.kps + j) * G_B_BYTES + (size_t)rank * (G_B_BYTES / 2),
-                                               &map_w, &bars->full[stage], (kc + j) * GK, tn * GN + rank * (GN / 2),
-                                               (uint16_t)0x3);
+                        ptx::tma_load_2d_pair(smem_a + (size_t)(stage * p.kps + j) * G_A_BYTES, &map_a, &bars->full[stage],
+                                              (kc + j) * GK, tm * GM);
+                        ptx::tma_load_2d_pair(smem_b + (size_t)(stage * p.kps + j) * G_B_BYTES, &map_w, &bars->full[stage],
+                                              (kc + j) * GK, tn * GN + rank * (GN / 2));
                     }
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05 instructions
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(GM, GN);
+        // LEADER CTA only.  Whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05
+        // instructions, each spanning the pair (M = 256)
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(GM * G_CLUSTER, GN);
         const uint64_t a_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_a));
         const uint64_t b_desc0 = ptx::make_desc_sw128(ptx::smem_u32(smem_b));
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
+        for (int t = pair; rank == 0 && t < n_tiles; t += n_pairs, ++it) {
             const int as = it % G_ACC;
             const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
-            ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);
+            ptx::mbar_wait(&bars->acc_empty[as], aph ^ 1);                       // both CTAs' epilogues have drained it
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * GN);
             for (int kc = 0; kc < kchunks; kc += p.kps) {
@@ -160,12 +163,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int j = 0; j < p.kps; ++j) {
 #pragma unroll
                         for (int k4 = 0; k4 < GK / 16; ++k4)
-                            ptx::umma_f16_ss(d_tmem, a_desc + (uint64_t)(j * (G_A_BYTES >> 4) + k4 * 2),
-                                             b_desc + (uint64_t)(j * (G_B_BYTES >> 4) + k4 * 2), idesc,
-                                             (uint32_t)((kc | j | k4) != 0));
+                            ptx::umma_f16_ss_pair(d_tmem, a_desc + (uint64_t)(j * (G_A_BYTES >> 4) + k4 * 2),
+                                                  b_desc + (uint64_t)(j * (G_B_BYTES >> 4) + k4 * 2), idesc,
+                                                  (uint32_t)((kc | j | k4) != 0));
                     }
-                    ptx::umma_commit_mcast(&bars->empty[stage], (uint16_t)0x3);   // frees the stage in both CTAs
-                    if (kc + p.kps >= kchunks) ptx::umma_commit(&bars->acc_full[as]);
+                    ptx::umma_commit_pair(&bars->empty[stage], (uint16_t)0x3);    // frees the stage in both CTAs
+                    if (kc + p.kps >= kchunks) ptx::umma_commit_pair(&bars->acc_full[as], (uint16_t)0x3);   // both epilogues
                 }
                 __syncwarp();
                 if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -255,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (ci == cpw - 1) {
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[as]);
+                    if (lane == 0) ptx::mbar_arrive_remote(&bars->acc_empty[as], 0u);      // the leader's barrier
                 }
                 const int ocol = ocol_base + c * 32;
                 if (row_ok && ocol < n_out) {
@@ -296,10 +299,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync();                 // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+    ptx::cluster_sync();                 // no CTA leaves (or frees tensor memory) while the pair's MMAs / arrivals are in flight
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<G_ACC * GN>(tmem_base);
+        ptx::tmem_dealloc_pair<G_ACC * GN>(tmem_base);
     }
 }
 

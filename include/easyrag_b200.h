@@ -138,6 +138,11 @@ int ezr_bm25_term_max(const int64_t* indptr, const uint32_t* post_pk, int32_t vo
  * candidates cost more rescoring time than the skipped postings save (profiles/README.md), hence the default. */
 int ezr_bm25_set_skipping(int32_t on);
 
+/* 1 (default): every candidate launch is preceded by a plan kernel that resolves token -> posting segment for all its
+ * (query, range) pairs in parallel; 0: the candidate CTAs walk that chain of dependent loads themselves (A/B switch;
+ * results are identical). */
+int ezr_bm25_set_plan(int32_t on);
+
 /* candidates per query the two-phase path can hold before it hands a query to the ordered kernel (0: not built) */
 int ezr_bm25_cand_capacity(void);
 
