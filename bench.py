@@ -73,6 +73,9 @@ def parse():
     ap.add_argument("--dense-kernel", type=int, default=0,
                     help="0 auto, 1 simt, 2 tcgen05 SS, 3 tcgen05 TS (N=64), 4 TS (N=128), 5 TS128 in cluster pairs (multicast)")
     ap.add_argument("--overlap", type=int, default=1, help="1 (default): dense and BM25 routes on two streams")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="1 (default, needs --overlap 1): steps are submitted, not joined -- the join of step i (all-gather, "
+                         "merges, RRF) runs under the route kernels of step i+1; 0: every step joins the caller's stream")
     ap.add_argument("--cal-steps", type=int, default=5, help="non-overlapped calibration steps for per-kernel times")
     ap.add_argument("--self-check", type=int, default=64,
                     help="after timing: first N queries through both BM25 kernel paths at full size, compared bit for bit")
@@ -392,14 +395,19 @@ def run_ours(args):
     h_ids = torch.empty(args.queries, k, dtype=torch.int32).pin_memory()
     h_sc = torch.empty(args.queries, k, dtype=torch.float64).pin_memory()
     pipe = batched.HostPipeline(sharded if sharded is not None else ranker, args.queries, args.dim,
-                                int(h_terms.numel()), k, k)
+                                int(h_terms.numel()), k, k, pipelined=bool(args.pipeline) and overlap)
 
     def hybrid(r, s, qv, qp, qt):
         if s is not None:
             return s.hybrid(qv, qp, qt, k=k, k_out=k)
         return r.hybrid(qv, qp, qt, k, k, k)
 
+    pipelined = bool(args.pipeline) and overlap
+    top = sharded if sharded is not None else ranker
+
     def step_device():
+        if pipelined:
+            return top.submit(d_qvec, d_ptr, d_terms, k=k, k_out=k)
         return hybrid(ranker, sharded, d_qvec, d_ptr, d_terms)[0]
 
     def step_cal():
@@ -459,6 +467,7 @@ def run_ours(args):
     for _ in range(n_warm):
         step_cal()
         step_device()
+    top.join()
     torch.cuda.synchronize()
     # ---- calibration: the routes back to back on one stream, per-kernel CUDA events (roofline durations)
     _lib.check(L.ezr_profile_reset())
@@ -485,7 +494,7 @@ def run_ours(args):
     _lib.check(L.ezr_profile_reset())
     launches0 = L.ezr_launch_count()
     sampler.begin()
-    ms, per_step = timed(step_device, args.steps)
+    ms, per_step = timed(step_device, args.steps, drain=top.join)
     sampler.end()
     launches_timed = L.ezr_launch_count() - launches0
     prof_timed = read_prof()
@@ -663,6 +672,7 @@ def run_ours(args):
                    "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "queries_per_step": args.queries,
                    "k": k, "rrf_K": 60, "tokens": data["n_tokens"], "postings_local": postings_local,
                    "queries_per_corpus_pass": min(args.queries, 128), "routes_overlapped": overlap,
+                   "steps_pipelined": pipelined,
                    "dense_ring_stages_cap": stage_cap, "timed_region_starts_from": "query vectors + term ids",
                    "l2": ("explicit flush: 512 MB written between steps, every step timed on its own" if l2_flush else
                           "inputs larger than L2 (corpus shard and postings >> 126 MB), no explicit flush"),

@@ -243,17 +243,23 @@ class CoarseRanker:
     """
 
     def __init__(self, dense: DenseIndex, sparse: Bm25Index, canon: Optional[torch.Tensor] = None,
-                 overlap: bool = False):
+                 overlap: bool = False, depth: int = 2):
         assert dense.device == sparse.device
         self.dense, self.sparse = dense, sparse
         self.device = dense.device
         self.canon = None if canon is None else canon.to(device=self.device, dtype=torch.int32).contiguous()
         self.overlap = overlap
+        self.depth = max(int(depth), 1)
         self.s_dense = torch.cuda.Stream(device=self.device) if overlap else None
         self.s_sparse = torch.cuda.Stream(device=self.device) if overlap else None
+        # the join of a submitted batch (collective, merges, RRF): short kernels, scheduled ahead of the next
+        # batch's route CTAs whenever an SM has room
+        self.s_tail = torch.cuda.Stream(device=self.device, priority=-1) if overlap else None
         self.ws_dense = Workspace(self.device)
         self.ws_sparse = Workspace(self.device)
         self._bufs = {}
+        self._slots = {}
+        self._n_submit = 0
 
     def _buffers(self, nq, kd, ks, ko):
         key = (nq, kd, ks, ko)
@@ -306,6 +312,87 @@ class CoarseRanker:
         rrf_fuse(s_out.ids, s_out.counts, d_out.ids, d_out.counts, k_out, K=K, canon=self.canon, out=f_out)
         return f_out, s_out, d_out
 
+    # ---- batch pipelining: submit() returns before the batch is joined to the caller's stream -------------------
+    def _slot(self, key, make):
+        """Result buffers + events of the next in-flight batch (``depth`` of them per key, used round robin)."""
+        if key not in self._slots:
+            self._slots[key] = [dict(make(), ev_in=torch.cuda.Event(), ev_d=torch.cuda.Event(),
+                                     ev_s=torch.cuda.Event(), done=torch.cuda.Event(), free=torch.cuda.Event())
+                                for _ in range(self.depth)]
+        slot = self._slots[key][self._n_submit % self.depth]
+        self._n_submit += 1
+        return slot
+
+    def launch_routes(self, slot, queries, q_ptr, q_terms, k, q_group, d_out: TopK, s_out: TopK) -> None:
+        """Both routes on their streams, ordered after (a) the caller's stream at this point (the inputs), (b) the
+        join that last read this slot's buffers and (c) the consumer's release of the slot.  Nothing is joined back
+        to the caller's stream: ``slot['ev_d']`` / ``slot['ev_s']`` mark the two routes' results."""
+        if not self.overlap:
+            raise RuntimeError("submit() needs CoarseRanker(overlap=True): the routes and the join run on own streams")
+        cur = torch.cuda.current_stream(self.device)
+        slot["ev_in"].record(cur)
+        for st in (self.s_dense, self.s_sparse):
+            st.wait_event(slot["ev_in"])
+            st.wait_event(slot["done"])          # never-recorded events do not block
+            st.wait_event(slot["free"])
+        with torch.cuda.stream(self.s_dense):
+            dense_topk(self.dense, queries, k, q_group=q_group, ws=self.ws_dense, stream=self.s_dense, out=d_out)
+            slot["ev_d"].record(self.s_dense)
+        with torch.cuda.stream(self.s_sparse):
+            bm25_topk(self.sparse, q_ptr, q_terms, k, q_group=q_group, ws=self.ws_sparse, stream=self.s_sparse,
+                      out=s_out)
+            slot["ev_s"].record(self.s_sparse)
+
+    def submit(self, queries: torch.Tensor, q_ptr: torch.Tensor, q_terms: torch.Tensor, k: int = 10, k_out: int = 10,
+               K: int = 60, q_group: Optional[torch.Tensor] = None) -> "Ticket":
+        """:meth:`hybrid` for a stream of independent batches: the same kernels, but the batch is NOT joined to the
+        caller's stream, so the routes of the next submitted batch start while this batch's RRF (and, sharded, its
+        all-gather and merges) are still running.  Up to ``depth`` batches are in flight; a slot's buffers are
+        rewritten ``depth`` submits later, after its join has finished and -- if the consumer reads them on another
+        stream -- after :meth:`Ticket.release`.  Read the results after :meth:`Ticket.wait` or :meth:`join`."""
+        nq = queries.shape[0]
+
+        def make():
+            mk = lambda dt, *shape: torch.empty(*shape, dtype=dt, device=self.device)
+            return dict(d=TopK(mk(torch.float32, nq, k), mk(torch.int32, nq, k), mk(torch.int32, nq)),
+                        s=TopK(mk(self.sparse.score_dtype, nq, k), mk(torch.int32, nq, k), mk(torch.int32, nq)),
+                        f=TopK(mk(torch.float64, nq, k_out), mk(torch.int32, nq, k_out), mk(torch.int32, nq)))
+        slot = self._slot((nq, k, k_out), make)
+        self.launch_routes(slot, queries, q_ptr, q_terms, k, q_group, slot["d"], slot["s"])
+        with torch.cuda.stream(self.s_tail):
+            self.s_tail.wait_event(slot["ev_d"])
+            self.s_tail.wait_event(slot["ev_s"])
+            rrf_fuse(slot["s"].ids, slot["s"].counts, slot["d"].ids, slot["d"].counts, k_out, K=K, canon=self.canon,
+                     out=slot["f"], stream=self.s_tail)
+            slot["done"].record(self.s_tail)
+        return Ticket(slot["f"], slot["s"], slot["d"], slot)
+
+    def join(self) -> None:
+        """The caller's stream waits for every submitted batch."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in (self.s_tail, self.s_dense, self.s_sparse):
+            if st is not None:
+                cur.wait_stream(st)
+
+
+class Ticket:
+    """A submitted batch: result buffers (valid once ``done`` has fired) and the slot they live in."""
+    __slots__ = ("fused", "sparse", "dense", "_slot")
+
+    def __init__(self, fused: TopK, sparse: TopK, dense: TopK, slot: dict):
+        self.fused, self.sparse, self.dense, self._slot = fused, sparse, dense, slot
+
+    @property
+    def done(self) -> torch.cuda.Event:
+        return self._slot["done"]
+
+    def wait(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        (stream or torch.cuda.current_stream(self.fused.ids.device)).wait_event(self._slot["done"])
+
+    def release(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Call on the stream that read the results, after the reads: the slot may be rewritten once they finish."""
+        self._slot["free"].record(stream or torch.cuda.current_stream(self.fused.ids.device))
+
 
 class HostPipeline:
     """Host-buffer front end of the batched path: pinned host inputs in, pinned host results out, every call.
@@ -313,13 +400,18 @@ class HostPipeline:
     ``step`` enqueues, without blocking the host: H2D of the query vectors / term pointers / term ids on a copy
     stream, both routes + (all-gather, merge) + RRF on the caller's stream, D2H of the fused ids and float64 scores
     on a second copy stream.  Inputs are double buffered on the device, so the copies of step i+1 run under the
-    kernels of step i; a result buffer is only reused once its D2H has completed.  ``ranker`` is a
+    kernels of step i; a result buffer is only reused once its D2H has completed.  With a ranker built with
+    ``overlap=True`` the steps are *submitted* (``CoarseRanker.submit``): the join and the D2H of step i run under the
+    route kernels of step i+1.  ``ranker`` is a
     :class:`CoarseRanker` or an :class:`easyrag_b200.dist.ShardedCoarseRanker`.
     """
 
-    def __init__(self, ranker, n_queries: int, dim: int, max_terms: int, k: int = 10, k_out: int = 10, depth: int = 2):
+    def __init__(self, ranker, n_queries: int, dim: int, max_terms: int, k: int = 10, k_out: int = 10, depth: int = 2,
+                 pipelined: Optional[bool] = None):
         base = getattr(ranker, "ranker", ranker)
         self.ranker, self.k, self.k_out = ranker, k, k_out
+        # pipelined (default whenever the ranker runs its routes on own streams): steps are submitted, not joined
+        self.pipelined = bool(base.overlap) if pipelined is None else bool(pipelined)
         self.device = dev = base.device
         self.sharded = base is not ranker
         self.s_in = torch.cuda.Stream(device=dev)
@@ -352,6 +444,22 @@ class HostPipeline:
             slot["terms"][:nt].copy_(h_terms, non_blocking=True)
             slot["ev_in"].record(self.s_in)
         cur.wait_event(slot["ev_in"])
+        if self.pipelined:
+            # the batch is not joined to the caller's stream: the routes of the next step start while this step's
+            # join (all-gather, merges, RRF) and its D2H are still running
+            if self.sharded:
+                t = self.ranker.submit(slot["qvec"], slot["ptr"], slot["terms"], k=self.k, k_out=self.k_out,
+                                       q_group=q_group)
+            else:
+                t = self.ranker.submit(slot["qvec"], slot["ptr"], slot["terms"], self.k, self.k_out, q_group=q_group)
+            slot["ev_free"] = t.done                         # both routes have read the inputs once the join has run
+            with torch.cuda.stream(self.s_out):
+                t.wait(self.s_out)
+                h_ids_out.copy_(t.fused.ids, non_blocking=True)
+                h_scores_out.copy_(t.fused.scores, non_blocking=True)
+                t.release(self.s_out)                        # the result slot may be rewritten after these copies
+                self.ev_out.record(self.s_out)
+            return
         cur.wait_event(self.ev_out)                          # the previous results have left the fused buffer
         if self.sharded:
             fused = self.ranker.hybrid(slot["qvec"], slot["ptr"], slot["terms"], k=self.k, k_out=self.k_out,

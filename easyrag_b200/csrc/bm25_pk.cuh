@@ -511,6 +511,7 @@ bm25_bound_kernel(const Bm25Params p, const PkParams c) {
 // ---- phase 2: exact scores of the candidates in token order, canonical top-k ----
 constexpr int kRsThreads = 128;
 constexpr int kRsTok = 64;     // tokens whose (term, base) are staged in shared memory
+constexpr int kRsU = 4;        // candidates a warp scores at once (independent binary searches in flight)
 
 __global__ void __launch_bounds__(kRsThreads)
 bm25_rescore_kernel(const Bm25Params p, const PkParams c, double* __restrict__ out_scores,
@@ -537,35 +538,74 @@ bm25_rescore_kernel(const Bm25Params p, const PkParams c, double* __restrict__ o
     }
     __syncthreads();
     const double* __restrict__ post_w = reinterpret_cast<const double*>(p.post_w);
-    for (int ci = warp; ci < n; ci += kRsThreads / 32) {
-        const int doc = c.cand_ids[(int64_t)q * kPkListCap + ci];
-        const int r = doc / kBmRange;
-        double s = 0.0;
+    // A warp scores kRsU candidates at once (lane = token): the kRsU binary searches of a lane are independent, so
+    // their loads are in flight together -- the kernel is bound by the latency of those dependent L2 reads, not by
+    // their count.  The sums stay per candidate, in token order.
+    for (int cb = warp * kRsU; cb < n; cb += (kRsThreads / 32) * kRsU) {
+        int doc[kRsU];
+        double s[kRsU];
+#pragma unroll
+        for (int u = 0; u < kRsU; ++u) {
+            doc[u] = cb + u < n ? c.cand_ids[(int64_t)q * kPkListCap + cb + u] : -1;
+            s[u] = 0.0;
+        }
         for (int c0 = 0; c0 < m; c0 += 32) {
             const int j = c0 + lane;
-            double wv = 0.0;
+            double wv[kRsU];
+#pragma unroll
+            for (int u = 0; u < kRsU; ++u) wv[u] = 0.0;
+            int t = -1, base = 0;
             if (j < m) {
-                int t, base;
                 if (j < kRsTok) { t = s_t[j]; base = s_base[j]; }
                 else {
                     t = p.q_terms[qs + j];
                     if (t < 0 || t >= p.vocab) t = -1;
                     base = t >= 0 ? (int)p.indptr[t] : 0;
                 }
-                if (t >= 0) {
-                    const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + r;
-                    int lo = base + (int)ro[0], hi = base + (int)ro[1];
-                    while (lo < hi) {                    // lower_bound of doc in the term's postings of range r
-                        const int mid = lo + ((hi - lo) >> 1);       // lo + hi can pass 2^31 on a 2^30+ posting shard
-                        if (__ldg(p.post_doc + mid) < doc) lo = mid + 1; else hi = mid;
+            }
+            if (t >= 0) {
+                int lo[kRsU], hi[kRsU], end[kRsU];
+#pragma unroll
+                for (int u = 0; u < kRsU; ++u) {
+                    lo[u] = hi[u] = end[u] = 0;
+                    if (doc[u] >= 0) {
+                        const uint32_t* ro = p.range_off + (int64_t)t * (p.n_ranges + 1) + doc[u] / kBmRange;
+                        lo[u] = base + (int)ro[0];
+                        hi[u] = end[u] = base + (int)ro[1];
                     }
-                    if (lo < base + (int)ro[1] && __ldg(p.post_doc + lo) == doc) wv = __ldg(post_w + lo);
                 }
+                bool more = true;
+                while (more) {                           // lower_bound of doc[u] in the term's postings of its range
+                    more = false;
+                    int got[kRsU], mid[kRsU];
+#pragma unroll
+                    for (int u = 0; u < kRsU; ++u) {
+                        mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1);     // lo + hi can pass 2^31 on a 2^30+ posting shard
+                        got[u] = lo[u] < hi[u] ? __ldg(p.post_doc + mid[u]) : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kRsU; ++u) {
+                        if (lo[u] < hi[u]) {
+                            if (got[u] < doc[u]) lo[u] = mid[u] + 1; else hi[u] = mid[u];
+                            more |= lo[u] < hi[u];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kRsU; ++u)
+                    if (lo[u] < end[u] && __ldg(p.post_doc + lo[u]) == doc[u]) wv[u] = __ldg(post_w + lo[u]);
             }
             const int cnt = min(32, m - c0);
-            for (int jj = 0; jj < cnt; ++jj) s = __dadd_rn(s, __shfl_sync(0xffffffffu, wv, jj));   // token order
+            for (int jj = 0; jj < cnt; ++jj) {
+#pragma unroll
+                for (int u = 0; u < kRsU; ++u) s[u] = __dadd_rn(s[u], __shfl_sync(0xffffffffu, wv[u], jj));   // token order
+            }
         }
-        if (lane == 0) { s_sc[ci] = s; s_id[ci] = doc; }
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < kRsU; ++u)
+                if (cb + u < n) { s_sc[cb + u] = s[u]; s_id[cb + u] = doc[u]; }
+        }
     }
     __syncthreads();
     for (int i = tid; i < n; i += kRsThreads) {

@@ -27,12 +27,24 @@
 #include "../ezr_common.cuh"
 #include "../ptx.cuh"
 
+#ifndef EZR_GEMM_PROBE
+#define EZR_GEMM_PROBE 0       // tuning probes (variant builds only): 1 = epilogue without stores, 2 = no epilogue
+#endif
+
 namespace ezr {
 
 constexpr int GM = 128, GN = 256, GK = 64;
-constexpr int G_STAGES = 6;
+#ifndef EZR_GEMM_STAGES
+#define EZR_GEMM_STAGES 6
+#endif
+constexpr int G_STAGES = EZR_GEMM_STAGES;
 constexpr int G_ACC = 2;
-constexpr int G_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
+#ifndef EZR_GEMM_EPI_WARPS
+#define EZR_GEMM_EPI_WARPS 8
+#endif
+constexpr int G_EPI_WARPS = EZR_GEMM_EPI_WARPS;          // 8 or 16: G_EPI_WARPS / 4 warps share a TMEM lane quadrant, splitting the columns
+constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;         // TMA warp, MMA warp, epilogue warps
+constexpr int G_ST_BYTES = 32 * 32 * 2;                  // one epilogue warp's store staging: 32 rows x 32 bf16 columns
 constexpr int G_A_BYTES = GM * GK * 2;   // 16 KB
 constexpr int G_B_BYTES = (GN / 2) * GK * 2;   // 16 KB: this CTA's half of the 256-row W tile
 constexpr int G_CLUSTER = 2;             // CTAs of a pair
@@ -49,6 +61,7 @@ struct GemmParams {
     int64_t ldr;
     __nv_bfloat16* out;              // [M, ldo]
     int64_t ldo;
+    int tma_out;                     // 1: the output goes through shared memory and TMA stores (ldo % 8 == 0, 16-byte aligned)
 };
 
 struct GemmBarriers {
@@ -87,14 +100,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int EPI>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const GemmParams p) {          // map_w: boxes of GN / 2 rows (this CTA's half of the W tile)
+               const __grid_constant__ CUtensorMap map_o, const GemmParams p) {          // map_w: boxes of GN / 2 rows (this CTA's half of the W tile)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_a = smem;
     unsigned char* smem_b = smem + (size_t)G_STAGES * G_A_BYTES;
-    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_b + (size_t)G_STAGES * G_B_BYTES);
+    unsigned char* smem_st = smem_b + (size_t)G_STAGES * G_B_BYTES;          // 1024-aligned: the rings are multiples of 16 KB
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_st + (size_t)G_EPI_WARPS * G_ST_BYTES);
 
-    __shared__ float s_bias[8][GN];          // per epilogue warp: bias of its column half (x2 rows for SwiGLU)
+    __shared__ float s_bias[G_EPI_WARPS][GN * 4 / G_EPI_WARPS];   // per epilogue warp: bias of its columns (x2 rows for SwiGLU)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work = super-tiles of (two M tiles) x (one N tile), walked by cluster pairs; this CTA owns M tile 2 * sm + rank
     const int rank = (int)ptx::cluster_ctarank();
@@ -106,9 +120,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_w);
+        ptx::prefetch_tensormap(&map_o);
         for (int i = 0; i < G_STAGES; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); }
-        // acc_empty is only waited on in the leader: 8 epilogue warps of each CTA of the pair arrive there
-        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], 8 * G_CLUSTER); }
+        // acc_empty is only waited on in the leader: the epilogue warps of both CTAs of the pair arrive there
+        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], G_EPI_WARPS * G_CLUSTER); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc_pair<G_ACC * GN>(&bars->tmem_base);
@@ -175,13 +190,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ---------------- epilogue: 8 warps, two per TMEM lane quadrant, each owning half of the tile's columns.
+        // ---------------- epilogue: G_EPI_WARPS warps, G_EPI_WARPS / 4 per TMEM lane quadrant, each owning a slice of the
+        // tile's columns.  A warp's 32 x 32 output block is packed to bf16 into its own shared-memory staging buffer
+        // (TMA's 64-byte swizzle: conflict-free 16-byte writes) and leaves as ONE TMA store of full 64-byte row
+        // segments; stores straight from the registers (one output row per lane, 16 bytes per instruction) touched 32
+        // half-filled sectors per instruction and were measured as the limit of every K = 768 shape.
         // Global-memory latency is kept off the critical path: the bias slice is staged in shared memory BEFORE the
         // accumulator wait, and the residual of chunk c+1 is in flight while chunk c is processed.
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? GN / 64 : GN / 32;   // 32 output columns per chunk
-        constexpr int cpw = n_out_chunks / 2;                                   // chunks per warp
+        constexpr int cpw = n_out_chunks / (G_EPI_WARPS / 4);                   // chunks per warp
+        static_assert(cpw >= 1 && (EPI == EPI_SWIGLU ? 2 : 1) * cpw * 32 <= GN * 4 / G_EPI_WARPS, "bias slice must fit s_bias");
+        unsigned char* my_st = smem_st + (size_t)(warp - 2) * G_ST_BYTES;
+        const int st_row = lane * 64, st_sw = (lane >> 1) & 3;                  // this lane's staging row, its swizzle
         float* sb = s_bias[warp - 2];                                           // this warp's bias slice
         const int n_out = (EPI == EPI_SWIGLU) ? p.N / 2 : p.N;
         int it = 0;
@@ -223,6 +245,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
             ptx::mbar_wait(&bars->acc_full[as], aph);
             ptx::tc_fence_after();
+#if EZR_GEMM_PROBE == 2
+            // tuning probe (never in the shipped build): no epilogue at all -> the TMA + MMA rate alone
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(&bars->acc_empty[as], 0u);
+            continue;
+#endif
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * GN);
             // NOT unrolled: inlined copies of the 32-wide body are >130 KB of SASS (230 KB with GELU) and stream
             // through the instruction cache on every tile.
@@ -261,19 +290,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (lane == 0) ptx::mbar_arrive_remote(&bars->acc_empty[as], 0u);      // the leader's barrier
                 }
                 const int ocol = ocol_base + c * 32;
-                if (row_ok && ocol < n_out) {
-                    if (p.residual) {
-                        if (res_vec && ocol + 32 <= n_out) {
-                            const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(rv);
+                if (p.residual && row_ok && ocol < n_out) {
+                    if (res_vec && ocol + 32 <= n_out) {
+                        const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(rv);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(rh[j]);
-                        } else {
-                            const __nv_bfloat16* rr = p.residual + (int64_t)row * p.ldr + ocol;
+                        for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(rh[j]);
+                    } else {
+                        const __nv_bfloat16* rr = p.residual + (int64_t)row * p.ldr + ocol;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (ocol + j < n_out) v[j] += __bfloat162float(rr[j]);
+                        for (int j = 0; j < 32; ++j)
+                            if (ocol + j < n_out) v[j] += __bfloat162float(rr[j]);
+                    }
+                }
+#if EZR_GEMM_PROBE == 1
+                if (p.M < 0) {                                  // tuning probe: the epilogue's math without its stores
+#else
+                if (p.tma_out) {
+#endif
+                    if (ocol < n_out) {                          // warp-uniform
+                        // the staging buffer is free once the previous store has READ it (not: reached memory)
+                        if (lane == 0) ptx::tma_store_wait_read<0>();
+                        __syncwarp();
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint4 pk;
+                            pk.x = pack_bf16(v[j4 * 8], v[j4 * 8 + 1]);
+                            pk.y = pack_bf16(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+                            pk.z = pack_bf16(v[j4 * 8 + 4], v[j4 * 8 + 5]);
+                            pk.w = pack_bf16(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+                            *reinterpret_cast<uint4*>(my_st + st_row + ((j4 ^ st_sw) << 4)) = pk;
+                        }
+                        ptx::fence_proxy_async();                // generic-proxy writes -> visible to the TMA engine
+                        __syncwarp();
+                        if (lane == 0) {                         // rows past M and columns past n_out are clipped by the map
+                            ptx::tma_store_2d(&map_o, my_st, ocol, tm * GM + quad * 32);
+                            ptx::tma_store_commit();
                         }
                     }
+                } else if (row_ok && ocol < n_out) {
                     __nv_bfloat16* op = p.out + (int64_t)row * p.ldo + ocol;
                     if (ocol + 32 <= n_out && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
@@ -295,6 +349,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int j = 0; j < 4; ++j) rv[j] = rn[j];
             }
         }
+        if (lane == 0) ptx::tma_store_wait<0>();         // this warp's stores have left shared memory and are complete
     }
 
     ptx::tc_fence_before();
@@ -322,13 +377,21 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     p.bias = bias; p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo;
     p.kps = 1;            // 2 chunks per stage was measured slower (coarser producer/consumer hand-off)
     p.n_stages = G_STAGES / p.kps;
-    CUtensorMap map_a, map_w;
+    const int n_out = epi == EPI_SWIGLU ? N / 2 : N;
+    p.tma_out = (ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    CUtensorMap map_a, map_w, map_o;
     int rc = encode_tmap_2d_bf16(&map_a, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GK, GM);
     if (rc) return rc;
     rc = encode_tmap_2d_bf16(&map_w, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GK, GN / G_CLUSTER);
     if (rc) return rc;
-    const size_t smem = 1024 + (size_t)G_STAGES * (G_A_BYTES + G_B_BYTES) + sizeof(GemmBarriers) + 64;
-    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const GemmParams);
+    // output map: boxes of 32 columns x 32 rows (one epilogue warp's block), 64-byte swizzle.  Without TMA stores the
+    // kernel never touches it; it is then encoded over A so that the argument stays a valid descriptor.
+    if (p.tma_out) rc = encode_tmap_2d_bf16(&map_o, out, (uint64_t)n_out, (uint64_t)M, (uint64_t)ldo, 32, 32, 64);
+    else map_o = map_a;
+    if (rc) return rc;
+    const size_t smem = 1024 + (size_t)G_STAGES * (G_A_BYTES + G_B_BYTES) + (size_t)G_EPI_WARPS * G_ST_BYTES +
+                        sizeof(GemmBarriers) + 64;
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
     static const kern_t table[3] = {gemm_tc_kernel<EPI_NONE>, gemm_tc_kernel<EPI_GELU>, gemm_tc_kernel<EPI_SWIGLU>};
     static bool attr_done[3] = {false, false, false};
     if (!attr_done[epi]) {
@@ -352,7 +415,7 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     cfg.numAttrs = 1;
     {
         ProfScope prof(EZR_PROF_ENC_GEMM, st);
-        EZR_CUDA(cudaLaunchKernelEx(&cfg, table[epi], map_a, map_w, p));
+        EZR_CUDA(cudaLaunchKernelEx(&cfg, table[epi], map_a, map_w, map_o, p));
     }
     EZR_LAUNCH_CHECK();
     return EZR_OK;

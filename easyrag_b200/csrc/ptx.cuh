@@ -286,6 +286,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // cuTensorMapEncodeTiled is fetched through the runtime (cudaGetDriverEntryPoint) so the
 // library has no link-time dependency on libcuda and still loads on a GPU-less build box.
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems,
-                        uint32_t box_cols, uint32_t box_rows);
+                        uint32_t box_cols, uint32_t box_rows, int swizzle_bytes = 128);
 
 }  // namespace ezr

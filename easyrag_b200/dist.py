@@ -88,24 +88,39 @@ class ShardedCoarseRanker:
         self.rank = dist.get_rank(group)
         self._state = {}
 
-    def _buffers(self, nq: int, k: int, sparse_dtype):
+    def _make(self, nq: int, k: int, sparse_dtype):
         from .batched import TopK
+        dev = self.ranker.device
+        layout = RecordLayout(nq, k, 8 if sparse_dtype == torch.float64 else 4)
+        record = torch.zeros(layout.nbytes, dtype=torch.uint8, device=dev)
+        gathered = torch.zeros(self.world * layout.nbytes, dtype=torch.uint8, device=dev)
+        ds, di, ss, si = record_views(layout, record)
+        cnt = lambda: torch.empty(nq, dtype=torch.int32, device=dev)
+        mk = lambda dt: torch.empty(nq, k, dtype=dt, device=dev)
+        return dict(
+            layout=layout, record=record, gathered=gathered,
+            d_local=TopK(ds, di, cnt()), s_local=TopK(ss, si, cnt()),
+            views=record_views(layout, gathered[:layout.nbytes]),
+            dense=TopK(mk(torch.float32), mk(torch.int32), cnt()),
+            sparse=TopK(mk(sparse_dtype), mk(torch.int32), cnt()))
+
+    def _buffers(self, nq: int, k: int, sparse_dtype):
         key = (nq, k, sparse_dtype)
         if key not in self._state:
-            dev = self.ranker.device
-            layout = RecordLayout(nq, k, 8 if sparse_dtype == torch.float64 else 4)
-            record = torch.zeros(layout.nbytes, dtype=torch.uint8, device=dev)
-            gathered = torch.zeros(self.world * layout.nbytes, dtype=torch.uint8, device=dev)
-            ds, di, ss, si = record_views(layout, record)
-            cnt = lambda: torch.empty(nq, dtype=torch.int32, device=dev)
-            mk = lambda dt: torch.empty(nq, k, dtype=dt, device=dev)
-            self._state[key] = dict(
-                layout=layout, record=record, gathered=gathered,
-                d_local=TopK(ds, di, cnt()), s_local=TopK(ss, si, cnt()),
-                views=record_views(layout, gathered[:layout.nbytes]),
-                dense=TopK(mk(torch.float32), mk(torch.int32), cnt()),
-                sparse=TopK(mk(sparse_dtype), mk(torch.int32), cnt()))
+            self._state[key] = self._make(nq, k, sparse_dtype)
         return self._state[key]
+
+    def _join(self, st, k: int, k_out: int, K: int, canon, f_out, stream=None):
+        """all-gather of the records, per-route merge of the world's lists, RRF -- on the current stream."""
+        from . import batched
+        dist.all_gather_into_tensor(st["gathered"], st["record"], group=self.group)   # the one collective
+        g_ds, g_di, g_ss, g_si = st["views"]
+        nbytes = st["layout"].nbytes
+        dense = batched.merge_topk_parts(g_ds, g_di, self.world, nbytes, k, out=st["dense"], stream=stream)
+        sparse = batched.merge_topk_parts(g_ss, g_si, self.world, nbytes, k, out=st["sparse"], stream=stream)
+        fused = batched.rrf_fuse(sparse.ids, sparse.counts, dense.ids, dense.counts, k_out, K=K, canon=canon, out=f_out,
+                                 stream=stream)
+        return fused, sparse, dense
 
     def hybrid(self, queries, q_ptr, q_terms, k: int = 10, k_out: int = 10, K: int = 60, q_group=None,
                canon: Optional[torch.Tensor] = None):
@@ -117,11 +132,34 @@ class ShardedCoarseRanker:
         st = self._buffers(nq, k, r.sparse.score_dtype)
         _, _, f_out = r.routes(queries, q_ptr, q_terms, k, k_out, q_group=q_group, d_out=st["d_local"],
                                s_out=st["s_local"])
-        dist.all_gather_into_tensor(st["gathered"], st["record"], group=self.group)   # the one collective
-        g_ds, g_di, g_ss, g_si = st["views"]
-        nbytes = st["layout"].nbytes
-        dense = batched.merge_topk_parts(g_ds, g_di, self.world, nbytes, k, out=st["dense"])
-        sparse = batched.merge_topk_parts(g_ss, g_si, self.world, nbytes, k, out=st["sparse"])
-        cn = canon if canon is not None else r.canon
-        fused = batched.rrf_fuse(sparse.ids, sparse.counts, dense.ids, dense.counts, k_out, K=K, canon=cn, out=f_out)
-        return fused, sparse, dense
+        return self._join(st, k, k_out, K, canon if canon is not None else r.canon, f_out)
+
+    def submit(self, queries, q_ptr, q_terms, k: int = 10, k_out: int = 10, K: int = 60, q_group=None,
+               canon: Optional[torch.Tensor] = None):
+        """:meth:`hybrid` without the join to the caller's stream (see ``CoarseRanker.submit``): the all-gather, the
+        merges and the RRF of this batch run on the ranker's join stream while the routes of the next submitted
+        batch already occupy the SMs.  Every rank must submit the same sequence of batches (one collective each)."""
+        from . import batched
+        r = self.ranker
+        nq = queries.shape[0]
+        if k > 32:
+            raise ValueError("the sharded path merges per-shard lists of k <= 32")
+
+        def make():
+            st = self._make(nq, k, r.sparse.score_dtype)
+            st["f"] = batched.TopK(torch.empty(nq, k_out, dtype=torch.float64, device=r.device),
+                                   torch.empty(nq, k_out, dtype=torch.int32, device=r.device),
+                                   torch.empty(nq, dtype=torch.int32, device=r.device))
+            return st
+        slot = r._slot(("sharded", id(self), nq, k, k_out), make)
+        r.launch_routes(slot, queries, q_ptr, q_terms, k, q_group, slot["d_local"], slot["s_local"])
+        with torch.cuda.stream(r.s_tail):
+            r.s_tail.wait_event(slot["ev_d"])
+            r.s_tail.wait_event(slot["ev_s"])
+            fused, sparse, dense = self._join(slot, k, k_out, K, canon if canon is not None else r.canon, slot["f"],
+                                              stream=r.s_tail)
+            slot["done"].record(r.s_tail)
+        return batched.Ticket(fused, sparse, dense, slot)
+
+    def join(self) -> None:
+        self.ranker.join()

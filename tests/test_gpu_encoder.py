@@ -46,6 +46,24 @@ def test_gemm_bias(m, n, k):
     _close(got, ref)
 
 
+def test_gemm_store_paths_strided_and_unaligned_outputs():
+    # (a) a column slice of a wider buffer (row stride > N, TMA-store path): the neighbours stay untouched, rows past M
+    #     and columns past N are clipped; (b) a row stride that is not a multiple of 8 (register-store path)
+    m, n, k = 333, 136, 128
+    a, w = _rand(m, k, seed=11), _rand(n, k, seed=12, scale=0.05)
+    ref = a.float() @ w.float().T
+    wide = torch.full((m + 5, 256), 7.0, dtype=torch.bfloat16, device=DEV)
+    out = wide[:m, 64:64 + n]
+    enc.gemm(a.to(DEV), w.to(DEV), out=out)
+    _close(wide[:m, 64:64 + n], ref)
+    keep = wide.float().cpu()
+    assert (keep[:m, :64] == 7).all() and (keep[:m, 64 + n:] == 7).all() and (keep[m:] == 7).all()
+    n2 = 100
+    w2 = _rand(n2, k, seed=13, scale=0.05)
+    got = enc.gemm(a.to(DEV), w2.to(DEV))                       # ldo = 100: not a multiple of 8
+    _close(got, a.float() @ w2.float().T)
+
+
 def test_gemm_exact_small_integers():
     # integer-valued operands: every partial sum is exact, so the tensor-core result must be bit-exact
     g = torch.Generator().manual_seed(5)

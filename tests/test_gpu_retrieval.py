@@ -638,6 +638,68 @@ def test_hybrid_dense_bm25_rrf_matches_oracle(c1):
         assert f_sc[i, :f_cnt[i]].tobytes() == ref_s.tobytes()
 
 
+def test_submitted_batches_equal_joined_batches_and_host_pipeline(c1):
+    # batch pipelining: six different batches submitted back to back (two result slots, reused three times) must give
+    # exactly what hybrid() gives for each batch on its own; then the same through HostPipeline (pinned host buffers)
+    n, dim, k = c1["stats"].n_docs, 256, 10
+    q = c1["queries"]
+    nq = q.n
+    ranker = batched.CoarseRanker(DenseIndex(_dense_case(n, dim, 1, 77, integer=True)[0], device=DEV), c1["index"],
+                                  overlap=True)
+    ptr, terms = q.term_ptr.to(DEV), q.terms.to(DEV)
+    qvs = [_dense_case(8, dim, nq, 100 + i, integer=True)[1].to(DEV) for i in range(6)]
+    # a different BM25 batch per step too: rotate the queries (term lists of query j move to position j + i)
+    tp = q.term_ptr.numpy().astype(np.int64)
+    tt = q.terms.numpy()
+    bm = []
+    for i in range(6):
+        order = np.roll(np.arange(nq), i)
+        lens = (tp[1:] - tp[:-1])[order]
+        nptr = np.zeros(nq + 1, np.int32)
+        np.cumsum(lens, out=nptr[1:])
+        nterms = np.concatenate([tt[tp[j]:tp[j + 1]] for j in order]) if nq else tt
+        bm.append((torch.from_numpy(nptr), torch.from_numpy(nterms.astype(np.int32))))
+    want = []
+    for i in range(6):
+        f, _, _ = ranker.hybrid(qvs[i], bm[i][0].to(DEV), bm[i][1].to(DEV), k, k, k)
+        want.append((f.ids.clone(), f.scores.clone(), f.counts.clone()))
+    torch.cuda.synchronize()
+    got = []
+    d_bm = [(a.to(DEV), b.to(DEV)) for a, b in bm]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()                                # the consumer: the caller's stream never waits for a join
+    for i in range(6):
+        t = ranker.submit(qvs[i], d_bm[i][0], d_bm[i][1], k=k, k_out=k)
+        with torch.cuda.stream(side):
+            t.wait(side)
+            got.append((t.fused.ids.clone(), t.fused.scores.clone(), t.fused.counts.clone()))
+            t.release(side)
+    ranker.join()
+    torch.cuda.synchronize()
+    for i in range(6):
+        for a, b in zip(got[i], want[i]):
+            assert torch.equal(a, b), f"batch {i}"
+    assert not torch.equal(want[0][0], want[1][0])          # the batches really differ
+    # host pipeline: pinned inputs and outputs, one output buffer per step
+    max_terms = max(int(b.numel()) for _, b in bm)
+    pipe = batched.HostPipeline(ranker, nq, dim, max_terms, k, k)
+    assert pipe.pipelined
+    outs = []
+    for i in range(6):
+        h_ids = torch.empty(nq, k, dtype=torch.int32).pin_memory()
+        h_sc = torch.empty(nq, k, dtype=torch.float64).pin_memory()
+        pipe.step(qvs[i].cpu().pin_memory(), bm[i][0].pin_memory(), bm[i][1].pin_memory(), h_ids, h_sc)
+        outs.append((h_ids, h_sc))
+    pipe.drain()
+    torch.cuda.synchronize()
+    for i in range(6):
+        cnt = want[i][2].cpu().numpy()
+        wi, ws = want[i][0].cpu().numpy(), want[i][1].cpu().numpy()
+        for j in range(nq):
+            assert np.array_equal(outs[i][0].numpy()[j, :cnt[j]], wi[j, :cnt[j]])
+            assert outs[i][1].numpy()[j, :cnt[j]].tobytes() == ws[j, :cnt[j]].tobytes()
+
+
 # ----------------------------------------------------- widening ----
 def test_index_save_load_roundtrip(c1, tmp_path):
     ix = c1["index"]
