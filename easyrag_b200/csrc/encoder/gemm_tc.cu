@@ -34,16 +34,13 @@
 namespace ezr {
 
 constexpr int GM = 128, GN = 256, GK = 64;
-#ifndef EZR_GEMM_STAGES
-#define EZR_GEMM_STAGES 6
-#endif
-constexpr int G_STAGES = EZR_GEMM_STAGES;
+constexpr int G_STAGES_MAX = 6;     // TMA ring: 6 stages of 32 KB beside 8 epilogue warps, 5 beside 16 (their staging buffers)
 constexpr int G_ACC = 2;
-#ifndef EZR_GEMM_EPI_WARPS
-#define EZR_GEMM_EPI_WARPS 8
-#endif
-constexpr int G_EPI_WARPS = EZR_GEMM_EPI_WARPS;          // 8 or 16: G_EPI_WARPS / 4 warps share a TMEM lane quadrant, splitting the columns
-constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;         // TMA warp, MMA warp, epilogue warps
+// Epilogue warps: EW / 4 warps share a TMEM lane quadrant and split the tile's columns.  Measured per shape (M = 147k
+// rows, session 11): the plain epilogue is fastest with 8 warps + 6 ring stages (qkv 1380 vs 1324 TFLOP/s), the
+// GELU and SwiGLU epilogues -- whose math is what the tile waits for -- with 16 warps + 5 stages (1153 vs 1088, 1367 vs 996).
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 0 ? 8 : 16; }
+__host__ __device__ constexpr int ring_stages(int epi) { return epi == 0 ? 6 : 5; }
 constexpr int G_ST_BYTES = 32 * 32 * 2;                  // one epilogue warp's store staging: 32 rows x 32 bf16 columns
 constexpr int G_A_BYTES = GM * GK * 2;   // 16 KB
 constexpr int G_B_BYTES = (GN / 2) * GK * 2;   // 16 KB: this CTA's half of the 256-row W tile
@@ -54,7 +51,7 @@ enum { EPI_NONE = 0, EPI_GELU = 1, EPI_SWIGLU = 2 };
 struct GemmParams {
     int M, N, K;
     int kps;                         // k-chunks (64-wide TMA boxes) per pipeline stage: 1 or 2
-    int n_stages;                    // G_STAGES / kps
+    int n_stages;                    // ring stages / kps
     int tiles_m, tiles_n;
     const __nv_bfloat16* bias;       // [N] or null
     const __nv_bfloat16* residual;   // [M, ldr] or null
@@ -65,8 +62,8 @@ struct GemmParams {
 };
 
 struct GemmBarriers {
-    uint64_t full[G_STAGES];
-    uint64_t empty[G_STAGES];
+    uint64_t full[G_STAGES_MAX];
+    uint64_t empty[G_STAGES_MAX];
     uint64_t acc_full[G_ACC];
     uint64_t acc_empty[G_ACC];
     uint32_t tmem_base;
@@ -98,17 +95,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * epi_warps(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_o, const GemmParams p) {          // map_w: boxes of GN / 2 rows (this CTA's half of the W tile)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_a = smem;
+    constexpr int EW = epi_warps(EPI);
+    constexpr int G_STAGES = ring_stages(EPI);
     unsigned char* smem_b = smem + (size_t)G_STAGES * G_A_BYTES;
     unsigned char* smem_st = smem_b + (size_t)G_STAGES * G_B_BYTES;          // 1024-aligned: the rings are multiples of 16 KB
-    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_st + (size_t)G_EPI_WARPS * G_ST_BYTES);
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_st + (size_t)EW * G_ST_BYTES);
 
-    __shared__ float s_bias[G_EPI_WARPS][GN * 4 / G_EPI_WARPS];   // per epilogue warp: bias of its columns (x2 rows for SwiGLU)
+    __shared__ float s_bias[EW][GN * 4 / EW];   // per epilogue warp: bias of its columns (x2 rows for SwiGLU)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work = super-tiles of (two M tiles) x (one N tile), walked by cluster pairs; this CTA owns M tile 2 * sm + rank
     const int rank = (int)ptx::cluster_ctarank();
@@ -123,7 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ptx::prefetch_tensormap(&map_o);
         for (int i = 0; i < G_STAGES; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); }
         // acc_empty is only waited on in the leader: the epilogue warps of both CTAs of the pair arrive there
-        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], G_EPI_WARPS * G_CLUSTER); }
+        for (int i = 0; i < G_ACC; ++i) { ptx::mbar_init(&bars->acc_full[i], 1); ptx::mbar_init(&bars->acc_empty[i], EW * G_CLUSTER); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc_pair<G_ACC * GN>(&bars->tmem_base);
@@ -190,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ---------------- epilogue: G_EPI_WARPS warps, G_EPI_WARPS / 4 per TMEM lane quadrant, each owning a slice of the
+        // ---------------- epilogue: EW warps, EW / 4 per TMEM lane quadrant, each owning a slice of the
         // tile's columns.  A warp's 32 x 32 output block is packed to bf16 into its own shared-memory staging buffer
         // (TMA's 64-byte swizzle: conflict-free 16-byte writes) and leaves as ONE TMA store of full 64-byte row
         // segments; stores straight from the registers (one output row per lane, 16 bytes per instruction) touched 32
@@ -200,8 +199,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? GN / 64 : GN / 32;   // 32 output columns per chunk
-        constexpr int cpw = n_out_chunks / (G_EPI_WARPS / 4);                   // chunks per warp
-        static_assert(cpw >= 1 && (EPI == EPI_SWIGLU ? 2 : 1) * cpw * 32 <= GN * 4 / G_EPI_WARPS, "bias slice must fit s_bias");
+        constexpr int cpw = n_out_chunks / (EW / 4);                            // chunks per warp
+        static_assert(cpw >= 1 && (EPI == EPI_SWIGLU ? 2 : 1) * cpw * 32 <= GN * 4 / EW, "bias slice must fit s_bias");
         unsigned char* my_st = smem_st + (size_t)(warp - 2) * G_ST_BYTES;
         const int st_row = lane * 64, st_sw = (lane >> 1) & 3;                  // this lane's staging row, its swizzle
         float* sb = s_bias[warp - 2];                                           // this warp's bias slice
@@ -242,6 +241,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             };
             load_res(c0, rv);
+            // the NEXT tile's residual block of this lane's row: pull it into L2 now, a whole tile ahead (the loads
+            // above only run one chunk ahead, which covers an L2 hit but not a DRAM miss)
+            if (p.residual && t + n_pairs < n_tiles) {
+                const int t2 = t + n_pairs;
+                const int row2 = ((t2 / p.tiles_n) * 2 + rank) * GM + quad * 32 + lane;
+                const int oc2 = ((EPI == EPI_SWIGLU) ? (t2 % p.tiles_n) * (GN / 2) : (t2 % p.tiles_n) * GN) + c0 * 32;
+                if (row2 < p.M && oc2 < n_out) {
+                    const char* a2 = reinterpret_cast<const char*>(p.residual + (int64_t)row2 * p.ldr + oc2);
+#pragma unroll
+                    for (int off = 0; off < cpw * 64; off += 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a2 + off));
+                }
+            }
 
             ptx::mbar_wait(&bars->acc_full[as], aph);
             ptx::tc_fence_after();
@@ -376,7 +388,10 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     p.tiles_n = (N + GN - 1) / GN;
     p.bias = bias; p.residual = residual; p.ldr = ldr; p.out = out; p.ldo = ldo;
     p.kps = 1;            // 2 chunks per stage was measured slower (coarser producer/consumer hand-off)
-    p.n_stages = G_STAGES / p.kps;
+    const int stages = epi == EPI_NONE ? ring_stages(EPI_NONE) : ring_stages(EPI_GELU);
+    const int ew = epi == EPI_NONE ? epi_warps(EPI_NONE) : epi_warps(EPI_GELU);
+    static_assert(ring_stages(EPI_GELU) == ring_stages(EPI_SWIGLU) && epi_warps(EPI_GELU) == epi_warps(EPI_SWIGLU), "");
+    p.n_stages = stages / p.kps;
     const int n_out = epi == EPI_SWIGLU ? N / 2 : N;
     p.tma_out = (ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
     CUtensorMap map_a, map_w, map_o;
@@ -389,7 +404,7 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     if (p.tma_out) rc = encode_tmap_2d_bf16(&map_o, out, (uint64_t)n_out, (uint64_t)M, (uint64_t)ldo, 32, 32, 64);
     else map_o = map_a;
     if (rc) return rc;
-    const size_t smem = 1024 + (size_t)G_STAGES * (G_A_BYTES + G_B_BYTES) + (size_t)G_EPI_WARPS * G_ST_BYTES +
+    const size_t smem = 1024 + (size_t)stages * (G_A_BYTES + G_B_BYTES) + (size_t)ew * G_ST_BYTES +
                         sizeof(GemmBarriers) + 64;
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
     static const kern_t table[3] = {gemm_tc_kernel<EPI_NONE>, gemm_tc_kernel<EPI_GELU>, gemm_tc_kernel<EPI_SWIGLU>};
@@ -403,7 +418,7 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     if (n_super < pairs) pairs = n_super;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(pairs * G_CLUSTER));
-    cfg.blockDim = dim3(G_THREADS);
+    cfg.blockDim = dim3((unsigned)(64 + 32 * ew));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -228,6 +228,46 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const i
     }
 }
 
+// 16-byte form (head_dim % 16 == 0, 16-byte aligned rows): a thread rotates 8 (x1, x2) pairs of one head -- two
+// 16-byte loads of the row, one of cos, one of sin, two 16-byte stores; same rounding points as rope_kernel.
+__global__ void __launch_bounds__(256)
+rope_vec_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const int32_t* __restrict__ positions,
+                const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t, int max_pos,
+                int n_heads_qk, int head_dim, int n_tokens) {
+    const int half = head_dim >> 1, per_head = half >> 3, per_tok = n_heads_qk * per_head;
+    const int64_t n_items = (int64_t)n_tokens * per_tok;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(it / per_tok), e = (int)(it % per_tok);
+        const int h = e / per_head, i = (e % per_head) << 3;
+        int pp = __ldg(positions + t);
+        pp = pp < 0 ? 0 : (pp >= max_pos ? max_pos - 1 : pp);
+        __nv_bfloat16* p = qkv + (int64_t)t * ld + h * head_dim + i;
+        const uint4 u1 = *reinterpret_cast<const uint4*>(p), u2 = *reinterpret_cast<const uint4*>(p + half);
+        const uint4 uc = __ldg(reinterpret_cast<const uint4*>(cos_t + (int64_t)pp * half + i));
+        const uint4 us = __ldg(reinterpret_cast<const uint4*>(sin_t + (int64_t)pp * half + i));
+        const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(&u1);
+        const __nv_bfloat16* x2 = reinterpret_cast<const __nv_bfloat16*>(&u2);
+        const __nv_bfloat16* cc = reinterpret_cast<const __nv_bfloat16*>(&uc);
+        const __nv_bfloat16* ss = reinterpret_cast<const __nv_bfloat16*>(&us);
+        uint4 o1, o2;
+        __nv_bfloat16* y1 = reinterpret_cast<__nv_bfloat16*>(&o1);
+        __nv_bfloat16* y2 = reinterpret_cast<__nv_bfloat16*>(&o2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = __bfloat162float(x1[j]), b = __bfloat162float(x2[j]);
+            const float cf = __bfloat162float(cc[j]), sf = __bfloat162float(ss[j]);
+            const float a1 = __bfloat162float(__float2bfloat16(a * cf));
+            const float b1 = __bfloat162float(__float2bfloat16(-b * sf));
+            const float a2 = __bfloat162float(__float2bfloat16(b * cf));
+            const float b2 = __bfloat162float(__float2bfloat16(a * sf));
+            y1[j] = __float2bfloat16(a1 + b1);
+            y2[j] = __float2bfloat16(a2 + b2);
+        }
+        *reinterpret_cast<uint4*>(p) = o1;
+        *reinterpret_cast<uint4*>(p + half) = o2;
+    }
+}
+
 // ---------------------------------------------------------------- pooling + (final norm) + L2 normalise (K9, K10)
 // pool: 0 = last token (gte_embeddings.py:42-50), 1 = first token / CLS, 2 = mean over tokens.
 // final_norm: 0 none, 1 RMSNorm with `gamma` (Qwen2Model.norm applied only to the pooled row: it is per-token).
@@ -346,6 +386,16 @@ int ezr_rope(void* qkv, int64_t ld, const int32_t* positions, const void* cos_ta
     if (n_tokens == 0) return EZR_OK;
     EZR_CHECK_ARG(head_dim % 2 == 0, "rope: head_dim must be even");
     ProfScope prof(EZR_PROF_ENC_OTHER, (cudaStream_t)stream);
+    if (head_dim % 16 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+        ((reinterpret_cast<uintptr_t>(cos_table) | reinterpret_cast<uintptr_t>(sin_table)) & 15) == 0) {
+        const int64_t n_items = (int64_t)n_tokens * n_heads_qk * (head_dim / 16);
+        const int64_t want = (n_items + 255) / 256, cap = (int64_t)sm_count() * 32;
+        rope_vec_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+            (__nv_bfloat16*)qkv, ld, positions, (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table, max_pos,
+            n_heads_qk, head_dim, n_tokens);
+        EZR_LAUNCH_CHECK();
+        return EZR_OK;
+    }
     rope_kernel<<<n_tokens, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv, ld, positions,
                                                             (const __nv_bfloat16*)cos_table,
                                                             (const __nv_bfloat16*)sin_table, max_pos, n_heads_qk,

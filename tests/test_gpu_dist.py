@@ -59,6 +59,30 @@ def _worker(rank, world, port, ret):
                 for a, b in ((f, f1), (s, s1), (d, d1)):
                     ok &= torch.equal(a.ids, b.ids) and torch.equal(a.counts, b.counts)
                     ok &= a.scores.cpu().numpy().tobytes() == b.scores.cpu().numpy().tobytes()
+        # submitted (pipelined) batches: four different batches in flight over two result slots, never joined to the
+        # caller's stream, must equal the joined path batch by batch
+        ranker_o = batched.CoarseRanker(ranker.dense, ranker.sparse, canon=canon, overlap=True)
+        sh_o = ezdist.ShardedCoarseRanker(ranker_o)
+        qd = qv.to(dev)
+        batches = [torch.roll(qd, 7 * i, 0).contiguous() for i in range(4)]
+        want_f = []
+        for b in batches:
+            f, _, _ = sharded.hybrid(b, args[1], args[2], k=k, k_out=k)
+            want_f.append((f.ids.clone(), f.scores.clone(), f.counts.clone()))
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(device=dev)
+        got_f = []
+        for b in batches:
+            t = sh_o.submit(b, args[1], args[2], k=k, k_out=k)
+            with torch.cuda.stream(side):
+                t.wait(side)
+                got_f.append((t.fused.ids.clone(), t.fused.scores.clone(), t.fused.counts.clone()))
+                t.release(side)
+        sh_o.join()
+        torch.cuda.synchronize()
+        for a, b in zip(got_f, want_f):
+            ok &= all(torch.equal(x, y) for x, y in zip(a, b))
+        ok &= not torch.equal(want_f[0][0], want_f[1][0])
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -190,6 +190,28 @@ def test_rmsnorm_layernorm():
            F.layer_norm(x.float(), (768,), g.float(), b.float(), 1e-12), rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("hd", [64, 128, 8])        # 16-byte path (two head sizes) and the scalar path
+def test_rope_matches_bf16_tensor_ops(hd):
+    L = _lib.lib()
+    t, h_qk, h_v, max_pos = 77, 5, 2, 64
+    half = hd // 2
+    qkv = _rand(t, (h_qk + h_v) * hd, seed=hd)
+    pos = torch.randint(0, 50, (t,), dtype=torch.int32, generator=torch.Generator().manual_seed(3))
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd))
+    fr = torch.arange(max_pos).float()[:, None] * inv[None]
+    cos, sin = fr.cos().to(torch.bfloat16).contiguous(), fr.sin().to(torch.bfloat16).contiguous()
+    x = qkv.to(DEV).clone()
+    _lib.check(L.ezr_rope(_lib.ptr(x), x.stride(0), _lib.ptr(pos.to(DEV)), _lib.ptr(cos.to(DEV)), _lib.ptr(sin.to(DEV)),
+                          max_pos, h_qk, hd, t, _lib.stream_ptr()), "ezr_rope")
+    # q * cos + rotate_half(q) * sin on bf16 tensors: every product and the sum are rounded to bf16
+    q = qkv[:, :h_qk * hd].view(t, h_qk, hd)
+    c, sn = cos[pos.long()][:, None, :], sin[pos.long()][:, None, :]
+    x1, x2 = q[..., :half], q[..., half:]
+    ref = qkv.clone()
+    ref[:, :h_qk * hd] = torch.cat([x1 * c + (-x2) * sn, x2 * c + x1 * sn], -1).reshape(t, -1)
+    assert torch.equal(x.cpu(), ref)                        # V columns untouched, Q/K columns bit-exact
+
+
 def test_pool_normalize_modes():
     L = _lib.lib()
     lens = [3, 1, 17]
