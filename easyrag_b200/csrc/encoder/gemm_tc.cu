@@ -20,10 +20,12 @@
 // the L2, the weights (a few MB) do: with M fastest every N tile re-streamed all of A from HBM (9x for the QKV
 // projection); with N fastest the CTAs in flight cover ~16 M tiles x all N tiles, so an A tile is fetched from HBM once.
 //
-// Persistent, warp-specialised: warp 0 = TMA producer (4-stage ring of 128x64 A and 256x64 W tiles),
-// warp 1 = tcgen05.mma issuer (128x256x16, fp32 accumulate into one of two 256-column TMEM stages; the 128x256
-// tile halves L2->SM operand traffic per flop versus 128x128, which measured L2-bound), warps 2-5 = epilogue (tcgen05.ld, one output row per thread, bias / GELU / SwiGLU / residual in
-// fp32, bf16 pack, 16-byte global stores) overlapping the next tile's MMAs.
+// Persistent, warp-specialised: warp 0 = TMA producer (ring of 128x64 A tiles and 128x64 W half-tiles, 6 or 5 stages),
+// warp 1 = tcgen05.mma issuer (leader CTA only; 256x256x16 per instruction over the pair, fp32 accumulation into one of
+// two 256-column TMEM stages), warps 2.. = epilogue (8 warps for the plain form, 16 for GELU / SwiGLU): tcgen05.ld with
+// one output row per thread, bias / GELU / SwiGLU / residual in fp32, bf16 blocks through a swizzled shared-memory
+// staging buffer and TMA stores, overlapping the next tile's MMAs.  Shared memory is used to the last KB
+// (ring + staging + bias slices + barriers = 231.6 KB of the 227 KB opt-in limit's 232,448 bytes).
 #include "../ezr_common.cuh"
 #include "../ptx.cuh"
 
@@ -40,8 +42,13 @@ constexpr int G_ACC = 2;
 // rows, session 11): the plain epilogue is fastest with 8 warps + 6 ring stages (qkv 1380 vs 1324 TFLOP/s), the
 // GELU and SwiGLU epilogues -- whose math is what the tile waits for -- with 16 warps + 5 stages (1153 vs 1088, 1367 vs 996).
 __host__ __device__ constexpr int epi_warps(int epi) { return epi == 0 ? 8 : 16; }
-__host__ __device__ constexpr int ring_stages(int epi) { return epi == 0 ? 6 : 5; }
-constexpr int G_ST_BYTES = 32 * 32 * 2;                  // one epilogue warp's store staging: 32 rows x 32 bf16 columns
+#ifndef EZR_GEMM_PLAIN_STAGES
+#define EZR_GEMM_PLAIN_STAGES 6      // tuning switch (variant builds)
+#endif
+__host__ __device__ constexpr int ring_stages(int epi) { return epi == 0 ? EZR_GEMM_PLAIN_STAGES : 5; }
+// epilogue staging (all warps): what the ring leaves of the 227 KB -- 32 KB beside 6 stages, 64 KB beside 5
+__host__ __device__ constexpr int staging_bytes(int stages) { return stages >= 6 ? 32768 : 65536; }
+constexpr int G_BIAS_BYTES = 2048;                       // bf16 bias slices of the epilogue warps
 constexpr int G_A_BYTES = GM * GK * 2;   // 16 KB
 constexpr int G_B_BYTES = (GN / 2) * GK * 2;   // 16 KB: this CTA's half of the 256-row W tile
 constexpr int G_CLUSTER = 2;             // CTAs of a pair
@@ -59,6 +66,7 @@ struct GemmParams {
     __nv_bfloat16* out;              // [M, ldo]
     int64_t ldo;
     int tma_out;                     // 1: the output goes through shared memory and TMA stores (ldo % 8 == 0, 16-byte aligned)
+    int smem_slack;                  // bytes the launch could spare for aligning the dynamic shared memory to 1024
 };
 
 struct GemmBarriers {
@@ -98,16 +106,18 @@ template <int EPI>
 __global__ void __launch_bounds__(64 + 32 * epi_warps(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_o, const GemmParams p) {          // map_w: boxes of GN / 2 rows (this CTA's half of the W tile)
-    extern __shared__ unsigned char smem_dyn[];
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_a = smem;
     constexpr int EW = epi_warps(EPI);
     constexpr int G_STAGES = ring_stages(EPI);
     unsigned char* smem_b = smem + (size_t)G_STAGES * G_A_BYTES;
+    constexpr int G_ST_TOTAL = staging_bytes(G_STAGES);
     unsigned char* smem_st = smem_b + (size_t)G_STAGES * G_B_BYTES;          // 1024-aligned: the rings are multiples of 16 KB
-    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_st + (size_t)EW * G_ST_BYTES);
-
-    __shared__ float s_bias[EW][GN * 4 / EW];   // per epilogue warp: bias of its columns (x2 rows for SwiGLU)
+    __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem_st + G_ST_TOTAL);
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_st + G_ST_TOTAL + G_BIAS_BYTES);
+    // the layout fills the 227 KB: the alignment slack is whatever the launch could spare (p.smem_slack)
+    if (threadIdx.x == 0 && (size_t)(smem - smem_dyn) > (size_t)p.smem_slack) __trap();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work = super-tiles of (two M tiles) x (one N tile), walked by cluster pairs; this CTA owns M tile 2 * sm + rank
     const int rank = (int)ptx::cluster_ctarank();
@@ -189,61 +199,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ---------------- epilogue: EW warps, EW / 4 per TMEM lane quadrant, each owning a slice of the
-        // tile's columns.  A warp's 32 x 32 output block is packed to bf16 into its own shared-memory staging buffer
-        // (TMA's 64-byte swizzle: conflict-free 16-byte writes) and leaves as ONE TMA store of full 64-byte row
-        // segments; stores straight from the registers (one output row per lane, 16 bytes per instruction) touched 32
-        // half-filled sectors per instruction and were measured as the limit of every K = 768 shape.
-        // Global-memory latency is kept off the critical path: the bias slice is staged in shared memory BEFORE the
-        // accumulator wait, and the residual of chunk c+1 is in flight while chunk c is processed.
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        // ---------------- epilogue: EW warps, EW / 4 per TMEM lane quadrant, each owning a slice of the tile's columns.
+        // A warp works in BLOCKS of 32 rows x BW columns (BW = 64, or 32 when the slice is that narrow): the
+        // accumulator chunks are read from tensor memory (one row per lane), bias / GELU / SwiGLU / residual applied
+        // in fp32, the block packed to bf16 into the warp's staging buffer -- laid out in the TMA swizzle of the block's
+        // row width, so every 16-byte shared-memory access is conflict-free -- and written by ONE TMA store of full
+        // 64/128-byte row segments.  (Stores straight from the registers, one output row per lane and 16 bytes per
+        // instruction, touch 32 half-filled sectors per instruction and were measured as the limit of every K = 768
+        // shape: profiles/R2j_*.)  The residual takes the same road backwards: a COALESCED load (LPR lanes per row)
+        // into registers one block ahead, through the staging buffer, read back row-per-lane -- the row-per-lane global
+        // load it replaces cost 32 L1 wavefronts per instruction.  With NB = 2 staging buffers the store of block k
+        // drains under block k + 1.
         constexpr int n_out_chunks = (EPI == EPI_SWIGLU) ? GN / 64 : GN / 32;   // 32 output columns per chunk
-        constexpr int cpw = n_out_chunks / (EW / 4);                            // chunks per warp
-        static_assert(cpw >= 1 && (EPI == EPI_SWIGLU ? 2 : 1) * cpw * 32 <= GN * 4 / EW, "bias slice must fit s_bias");
-        unsigned char* my_st = smem_st + (size_t)(warp - 2) * G_ST_BYTES;
-        const int st_row = lane * 64, st_sw = (lane >> 1) & 3;                  // this lane's staging row, its swizzle
-        float* sb = s_bias[warp - 2];                                           // this warp's bias slice
+        constexpr int cpw = n_out_chunks / (EW / 4);                            // chunks per warp and tile
+        constexpr int BW = cpw >= 2 ? 64 : 32;
+        constexpr int SUB = BW / 32, NBLK = cpw / SUB;
+        constexpr int ROWB = BW * 2, BUFB = 32 * ROWB;
+        constexpr int ST_W = G_ST_TOTAL / EW, NB = ST_W / BUFB;
+        constexpr int LPR = BW / 8, RPI = 32 / LPR;                             // residual load: lanes per row, rows per instruction
+        constexpr bool kResStage = (EW == 8);            // the 16-warp forms (96 registers) keep the direct residual path
+        constexpr int kBiasPerWarp = cpw * 32 * (EPI == EPI_SWIGLU ? 2 : 1);
+        static_assert(NB >= 1 && NB <= 2 && cpw % SUB == 0 && kBiasPerWarp * EW * 2 <= G_BIAS_BYTES, "epilogue layout");
+        const int ew = warp - 2, quad = warp & 3, part = ew >> 2;
+        unsigned char* st0 = smem_st + (size_t)ew * ST_W;
+        __nv_bfloat16* sb = s_bias + ew * kBiasPerWarp;
         const int n_out = (EPI == EPI_SWIGLU) ? p.N / 2 : p.N;
-        int it = 0;
+        const int sw_own = BW == 64 ? (lane & 7) : ((lane >> 1) & 3);           // swizzle term of this lane's own row
+        const int ld_row = lane / LPR, ld_ch = lane % LPR;
+        const bool res_on = p.residual != nullptr;
+        const bool res_stage = kResStage && res_on && p.tma_out && (p.ldr % 8 == 0) && (n_out % 8 == 0) &&
+                               ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+        int it = 0, seq = 0;                             // seq: blocks this warp has staged (buffer = seq % NB)
         for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
             const int tn = t % p.tiles_n, tm = (t / p.tiles_n) * 2 + rank;     // N tiles fastest: see the header
             const int as = it % G_ACC;
             const uint32_t aph = (uint32_t)(it / G_ACC) & 1u;
-            const int row = tm * GM + quad * 32 + lane;
+            const int row0 = tm * GM + quad * 32;
+            const int row = row0 + lane;
             const bool row_ok = row < p.M;
-            const int c0 = half * cpw;
-            // bias: columns [gc0, gc0 + cpw*32) (and the matching "up" columns for SwiGLU) -> sb[0 .. cpw*32 (*2))
+            const int c0 = part * cpw;
+            const int ocol_base = (EPI == EPI_SWIGLU) ? tn * (GN / 2) : tn * GN;
+            // bias: columns [c0 * 32, (c0 + cpw) * 32) of the tile (and the matching "up" columns for SwiGLU), as bf16
             if (p.bias) {
                 __syncwarp();
                 for (int i = lane; i < cpw * 32; i += 32) {
                     const int col = tn * GN + c0 * 32 + i;
-                    sb[i] = col < p.N ? __bfloat162float(__ldg(p.bias + col)) : 0.f;
+                    sb[i] = col < p.N ? p.bias[col] : __float2bfloat16(0.f);
                     if (EPI == EPI_SWIGLU) {
                         const int col2 = col + GN / 2;
-                        sb[cpw * 32 + i] = col2 < p.N ? __bfloat162float(__ldg(p.bias + col2)) : 0.f;
+                        sb[cpw * 32 + i] = col2 < p.N ? p.bias[col2] : __float2bfloat16(0.f);
                     }
                 }
                 __syncwarp();
             }
-            // residual of the first chunk
-            uint4 rv[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u),
-                           make_uint4(0u, 0u, 0u, 0u)};
-            const int ocol_base = (EPI == EPI_SWIGLU) ? tn * (GN / 2) : tn * GN;
-            const bool res_vec = p.residual && row_ok && (p.ldr % 8 == 0) &&
-                                 ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-            auto load_res = [&](int c, uint4 (&dst)[4]) {
-                const int oc = ocol_base + c * 32;
-                if (res_vec && oc + 32 <= n_out) {
-                    const uint4* rr = reinterpret_cast<const uint4*>(p.residual + (int64_t)row * p.ldr + oc);
+            uint4 rn[LPR];
+            auto load_res = [&](int tile_ocol_base, int tile_row0, int b) {
+                const int oc = tile_ocol_base + (c0 + b * SUB) * 32 + ld_ch * 8;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dst[j] = rr[j];
+                for (int i = 0; i < LPR; ++i) {
+                    const int r = tile_row0 + ld_row + i * RPI;
+                    rn[i] = (r < p.M && oc + 8 <= n_out)
+                                ? __ldg(reinterpret_cast<const uint4*>(p.residual + (int64_t)r * p.ldr + oc))
+                                : make_uint4(0u, 0u, 0u, 0u);
                 }
             };
-            load_res(c0, rv);
-            // the NEXT tile's residual block of this lane's row: pull it into L2 now, a whole tile ahead (the loads
-            // above only run one chunk ahead, which covers an L2 hit but not a DRAM miss)
-            if (p.residual && t + n_pairs < n_tiles) {
+            if (kResStage && res_stage) load_res(ocol_base, row0, 0);
+            // the NEXT tile's residual block of this lane's row: pull it into L2 now, a whole tile ahead (the register
+            // loads run one block ahead, which covers an L2 hit but not a DRAM miss)
+            if (res_on && t + n_pairs < n_tiles) {
                 const int t2 = t + n_pairs;
                 const int row2 = ((t2 / p.tiles_n) * 2 + rank) * GM + quad * 32 + lane;
                 const int oc2 = ((EPI == EPI_SWIGLU) ? (t2 % p.tiles_n) * (GN / 2) : (t2 % p.tiles_n) * GN) + c0 * 32;
@@ -265,100 +288,148 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             continue;
 #endif
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * GN);
-            // NOT unrolled: inlined copies of the 32-wide body are >130 KB of SASS (230 KB with GELU) and stream
+            // NOT unrolled: inlined copies of the block body are >130 KB of SASS (230 KB with GELU) and stream
             // through the instruction cache on every tile.
 #pragma unroll 1
-            for (int ci = 0; ci < cpw; ++ci) {
-                const int c = c0 + ci;
-                uint32_t r[32];
-                float v[32];
-                uint4 rn[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u),
-                               make_uint4(0u, 0u, 0u, 0u)};
-                ptx::tmem_ld_32x32(taddr + c * 32, r);
-                if (ci + 1 < cpw) load_res(c + 1, rn);                 // next chunk's residual: in flight from here
-                if (EPI == EPI_SWIGLU) {
-                    uint32_t r2[32];
-                    ptx::tmem_ld_32x32(taddr + GN / 2 + c * 32, r2);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float g = __uint_as_float(r[j]), u = __uint_as_float(r2[j]);
-                        if (p.bias) { g += sb[ci * 32 + j]; u += sb[cpw * 32 + ci * 32 + j]; }
-                        v[j] = silu(g) * u;
-                    }
-                } else {
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(r[j]);
-                        if (p.bias) x += sb[ci * 32 + j];
-                        if (EPI == EPI_GELU) x = gelu_erf(x);
-                        v[j] = x;
-                    }
-                }
-                if (ci == cpw - 1) {
-                    ptx::tc_fence_before();
+            for (int b = 0; b < NBLK; ++b, ++seq) {
+                unsigned char* buf = st0 + (size_t)(seq % NB) * BUFB;
+                const int cb = c0 + b * SUB;
+                const int ocol = ocol_base + cb * 32;
+                const bool live = ocol < n_out;          // warp-uniform: the block has columns inside the output
+                bool buf_free = false;
+                if (kResStage && res_stage && live) {
+                    // the buffer is free once the store that last used it has READ it (not: reached memory)
+                    if (lane == 0) ptx::tma_store_wait_read<NB - 1>();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_remote(&bars->acc_empty[as], 0u);      // the leader's barrier
-                }
-                const int ocol = ocol_base + c * 32;
-                if (p.residual && row_ok && ocol < n_out) {
-                    if (res_vec && ocol + 32 <= n_out) {
-                        const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(rv);
+                    buf_free = true;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(rh[j]);
-                    } else {
-                        const __nv_bfloat16* rr = p.residual + (int64_t)row * p.ldr + ocol;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (ocol + j < n_out) v[j] += __bfloat162float(rr[j]);
+                    for (int i = 0; i < LPR; ++i) {
+                        const int r = ld_row + i * RPI;
+                        const int swz = BW == 64 ? (r & 7) : ((r >> 1) & 3);
+                        *reinterpret_cast<uint4*>(buf + r * ROWB + ((ld_ch ^ swz) << 4)) = rn[i];
                     }
+                    __syncwarp();
+                }
+                uint32_t pk[SUB][16];
+#pragma unroll
+                for (int sidx = 0; sidx < SUB; ++sidx) {
+                    const int ci = b * SUB + sidx;       // chunk within this warp's slice
+                    const int c = c0 + ci;
+                    uint32_t r[32];
+                    float v[32];
+                    ptx::tmem_ld_32x32(taddr + c * 32, r);
+                    if (kResStage && sidx == 0 && res_stage && b + 1 < NBLK) load_res(ocol_base, row0, b + 1);
+                    if (EPI == EPI_SWIGLU) {
+                        uint32_t r2[32];
+                        ptx::tmem_ld_32x32(taddr + GN / 2 + c * 32, r2);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            uint4 bg = make_uint4(0u, 0u, 0u, 0u), bu = make_uint4(0u, 0u, 0u, 0u);
+                            if (p.bias) {
+                                bg = *reinterpret_cast<const uint4*>(sb + ci * 32 + j8 * 8);
+                                bu = *reinterpret_cast<const uint4*>(sb + cpw * 32 + ci * 32 + j8 * 8);
+                            }
+                            const __nv_bfloat16* hg = reinterpret_cast<const __nv_bfloat16*>(&bg);
+                            const __nv_bfloat16* hu = reinterpret_cast<const __nv_bfloat16*>(&bu);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float g = __uint_as_float(r[j8 * 8 + j]) + __bfloat162float(hg[j]);
+                                const float u = __uint_as_float(r2[j8 * 8 + j]) + __bfloat162float(hu[j]);
+                                v[j8 * 8 + j] = silu(g) * u;
+                            }
+                        }
+                    } else {
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            uint4 b4 = make_uint4(0u, 0u, 0u, 0u);
+                            if (p.bias) b4 = *reinterpret_cast<const uint4*>(sb + ci * 32 + j8 * 8);
+                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&b4);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float x = __uint_as_float(r[j8 * 8 + j]) + __bfloat162float(hb[j]);
+                                if (EPI == EPI_GELU) x = gelu_erf(x);
+                                v[j8 * 8 + j] = x;
+                            }
+                        }
+                    }
+                    if (b == NBLK - 1 && sidx == SUB - 1) {          // the tile's last read of tensor memory
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive_remote(&bars->acc_empty[as], 0u);      // the leader's barrier
+                    }
+                    const int oc_s = ocol + sidx * 32;
+                    if (kResStage && res_stage) {
+                        if (live) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const uint4 q4 = *reinterpret_cast<const uint4*>(buf + lane * ROWB + (((sidx * 4 + j4) ^ sw_own) << 4));
+                                const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(&q4);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j4 * 8 + j] += __bfloat162float(rh[j]);
+                            }
+                        }
+                    } else if (res_on && row_ok && oc_s < n_out) {
+                        const __nv_bfloat16* rr = p.residual + (int64_t)row * p.ldr + oc_s;
+                        if (oc_s + 32 <= n_out && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(rr) & 15) == 0)) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(rr) + j4);
+                                const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(&q4);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j4 * 8 + j] += __bfloat162float(rh[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (oc_s + j < n_out) v[j] += __bfloat162float(rr[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[sidx][j] = pack_bf16(v[2 * j], v[2 * j + 1]);
                 }
 #if EZR_GEMM_PROBE == 1
                 if (p.M < 0) {                                  // tuning probe: the epilogue's math without its stores
 #else
                 if (p.tma_out) {
 #endif
-                    if (ocol < n_out) {                          // warp-uniform
-                        // the staging buffer is free once the previous store has READ it (not: reached memory)
-                        if (lane == 0) ptx::tma_store_wait_read<0>();
-                        __syncwarp();
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint4 pk;
-                            pk.x = pack_bf16(v[j4 * 8], v[j4 * 8 + 1]);
-                            pk.y = pack_bf16(v[j4 * 8 + 2], v[j4 * 8 + 3]);
-                            pk.z = pack_bf16(v[j4 * 8 + 4], v[j4 * 8 + 5]);
-                            pk.w = pack_bf16(v[j4 * 8 + 6], v[j4 * 8 + 7]);
-                            *reinterpret_cast<uint4*>(my_st + st_row + ((j4 ^ st_sw) << 4)) = pk;
+                    if (live) {
+                        if (!buf_free) {
+                            if (lane == 0) ptx::tma_store_wait_read<NB - 1>();
+                            __syncwarp();
                         }
+#pragma unroll
+                        for (int sidx = 0; sidx < SUB; ++sidx)
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4)
+                                *reinterpret_cast<uint4*>(buf + lane * ROWB + (((sidx * 4 + j4) ^ sw_own) << 4)) =
+                                    make_uint4(pk[sidx][j4 * 4], pk[sidx][j4 * 4 + 1], pk[sidx][j4 * 4 + 2], pk[sidx][j4 * 4 + 3]);
                         ptx::fence_proxy_async();                // generic-proxy writes -> visible to the TMA engine
                         __syncwarp();
                         if (lane == 0) {                         // rows past M and columns past n_out are clipped by the map
-                            ptx::tma_store_2d(&map_o, my_st, ocol, tm * GM + quad * 32);
+                            ptx::tma_store_2d(&map_o, buf, ocol, row0);
                             ptx::tma_store_commit();
                         }
                     }
-                } else if (row_ok && ocol < n_out) {
-                    __nv_bfloat16* op = p.out + (int64_t)row * p.ldo + ocol;
-                    if (ocol + 32 <= n_out && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+                } else if (row_ok && live) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            pk.x = pack_bf16(v[j], v[j + 1]);
-                            pk.y = pack_bf16(v[j + 2], v[j + 3]);
-                            pk.z = pack_bf16(v[j + 4], v[j + 5]);
-                            pk.w = pack_bf16(v[j + 6], v[j + 7]);
-                            *reinterpret_cast<uint4*>(op + j) = pk;
+                    for (int sidx = 0; sidx < SUB; ++sidx) {
+                        const int oc_s = ocol + sidx * 32;
+                        __nv_bfloat16* op = p.out + (int64_t)row * p.ldo + oc_s;
+                        if (oc_s + 32 <= n_out && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4)
+                                *reinterpret_cast<uint4*>(op + j4 * 8) =
+                                    make_uint4(pk[sidx][j4 * 4], pk[sidx][j4 * 4 + 1], pk[sidx][j4 * 4 + 2], pk[sidx][j4 * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (oc_s + j < n_out)
+                                    op[j] = reinterpret_cast<const __nv_bfloat16*>(&pk[sidx][j >> 1])[j & 1];
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (ocol + j < n_out) op[j] = __float2bfloat16(v[j]);
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rv[j] = rn[j];
             }
         }
         if (lane == 0) ptx::tma_store_wait<0>();         // this warp's stores have left shared memory and are complete
@@ -399,13 +470,19 @@ static int gemm_launch(const __nv_bfloat16* A, int M, int K, int64_t lda, const 
     if (rc) return rc;
     rc = encode_tmap_2d_bf16(&map_w, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GK, GN / G_CLUSTER);
     if (rc) return rc;
-    // output map: boxes of 32 columns x 32 rows (one epilogue warp's block), 64-byte swizzle.  Without TMA stores the
-    // kernel never touches it; it is then encoded over A so that the argument stays a valid descriptor.
-    if (p.tma_out) rc = encode_tmap_2d_bf16(&map_o, out, (uint64_t)n_out, (uint64_t)M, (uint64_t)ldo, 32, 32, 64);
+    // output map: boxes of BW columns x 32 rows (one epilogue warp's block), swizzle = the block's row bytes.  Without
+    // TMA stores the kernel never touches it; it is then encoded over A so that the argument stays a valid descriptor.
+    const int cpw = (epi == EPI_SWIGLU ? GN / 64 : GN / 32) / (ew / 4);
+    const int bw = cpw >= 2 ? 64 : 32;                    // block width of the kernel's epilogue (see there)
+    if (p.tma_out) rc = encode_tmap_2d_bf16(&map_o, out, (uint64_t)n_out, (uint64_t)M, (uint64_t)ldo, (uint32_t)bw, 32, bw * 2);
     else map_o = map_a;
     if (rc) return rc;
-    const size_t smem = 1024 + (size_t)stages * (G_A_BYTES + G_B_BYTES) + (size_t)ew * G_ST_BYTES +
-                        sizeof(GemmBarriers) + 64;
+    const size_t need = (size_t)stages * (G_A_BYTES + G_B_BYTES) + (size_t)staging_bytes(stages) + G_BIAS_BYTES +
+                        sizeof(GemmBarriers);
+    const size_t kMaxSmem = 232448;                       // 227 KB opt-in limit of sm_100
+    EZR_CHECK_ARG(need <= kMaxSmem, "gemm: shared-memory layout of %zu bytes does not fit", need);
+    p.smem_slack = (int)(kMaxSmem - need < 1023 ? kMaxSmem - need : 1023);
+    const size_t smem = need + (size_t)p.smem_slack;
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
     static const kern_t table[3] = {gemm_tc_kernel<EPI_NONE>, gemm_tc_kernel<EPI_GELU>, gemm_tc_kernel<EPI_SWIGLU>};
     static bool attr_done[3] = {false, false, false};

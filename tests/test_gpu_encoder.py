@@ -201,8 +201,10 @@ def test_rope_matches_bf16_tensor_ops(hd):
     fr = torch.arange(max_pos).float()[:, None] * inv[None]
     cos, sin = fr.cos().to(torch.bfloat16).contiguous(), fr.sin().to(torch.bfloat16).contiguous()
     x = qkv.to(DEV).clone()
-    _lib.check(L.ezr_rope(_lib.ptr(x), x.stride(0), _lib.ptr(pos.to(DEV)), _lib.ptr(cos.to(DEV)), _lib.ptr(sin.to(DEV)),
+    d_pos, d_cos, d_sin = pos.to(DEV), cos.to(DEV), sin.to(DEV)         # named: the pointers must outlive the launch
+    _lib.check(L.ezr_rope(_lib.ptr(x), x.stride(0), _lib.ptr(d_pos), _lib.ptr(d_cos), _lib.ptr(d_sin),
                           max_pos, h_qk, hd, t, _lib.stream_ptr()), "ezr_rope")
+    torch.cuda.synchronize()
     # q * cos + rotate_half(q) * sin on bf16 tensors: every product and the sum are rounded to bf16
     q = qkv[:, :h_qk * hd].view(t, h_qk, hd)
     c, sn = cos[pos.long()][:, None, :], sin[pos.long()][:, None, :]
