@@ -73,6 +73,10 @@ def parse():
     ap.add_argument("--dense-kernel", type=int, default=0,
                     help="0 auto, 1 simt, 2 tcgen05 SS, 3 tcgen05 TS (N=64), 4 TS (N=128), 5 TS128 in cluster pairs (multicast)")
     ap.add_argument("--overlap", type=int, default=1, help="1 (default): dense and BM25 routes on two streams")
+    ap.add_argument("--bm25-span", type=int, default=4, help="document ranges in the first candidate launch (tuning)")
+    ap.add_argument("--serial-routes", type=int, default=0,
+                    help="1 (with --overlap 1 --pipeline 1): both routes on ONE side stream, dense kernel with its full "
+                         "shared-memory ring (cluster-pair form); the join still runs under the next step's routes")
     ap.add_argument("--pipeline", type=int, default=1,
                     help="1 (default, needs --overlap 1): steps are submitted, not joined -- the join of step i (all-gather, "
                          "merges, RRF) runs under the route kernels of step i+1; 0: every step joins the caller's stream")
@@ -367,13 +371,15 @@ def run_ours(args):
     L = _lib.lib()
     small_batch = args.queries <= 512
     overlap = bool(args.overlap)
-    stage_cap = args.dense_stages if args.dense_stages >= 0 else (3 if overlap and not small_batch else 0)
+    serial_routes = bool(args.serial_routes) and overlap and bool(args.pipeline)
+    stage_cap = args.dense_stages if args.dense_stages >= 0 else (3 if overlap and not small_batch and not serial_routes else 0)
     l2_flush = bool(args.l2_flush) if args.l2_flush >= 0 else small_batch
     _lib.check(L.ezr_dense_set_kernel(args.dense_kernel))
     _lib.check(L.ezr_dense_set_stage_cap(stage_cap))
     _lib.check(L.ezr_dense_set_probe(args.dense_probe))
     _lib.check(L.ezr_bm25_set_skipping(args.bm25_skip))
     _lib.check(L.ezr_bm25_set_plan(args.bm25_plan))
+    _lib.check(L.ezr_bm25_set_span(args.bm25_span))
 
     data = make_data(args, dev)
     lo, hi = ezdist.shard_bounds(args.rows, world, rank, align=64)
@@ -382,7 +388,7 @@ def run_ours(args):
     dense = DenseIndex(data["vec"][lo:hi], device=dev, row_lo=lo)
     torch.cuda.synchronize()
     build_s = time.time() - t0
-    ranker = batched.CoarseRanker(dense, sparse, canon=None, overlap=overlap)
+    ranker = batched.CoarseRanker(dense, sparse, canon=None, overlap=overlap, serial_routes=serial_routes)
     ranker_seq = batched.CoarseRanker(dense, sparse, canon=None, overlap=False)       # calibration: one stream
     sharded = ezdist.ShardedCoarseRanker(ranker) if world > 1 else None
     sharded_seq = ezdist.ShardedCoarseRanker(ranker_seq) if world > 1 else None
@@ -672,7 +678,7 @@ def run_ours(args):
                    "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "queries_per_step": args.queries,
                    "k": k, "rrf_K": 60, "tokens": data["n_tokens"], "postings_local": postings_local,
                    "queries_per_corpus_pass": min(args.queries, 128), "routes_overlapped": overlap,
-                   "steps_pipelined": pipelined,
+                   "steps_pipelined": pipelined, "routes_serial_on_side_stream": serial_routes,
                    "dense_ring_stages_cap": stage_cap, "timed_region_starts_from": "query vectors + term ids",
                    "l2": ("explicit flush: 512 MB written between steps, every step timed on its own" if l2_flush else
                           "inputs larger than L2 (corpus shard and postings >> 126 MB), no explicit flush"),

@@ -60,6 +60,7 @@ SIGNATURES = {
     "ezr_bm25_term_max": (C.c_int, [_p, _p, _i32, _p, _p]),
     "ezr_bm25_set_skipping": (C.c_int, [_i32]),
     "ezr_bm25_set_plan": (C.c_int, [_i32]),
+    "ezr_bm25_set_span": (C.c_int, [_i32]),
     "ezr_bm25_cand_capacity": (C.c_int, []),
     "ezr_bm25_topk_workspace": (_sz, [_IX, _i32, _i32]),
     "ezr_bm25_topk": (C.c_int, [_IX, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p, _sz, _p]),

@@ -243,12 +243,15 @@ class CoarseRanker:
     """
 
     def __init__(self, dense: DenseIndex, sparse: Bm25Index, canon: Optional[torch.Tensor] = None,
-                 overlap: bool = False, depth: int = 2):
+                 overlap: bool = False, depth: int = 2, serial_routes: bool = False):
         assert dense.device == sparse.device
         self.dense, self.sparse = dense, sparse
         self.device = dense.device
         self.canon = None if canon is None else canon.to(device=self.device, dtype=torch.int32).contiguous()
         self.overlap = overlap
+        # submit() only: both routes on ONE side stream (BM25, then dense with its full shared-memory ring) instead of
+        # side by side; the join still runs on its own stream under the next batch's routes
+        self.serial_routes = bool(serial_routes)
         self.depth = max(int(depth), 1)
         self.s_dense = torch.cuda.Stream(device=self.device) if overlap else None
         self.s_sparse = torch.cuda.Stream(device=self.device) if overlap else None
@@ -331,17 +334,22 @@ class CoarseRanker:
             raise RuntimeError("submit() needs CoarseRanker(overlap=True): the routes and the join run on own streams")
         cur = torch.cuda.current_stream(self.device)
         slot["ev_in"].record(cur)
-        for st in (self.s_dense, self.s_sparse):
+        s_sp = self.s_dense if self.serial_routes else self.s_sparse
+        for st in ((self.s_dense,) if self.serial_routes else (self.s_dense, self.s_sparse)):
             st.wait_event(slot["ev_in"])
             st.wait_event(slot["done"])          # never-recorded events do not block
             st.wait_event(slot["free"])
+        if self.serial_routes:
+            with torch.cuda.stream(s_sp):
+                bm25_topk(self.sparse, q_ptr, q_terms, k, q_group=q_group, ws=self.ws_sparse, stream=s_sp, out=s_out)
+                slot["ev_s"].record(s_sp)
         with torch.cuda.stream(self.s_dense):
             dense_topk(self.dense, queries, k, q_group=q_group, ws=self.ws_dense, stream=self.s_dense, out=d_out)
             slot["ev_d"].record(self.s_dense)
-        with torch.cuda.stream(self.s_sparse):
-            bm25_topk(self.sparse, q_ptr, q_terms, k, q_group=q_group, ws=self.ws_sparse, stream=self.s_sparse,
-                      out=s_out)
-            slot["ev_s"].record(self.s_sparse)
+        if not self.serial_routes:
+            with torch.cuda.stream(s_sp):
+                bm25_topk(self.sparse, q_ptr, q_terms, k, q_group=q_group, ws=self.ws_sparse, stream=s_sp, out=s_out)
+                slot["ev_s"].record(s_sp)
 
     def submit(self, queries: torch.Tensor, q_ptr: torch.Tensor, q_terms: torch.Tensor, k: int = 10, k_out: int = 10,
                K: int = 60, q_group: Optional[torch.Tensor] = None) -> "Ticket":

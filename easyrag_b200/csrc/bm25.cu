@@ -630,6 +630,7 @@ static int bm25_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int
 // lower bounds and the running bound tightens more slowly.  Kept (and parity-tested) as the starting point for a
 // version that refines the bounds between chunks.
 static int g_bm25_skip = 0;
+static int g_bm25_span = 4;     // ezr_bm25_set_span: ranges in the first candidate launch (then the same again, then doubling)
 static int g_bm25_plan = 1;     // ezr_bm25_set_plan: 1 = per-launch plan table (default), 0 = resolve segments inside the CTAs
 
 static bool pk_usable(const ezr_bm25_index* ix, int k) {
@@ -696,7 +697,8 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
     // around k however many ranges it spans.
     {
         ProfScope prof(EZR_PROF_BM25_CAND, st);
-        int r0 = 0, span = 4;
+        int r0 = 0, span = g_bm25_span;
+        const int first = span;
         while (r0 < ix->n_ranges) {
             int len = ix->n_ranges - r0 < span ? ix->n_ranges - r0 : span;
             if (span < kPkMaxChunk && ix->n_ranges - (r0 + len) < span / 2) len = ix->n_ranges - r0;   // no tiny last chunk
@@ -713,7 +715,7 @@ static int pk_launch(const ezr_bm25_index* ix, const int32_t* q_ptr, const int32
                 bm25_bound_kernel<<<n_queries, kBdThreads, 0, st>>>(p, c);
                 EZR_LAUNCH_CHECK();
             }
-            if (r0 > 4 && span < kPkMaxChunk) span *= 2;
+            if (r0 > first && span < kPkMaxChunk) span *= 2;
         }
     }
     {
@@ -830,6 +832,12 @@ int ezr_bm25_term_max(const int64_t* indptr, const uint32_t* post_pk, int32_t vo
 
 int ezr_bm25_set_skipping(int32_t on) {
     g_bm25_skip = on != 0;
+    return EZR_OK;
+}
+
+int ezr_bm25_set_span(int32_t first_ranges) {
+    EZR_CHECK_ARG(first_ranges >= 1 && first_ranges <= kPkMaxChunk, "bm25_set_span: %d out of [1,%d]", first_ranges, kPkMaxChunk);
+    g_bm25_span = first_ranges;
     return EZR_OK;
 }
 

@@ -143,6 +143,10 @@ int ezr_bm25_set_skipping(int32_t on);
  * results are identical). */
 int ezr_bm25_set_plan(int32_t on);
 
+/* Document ranges of the FIRST candidate launch (default 4; then the same number again, then doubling up to 32).  A
+ * tuning switch: fewer, larger launches on short shards; results are identical for every value. */
+int ezr_bm25_set_span(int32_t first_ranges);
+
 /* candidates per query the two-phase path can hold before it hands a query to the ordered kernel (0: not built) */
 int ezr_bm25_cand_capacity(void);
 

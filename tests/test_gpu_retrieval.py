@@ -224,6 +224,14 @@ def test_bm25_two_phase_equals_ordered_kernel_and_oracle():
         finally:
             _lib.check(_lib.lib().ezr_bm25_set_skipping(0))
         assert _topk_bytes(rc) == _topk_bytes(ra)
+        # the launch schedule of the ranges (first launch of 1 / 8 / 18 ranges instead of 4) never changes the result
+        for span in (1, 8, 18):
+            _lib.check(_lib.lib().ezr_bm25_set_span(span))
+            try:
+                rd = batched.bm25_topk(a, ptr, terms, k, id_base=1000)
+            finally:
+                _lib.check(_lib.lib().ezr_bm25_set_span(4))
+            assert _topk_bytes(rd) == _topk_bytes(ra), span
     _lib.lib().ezr_profile_enable(0)
     assert a.term_max is not None and int(a.term_max.max()) < (1 << 18)
     g = groups.numpy()
@@ -638,14 +646,15 @@ def test_hybrid_dense_bm25_rrf_matches_oracle(c1):
         assert f_sc[i, :f_cnt[i]].tobytes() == ref_s.tobytes()
 
 
-def test_submitted_batches_equal_joined_batches_and_host_pipeline(c1):
+@pytest.mark.parametrize("serial", [False, True])
+def test_submitted_batches_equal_joined_batches_and_host_pipeline(c1, serial):
     # batch pipelining: six different batches submitted back to back (two result slots, reused three times) must give
     # exactly what hybrid() gives for each batch on its own; then the same through HostPipeline (pinned host buffers)
     n, dim, k = c1["stats"].n_docs, 256, 10
     q = c1["queries"]
     nq = q.n
     ranker = batched.CoarseRanker(DenseIndex(_dense_case(n, dim, 1, 77, integer=True)[0], device=DEV), c1["index"],
-                                  overlap=True)
+                                  overlap=True, serial_routes=serial)
     ptr, terms = q.term_ptr.to(DEV), q.terms.to(DEV)
     qvs = [_dense_case(8, dim, nq, 100 + i, integer=True)[1].to(DEV) for i in range(6)]
     # a different BM25 batch per step too: rotate the queries (term lists of query j move to position j + i)
