@@ -41,12 +41,17 @@ constexpr int AT_TMEM_COLS = 256;
 constexpr int AT_O_COL = 128;
 constexpr float AT_RESCALE_LOG2 = 8.0f;   // rescale O only when the row maximum grows by more than 2^8
 
+constexpr int AT_MAX_STAGES = 4;
 struct AttnBarriers {
-    uint64_t q_full, q_empty;
-    uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+    uint64_t q_full[2], q_empty[2];
+    uint64_t k_full[AT_MAX_STAGES], k_empty[AT_MAX_STAGES], v_full[AT_MAX_STAGES], v_empty[AT_MAX_STAGES];
     uint64_t s_full[2], p_full[2], o_full;
     uint32_t tmem_base;
 };
+// shared-memory shape per head size: hd 64 -> two Q buffers + 4-deep K / V rings (96 KB, two CTAs per SM), so the first
+// QK^T of the NEXT work item is issued under the softmax of this item's last tile; hd 128 -> one Q buffer, 2-deep rings
+__host__ __device__ constexpr int at_qbuf(int hd) { return hd == 64 ? 2 : 1; }
+__host__ __device__ constexpr int at_stages(int hd) { return hd == 64 ? 4 : 2; }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -54,10 +59,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// plan[i] = (sequence << 8) | query block, for every 128-row query block that exists; plan_n[0] = their number.
+// plan[i] = {first token of the sequence, its length, first query row of the block, sequence} for every 128-row query
+// block that exists (fully resolved: the attention kernel's roles read ONE 16-byte entry per work item, one item
+// ahead, instead of a chain of dependent loads at every item start); plan_n[0] = their number.
 // One CTA; sequences in order, so the query blocks of a sequence are adjacent.
 __global__ void __launch_bounds__(256)
-attn_plan_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict__ plan, int32_t* __restrict__ plan_n) {
+attn_plan_kernel(const int32_t* __restrict__ cu, int n_seq, int4* __restrict__ plan, int32_t* __restrict__ plan_n) {
     __shared__ int s_warp[8];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -65,7 +72,8 @@ attn_plan_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict_
     __syncthreads();
     for (int b0 = 0; b0 < n_seq; b0 += 256) {
         const int b = b0 + tid;
-        const int nqb = b < n_seq ? (cu[b + 1] - cu[b] + AT_M - 1) / AT_M : 0;
+        const int lo_b = b < n_seq ? cu[b] : 0, len_b = b < n_seq ? cu[b + 1] - lo_b : 0;
+        const int nqb = (len_b + AT_M - 1) / AT_M;
         int inc = nqb;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -77,7 +85,7 @@ attn_plan_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict_
         int before = s_base;
         for (int w = 0; w < warp; ++w) before += s_warp[w];
         const int first = before + inc - nqb;
-        for (int j = 0; j < nqb; ++j) plan[first + j] = (b << 8) | j;
+        for (int j = 0; j < nqb; ++j) plan[first + j] = make_int4(lo_b, len_b, j * AT_M, b);
         __syncthreads();
         if (tid == 255) s_base = before + inc;
         __syncthreads();
@@ -88,16 +96,17 @@ attn_plan_kernel(const int32_t* __restrict__ cu, int n_seq, int32_t* __restrict_
 template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-               const int32_t* __restrict__ cu, const int32_t* __restrict__ plan, const int32_t* __restrict__ plan_n,
+               const int4* __restrict__ plan, const int32_t* __restrict__ plan_n,
                int n_heads, int n_kv_heads, float scale_log2, __nv_bfloat16* __restrict__ out, int64_t ldo) {
     constexpr int CH = HD / 64;                          // 64-column TMA boxes per tile
-    constexpr int Q_BYTES = CH * AT_BOX_BYTES;           // the Q tile
+    constexpr int Q_BYTES = CH * AT_BOX_BYTES;           // one Q tile
     constexpr int KV_BYTES = CH * AT_KV_BOX_BYTES;       // one K / V tile
-    constexpr int STAGES = 2;                            // K and V rings (own barriers each)
+    constexpr int STAGES = at_stages(HD);                // K and V rings (own barriers each)
+    constexpr int QBUF = at_qbuf(HD);
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* smem_q = smem;
-    unsigned char* smem_k = smem_q + Q_BYTES;
+    unsigned char* smem_k = smem_q + QBUF * Q_BYTES;
     unsigned char* smem_v = smem_k + STAGES * KV_BYTES;
     AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_v + STAGES * KV_BYTES);
 
@@ -109,15 +118,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_q);
         ptx::prefetch_tensormap(&map_kv);
-        ptx::mbar_init(&bars->q_full, 1);
-        ptx::mbar_init(&bars->q_empty, 1);
         for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&bars->q_full[i], 1);
+            ptx::mbar_init(&bars->q_empty[i], 1);
+            ptx::mbar_init(&bars->s_full[i], 1);
+            ptx::mbar_init(&bars->p_full[i], 4);
+        }
+        for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&bars->k_full[i], 1);
             ptx::mbar_init(&bars->k_empty[i], 1);
             ptx::mbar_init(&bars->v_full[i], 1);
             ptx::mbar_init(&bars->v_empty[i], 1);
-            ptx::mbar_init(&bars->s_full[i], 1);
-            ptx::mbar_init(&bars->p_full[i], 4);
         }
         ptx::mbar_init(&bars->o_full, 1);
         ptx::fence_barrier_init();
@@ -127,23 +138,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    // every role walks the same items w = blockIdx.x, + gridDim.x, ...; the plan entry of the NEXT item is requested at
+    // the top of each iteration, so no role ever waits for it
+    auto plan_at = [&](int w) { return w < n_work ? __ldg(plan + w % n_pairs) : make_int4(0, 0, 0, 0); };
 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer: runs ahead of the consumers, across work items ----------------
             int jt = 0;                                   // K/V tiles issued so far (ring position)
             int it = 0;                                   // items started
+            int4 cur = plan_at(blockIdx.x);
             for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                const int h = w / n_pairs, pe = plan[w % n_pairs];
-                const int b = pe >> 8, q0 = (pe & 0xff) * AT_M;
-                const int lo = cu[b], len = cu[b + 1] - lo;
+                const int4 nxt = plan_at(w + gridDim.x);
+                const int h = w / n_pairs;
+                const int lo = cur.x, len = cur.y, q0 = cur.z;
+                cur = nxt;
                 const int kvh = h / kv_group;
                 const int col_q = h * HD, col_k = (n_heads + kvh) * HD, col_v = (n_heads + n_kv_heads + kvh) * HD;
                 const int n_kt = (len + AT_N - 1) / AT_N;
-                ptx::mbar_wait(&bars->q_empty, ((uint32_t)it & 1u) ^ 1u);      // the previous item's QK^T MMAs are done
-                ptx::mbar_expect_tx(&bars->q_full, Q_BYTES);
+                const int qb = it % QBUF;
+                ptx::mbar_wait(&bars->q_empty[qb], ((uint32_t)(it / QBUF) & 1u) ^ 1u);   // the QK^T MMAs that read this buffer are done
+                ptx::mbar_expect_tx(&bars->q_full[qb], Q_BYTES);
                 for (int c = 0; c < CH; ++c)
-                    ptx::tma_load_2d(smem_q + c * AT_BOX_BYTES, &map_q, &bars->q_full, col_q + c * 64, lo + q0);
+                    ptx::tma_load_2d(smem_q + qb * Q_BYTES + c * AT_BOX_BYTES, &map_q, &bars->q_full[qb], col_q + c * 64, lo + q0);
                 for (int j = 0; j < n_kt; ++j, ++jt) {
                     const int s = jt % STAGES;
                     const uint32_t ph = (uint32_t)(jt / STAGES) & 1u;
@@ -162,13 +179,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     } else if (warp == 1) {
         // ---------------- MMA issuer (warp-uniform loops, one elected lane issues) ----------------
         constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(AT_M, HD) | ptx::kIdescBMajorMN;
-        const uint32_t q_addr = ptx::smem_u32(smem_q);
         const uint32_t tm_o = tmem_base + AT_O_COL;
-        // S_j = Q K_j^T into S buffer (jt & 1); jt counts this CTA's tiles across items
-        auto issue_qk = [&](int jt, int valid, bool last) {
+        // S_j = Q K_j^T into S buffer (jt & 1); jt counts this CTA's tiles across items; qb = the item's Q buffer
+        auto issue_qk = [&](int jt, int valid, bool last, int qb) {
             const int s = jt % STAGES;
             const uint32_t ph = (uint32_t)(jt / STAGES) & 1u;
             const int n_j = valid >= AT_N ? AT_N : ((valid + 15) & ~15);         // keys of this tile, multiple of 16
+            const uint32_t q_addr = ptx::smem_u32(smem_q + qb * Q_BYTES);
             const uint32_t k_addr = ptx::smem_u32(smem_k + s * KV_BYTES);
             ptx::mbar_wait(&bars->k_full[s], ph);
             ptx::tc_fence_after();
@@ -183,22 +200,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                                      idesc_qk, (uint32_t)(kk != 0));
                 }
                 ptx::umma_commit(&bars->k_empty[s]);
-                if (last) ptx::umma_commit(&bars->q_empty);                      // the Q tile may be overwritten
+                if (last) ptx::umma_commit(&bars->q_empty[qb]);                  // the Q tile may be overwritten
                 ptx::umma_commit(&bars->s_full[jt & 1]);
             }
             __syncwarp();
         };
         int jt = 0, it = 0;
+        bool pre = false;                                 // this item's first QK^T was issued during the previous item
+        int4 cur = plan_at(blockIdx.x);
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-            const int pe = plan[w % n_pairs];
-            const int b = pe >> 8;
-            const int len = cu[b + 1] - cu[b];
+            const int4 nxt = plan_at(w + gridDim.x);
+            const bool has_next = w + gridDim.x < n_work;
+            const int len = cur.y;
+            cur = nxt;
             const int n_kt = (len + AT_N - 1) / AT_N;
-            ptx::mbar_wait(&bars->q_full, (uint32_t)it & 1u);
-            issue_qk(jt, len, n_kt == 1);
+            const int qb = it % QBUF;
+            if (!pre) {
+                ptx::mbar_wait(&bars->q_full[qb], (uint32_t)(it / QBUF) & 1u);
+                issue_qk(jt, len, n_kt == 1, qb);
+            }
+            pre = false;
             for (int j = 0; j < n_kt; ++j, ++jt) {
-                // the next tile's scores first: they do not depend on this tile's softmax (other S buffer)
-                if (j + 1 < n_kt) issue_qk(jt + 1, len - (j + 1) * AT_N, j + 2 == n_kt);
+                // the next tile's scores first: they do not depend on this tile's softmax (other S buffer).  After the
+                // item's last tile that is the FIRST tile of the next item (its Q sits in the other Q buffer).
+                if (j + 1 < n_kt) {
+                    issue_qk(jt + 1, len - (j + 1) * AT_N, j + 2 == n_kt, qb);
+                } else if (QBUF == 2 && has_next) {
+                    const int len2 = nxt.y;
+                    const int qb2 = (it + 1) % QBUF;
+                    ptx::mbar_wait(&bars->q_full[qb2], (uint32_t)((it + 1) / QBUF) & 1u);
+                    issue_qk(jt + 1, len2, len2 <= AT_N, qb2);
+                    pre = true;
+                }
                 const int s = jt % STAGES;
                 const uint32_t ph = (uint32_t)(jt / STAGES) & 1u;
                 const int valid = len - j * AT_N;
@@ -226,10 +259,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t o_col = (uint32_t)AT_O_COL;
         int jt = 0, it = 0;
+        int4 cur = plan_at(blockIdx.x);
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-            const int h = w / n_pairs, pe = plan[w % n_pairs];
-            const int b = pe >> 8, q0 = (pe & 0xff) * AT_M;
-            const int lo = cu[b], len = cu[b + 1] - lo;
+            const int4 nxt = plan_at(w + gridDim.x);
+            const int h = w / n_pairs;
+            const int lo = cur.x, len = cur.y, q0 = cur.z;
+            cur = nxt;
             const int n_kt = (len + AT_N - 1) / AT_N;
             float m_run = -INFINITY, l_run = 0.f;
             for (int j = 0; j < n_kt; ++j, ++jt) {
@@ -249,9 +284,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         r1[i] = 32 + i < valid ? r1[i] : 0xff800000u;
                     }
                 }
-                float mx = -INFINITY;
+                // row maximum: four independent chains (one chain of 32 dependent FMNMX is ~130 cycles of pure latency
+                // in front of the exponentials)
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+                for (int i = 0; i < 32; ++i)
+                    mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 float m_new = fmaxf(m_run, mx);
                 const bool grow = (m_new - m_run) * scale_log2 > AT_RESCALE_LOG2;   // true on the first tile (m_run = -inf)
                 if (!grow) m_new = m_run;
@@ -346,7 +385,7 @@ int attn_bidir_legacy(const void* qkv, int64_t ld, const int32_t* cu_seqlens, in
 static int g_attn_kernel = 0;     // ezr_attn_set_kernel: 0 = tcgen05 (default), 1 = legacy mma.sync kernel (cross-checks)
 static thread_local const char* g_attn_last = "none";
 
-// plan buffer (query-block list) of the calling thread's device, grown on demand; (n_seq * 256 + 1) ints at most
+// plan buffer (query-block list) of the calling thread's device, grown on demand
 static thread_local int32_t* g_plan = nullptr;
 static thread_local size_t g_plan_cap = 0;
 static thread_local int g_plan_dev = -1;
@@ -354,7 +393,8 @@ static thread_local int g_plan_dev = -1;
 template <int HD>
 static int attn_tc_launch(const CUtensorMap& map_q, const CUtensorMap& map_kv, const int32_t* cu, int n_seq, int max_len,
                           int n_heads, int n_kv_heads, float scale_log2, __nv_bfloat16* out, int64_t ldo, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)(HD / 64) * (AT_BOX_BYTES + 4 * AT_KV_BOX_BYTES) + sizeof(AttnBarriers) + 64;
+    const size_t smem = 1024 + (size_t)(HD / 64) * (at_qbuf(HD) * AT_BOX_BYTES + 2 * at_stages(HD) * AT_KV_BOX_BYTES) +
+                        sizeof(AttnBarriers) + 64;
     static bool attr_done = false;
     if (!attr_done) {
         EZR_CUDA(cudaFuncSetAttribute(attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -363,8 +403,7 @@ static int attn_tc_launch(const CUtensorMap& map_q, const CUtensorMap& map_kv, c
         attr_done = true;
     }
     const int max_qb = (max_len + AT_M - 1) / AT_M;
-    EZR_CHECK_ARG(max_qb <= 256, "attn: sequences longer than %d tokens are not supported", 256 * AT_M);
-    const size_t need = (size_t)n_seq * max_qb + 1;
+    const size_t need = ((size_t)n_seq * max_qb + 1) * 4;          // ints: 4 for the count (keeps the entries 16-byte aligned) + 4 per entry
     int dev = 0;
     EZR_CUDA(cudaGetDevice(&dev));
     if (need > g_plan_cap || dev != g_plan_dev) {         // first call / larger batch / other device: (re)allocate
@@ -376,14 +415,13 @@ static int attn_tc_launch(const CUtensorMap& map_q, const CUtensorMap& map_kv, c
         g_plan_cap = need * 2;
     }
     int32_t* plan_n = g_plan;
-    int32_t* plan = g_plan + 1;
+    int4* plan = reinterpret_cast<int4*>(g_plan + 4);
     ProfScope prof(EZR_PROF_ENC_ATTN, st);
     attn_plan_kernel<<<1, 256, 0, st>>>(cu, n_seq, plan, plan_n);
     EZR_LAUNCH_CHECK();
     const long long upper = (long long)n_seq * max_qb * n_heads;      // work items at most
     const int grid = (int)(upper < 2ll * sm_count() ? upper : 2ll * sm_count());
-    attn_tc_kernel<HD><<<grid, AT_THREADS, smem, st>>>(map_q, map_kv, cu, plan, plan_n, n_heads, n_kv_heads, scale_log2, out,
-                                                       ldo);
+    attn_tc_kernel<HD><<<grid, AT_THREADS, smem, st>>>(map_q, map_kv, plan, plan_n, n_heads, n_kv_heads, scale_log2, out, ldo);
     EZR_LAUNCH_CHECK();
     return EZR_OK;
 }
