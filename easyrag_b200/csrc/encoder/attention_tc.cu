@@ -48,10 +48,15 @@ struct AttnBarriers {
     uint64_t s_full[2], p_full[2], o_full;
     uint32_t tmem_base;
 };
-// shared-memory shape per head size: hd 64 -> two Q buffers + 4-deep K / V rings (96 KB, two CTAs per SM), so the first
-// QK^T of the NEXT work item is issued under the softmax of this item's last tile; hd 128 -> one Q buffer, 2-deep rings
-__host__ __device__ constexpr int at_qbuf(int hd) { return hd == 64 ? 2 : 1; }
-__host__ __device__ constexpr int at_stages(int hd) { return hd == 64 ? 4 : 2; }
+// shared-memory shape: one Q buffer and 2-deep K / V rings (48 KB at hd 64, two CTAs per SM).  With EZR_ATTN_DEEP=1, hd 64
+// gets two Q buffers + 4-deep rings (96 KB) and the first QK^T of the NEXT work item is issued under the softmax of this
+// item's last tile -- measured on one box (session 20): 414-417 vs 416-418 TFLOP/s at L = 512, 290 vs 295 on ragged
+// batches: the two CTAs per SM already cover the item boundaries, so the switch is off.
+#ifndef EZR_ATTN_DEEP
+#define EZR_ATTN_DEEP 0          // tuning switch (variant builds): 1 = at hd 64 two Q buffers + 4-deep rings (see below); measured equal
+#endif
+__host__ __device__ constexpr int at_qbuf(int hd) { return (EZR_ATTN_DEEP && hd == 64) ? 2 : 1; }
+__host__ __device__ constexpr int at_stages(int hd) { return (EZR_ATTN_DEEP && hd == 64) ? 4 : 2; }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
