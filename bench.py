@@ -11,7 +11,9 @@ scaling.  One step = one pass of the hot path over the whole batch of synthetic 
 ``--queries 64`` is the HBM-bound small-batch regime of SURVEY.md 8(d), configs[4] adds ``--rows 4000000 --dim 1024``).
 
   value : whole-job queries/s with query vectors + term ids resident in HBM when the timed region starts; the
-          two routes run on two streams (``--overlap 1``, the product default).
+          two routes run on two streams (``--overlap 1``, the product default) and the K timed steps are submitted
+          back to back (``--pipeline 1``: the join of step i -- all-gather, merges, RRF -- runs under the routes of
+          step i+1; the bracket closes after ``join()``.  ``--pipeline 0`` joins every step to the caller's stream).
   e2e   : same metric through the public host-buffer API (``batched.HostPipeline``): pinned HOST inputs, H2D of
           the queries / term ids and D2H of the fused (id, score) lists inside the timed region, every step.
   roofline : dominant kernel, algorithmic FLOPs or bytes / CUDA-event duration on its launch stream, taken from
